@@ -1,0 +1,118 @@
+// Small fp32 vector helpers for the device code.
+//
+// Numerics contract (DESIGN.md "Numerics"): this translation unit is compiled with `-fmad=false`, IEEE division and
+// square root (nvcc defaults -prec-div=true -prec-sqrt=true), so that every +,-,*,/ and sqrt below rounds exactly like
+// the reference's x86 build without FMA contraction.  Sums are written in the association order of the reference's
+// loops (util/vector.h:138-147, 196-205: ((x*x + y*y) + z*z)).
+#ifndef PTB_DEVICE_MATH_CUH
+#define PTB_DEVICE_MATH_CUH
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#define PTB_DEV __device__ __forceinline__
+
+namespace ptb {
+
+    constexpr float kFloatMax = 3.402823466e+38F;
+    constexpr float kPi = 3.14159274101257324219F;    // static_cast<float>(M_PI)
+    constexpr float kTwoPi = 6.28318548202514648438F; // 2.0F * kPi (exact doubling)
+
+    struct V3 {
+        float x, y, z;
+    };
+
+    struct V4 {
+        float x, y, z, w;
+    };
+
+    PTB_DEV V3 mk3(float x, float y, float z) {
+        return V3{x, y, z};
+    }
+
+    PTB_DEV V3 operator+(V3 a, V3 b) {
+        return V3{a.x + b.x, a.y + b.y, a.z + b.z};
+    }
+
+    PTB_DEV V3 operator-(V3 a, V3 b) {
+        return V3{a.x - b.x, a.y - b.y, a.z - b.z};
+    }
+
+    PTB_DEV V3 operator-(V3 a) {
+        return V3{-a.x, -a.y, -a.z};
+    }
+
+    PTB_DEV V3 operator*(V3 a, float s) {
+        return V3{a.x * s, a.y * s, a.z * s};
+    }
+
+    PTB_DEV float dot(V3 a, V3 b) {
+        return (a.x * b.x + a.y * b.y) + a.z * b.z;
+    }
+
+    PTB_DEV V3 cross(V3 a, V3 b) {
+        return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+    }
+
+    PTB_DEV float length2(V3 a) {
+        return (a.x * a.x + a.y * a.y) + a.z * a.z;
+    }
+
+    PTB_DEV float length(V3 a) {
+        return sqrtf(length2(a));
+    }
+
+    // rt_vector::normalize (util/vector.h:161-167): multiply by the reciprocal of the length
+    PTB_DEV V3 normalize(V3 a) {
+        const float inv = 1.0F / length(a);
+        return a * inv;
+    }
+
+    // reflect (util/vector.h:250-255): v - n * 2 * d, evaluated as ((n * 2) * d)
+    PTB_DEV V3 reflect(V3 v, V3 n) {
+        const float d = dot(v, n);
+        return v - (n * 2.0F) * d;
+    }
+
+    PTB_DEV V4 operator+(V4 a, V4 b) {
+        return V4{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+    }
+
+    PTB_DEV V4 operator*(V4 a, V4 b) {
+        return V4{a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w};
+    }
+
+    PTB_DEV V4 operator*(V4 a, float s) {
+        return V4{a.x * s, a.y * s, a.z * s, a.w * s};
+    }
+
+    PTB_DEV V4 operator/(V4 a, float s) {
+        return V4{a.x / s, a.y / s, a.z / s, a.w / s};
+    }
+
+    PTB_DEV V4 ld4(const float4 *p) {
+        const float4 v = __ldg(p);
+        return V4{v.x, v.y, v.z, v.w};
+    }
+
+    PTB_DEV float4 f4(V4 v) {
+        return make_float4(v.x, v.y, v.z, v.w);
+    }
+
+    PTB_DEV V4 v4(float4 v) {
+        return V4{v.x, v.y, v.z, v.w};
+    }
+
+    // std::min / std::max select semantics (first argument wins ties and NaN comparisons)
+    PTB_DEV float stdmin(float a, float b) {
+        return b < a ? b : a;
+    }
+
+    PTB_DEV float stdmax(float a, float b) {
+        return a < b ? b : a;
+    }
+
+}
+
+#endif

@@ -1,0 +1,787 @@
+// Wavefront path-tracing kernels (sm_100a).
+//
+// One bounce iteration of impl::getSample (reference src/worker.cpp:44-138) for a whole pool of paths is five
+// launches over structure-of-arrays path state in HBM:
+//
+//   generate        primary rays for a batch of (pixel, sample) pairs            Camera::shootRay
+//   trace_closest   closest hit for every queued path                            Scene::getIntersection
+//   shade           emission, Russian roulette, light sampling -> shadow slots,  getSample body, sampleLights,
+//                   BSDF sampling -> next ray                                     BSDF::propagateRay/getSpectrum
+//   trace_shadow    visibility of the queued shadow candidates                   the shadow query, worker.cpp:80-86
+//   accumulate      adds the visible next-event contributions IN LIGHT ORDER, retires finished paths into the
+//                   per-sample buffer and compacts survivors into the next queue (warp-aggregated atomics)
+//
+// and, once all samples of a pixel group exist,
+//
+//   resolve         processItem's per-pixel statistics (worker.cpp:158-317) run sequentially over the samples
+//
+// Queues hold path indices; their lengths live in device memory so no launch depends on a host round trip.
+#ifndef PTB_KERNELS_CUH
+#define PTB_KERNELS_CUH
+
+#include "shading.cuh"
+#include "traverse.cuh"
+
+namespace ptb {
+
+    constexpr int kBlock = 128;
+
+    enum CounterSlot : int {
+        kCountQueueA = 0,
+        kCountQueueB = 1,
+        kCountShadow = 2,
+        kCountFetchClosest = 3,
+        kCountFetchShadow = 4,
+        kCountSkippedShadows = 5,
+        kCountVertices = 6,
+        kCounterSlots = 8
+    };
+
+    constexpr uint32_t kFlagTerminated = 1U;
+    constexpr uint32_t kFlagXorshift = 2U;
+
+    // Structure-of-arrays path pool.  Every array has `capacity` entries (shadow arrays capacity * shadow_stride).
+    struct PathPool {
+        float4 *ray_o;       // origin xyz
+        float4 *ray_d;       // direction xyz
+        float2 *hit;         // (t, slot bits)
+        float4 *throughput;  // sample_spectrum
+        float4 *radiance;    // out_spectrum
+        double *divisor;     // sample_divisor
+        double *bounce_pd;   // sample_bounce_pd
+        float *contribution; // contribution_unweighted
+        uint32_t *state;     // path_length << 8 | flags
+        uint64_t *rng;       // xorshift state or counter key
+        uint32_t *dest;      // index into the per-sample buffer
+        uint32_t *shadow_count; // candidates stored for the current vertex
+        float4 *shadow_o;    // (origin, limit)
+        float4 *shadow_d;    // (direction, 0)
+        float4 *shadow_c;    // (contribution rgb, visible flag)
+        uint32_t shadow_stride;
+        uint32_t capacity;
+    };
+
+    struct RenderParams {
+        ptb_camera camera;
+        int32_t image_width;
+        int32_t image_height;
+        float epsilon;
+        int32_t max_depth;
+        uint32_t rng_xorshift;
+        uint32_t any_hit_shadows;
+        uint32_t skip_null_shadows;
+        uint64_t seed;
+    };
+
+    PTB_DEV uint32_t laneId() {
+        return threadIdx.x & 31U;
+    }
+
+    // Appends one element per participating lane with a single atomic per warp.
+    // Must be reached by all 32 lanes of the warp.
+    PTB_DEV uint32_t warpAppend(uint32_t *counter, bool participate) {
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFU, participate);
+        if(!participate) {
+            return 0U;
+        }
+        const uint32_t leader = __ffs(mask) - 1U;
+        uint32_t base = 0U;
+        if(laneId() == leader) {
+            base = atomicAdd(counter, __popc(mask));
+        }
+        base = __shfl_sync(mask, base, leader);
+        return base + __popc(mask & ((1U << laneId()) - 1U));
+    }
+
+    PTB_DEV void loadPath(const PathPool &pool, uint32_t i, PathRegs &p, uint32_t &flags) {
+        const float4 o = pool.ray_o[i];
+        const float4 d = pool.ray_d[i];
+        p.ray_o = mk3(o.x, o.y, o.z);
+        p.ray_d = mk3(d.x, d.y, d.z);
+        p.throughput = v4(pool.throughput[i]);
+        p.radiance = v4(pool.radiance[i]);
+        p.divisor = pool.divisor[i];
+        p.bounce_pd = pool.bounce_pd[i];
+        p.contribution_unweighted = pool.contribution[i];
+        const uint32_t st = pool.state[i];
+        p.path_length = static_cast<int>(st >> 8);
+        flags = st & 0xFFU;
+        p.rng.state = pool.rng[i];
+        p.rng.counter = 0U;
+        p.rng.xorshift = (flags & kFlagXorshift) != 0U ? 1U : 0U;
+    }
+
+    PTB_DEV void storePath(const PathPool &pool, uint32_t i, const PathRegs &p, uint32_t flags) {
+        pool.ray_o[i] = make_float4(p.ray_o.x, p.ray_o.y, p.ray_o.z, 0.0F);
+        pool.ray_d[i] = make_float4(p.ray_d.x, p.ray_d.y, p.ray_d.z, 0.0F);
+        pool.throughput[i] = f4(p.throughput);
+        pool.radiance[i] = f4(p.radiance);
+        pool.divisor[i] = p.divisor;
+        pool.bounce_pd[i] = p.bounce_pd;
+        pool.contribution[i] = p.contribution_unweighted;
+        pool.state[i] = (static_cast<uint32_t>(p.path_length) << 8) | (flags & 0xFFU);
+        pool.rng[i] = p.rng.state;
+    }
+
+    // ------------------------------------------------------------------------------------------------ generate
+
+    // Batch element i is global work item g = first + i of the pixel group: sample = g / n_pixels,
+    // pixel = pixel_list[g % n_pixels] (x | y << 16), destination = sample * n_pixels + pixel index.
+    __global__ void __launch_bounds__(kBlock) generateKernel(PathPool pool, RenderParams params, const uint32_t *__restrict__ pixel_list, uint32_t n_pixels,
+                                                             uint64_t first, uint32_t count, uint32_t *__restrict__ queue, uint32_t *__restrict__ counters,
+                                                             int queue_slot) {
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if(i == 0U) {
+            counters[queue_slot] = count;
+        }
+        if(i >= count) {
+            return;
+        }
+        const uint64_t g = first + i;
+        const uint32_t sample = static_cast<uint32_t>(g / n_pixels);
+        const uint32_t q = static_cast<uint32_t>(g % n_pixels);
+        const uint32_t packed = pixel_list[q];
+        const int px = static_cast<int>(packed & 0xFFFFU);
+        const int py = static_cast<int>(packed >> 16);
+
+        PathRegs p;
+        initPath(p);
+        const uint64_t key = counterKey(params.seed, static_cast<uint32_t>(px), static_cast<uint32_t>(py), sample);
+        p.rng.xorshift = params.rng_xorshift;
+        p.rng.counter = 0U;
+        p.rng.state = params.rng_xorshift != 0U ? xorshiftSeed(key) : key;
+
+        float x_camera;
+        float y_camera;
+        pixelToCamera(px, py, params.image_width, params.image_height, x_camera, y_camera);
+        shootRay(params.camera, x_camera, y_camera, 1.0F / static_cast<float>(params.image_width), 1.0F / static_cast<float>(params.image_height), p.rng,
+                 p.ray_o, p.ray_d);
+
+        storePath(pool, i, p, params.rng_xorshift != 0U ? kFlagXorshift : 0U);
+        pool.dest[i] = static_cast<uint32_t>(g);
+        queue[i] = i;
+    }
+
+    // Validation batch: explicit (pixel, seed) pairs, RandomEngine(seed) per sample, destination = i
+    __global__ void __launch_bounds__(kBlock) generateSamplesKernel(PathPool pool, RenderParams params, const int32_t *__restrict__ pixels,
+                                                                    const uint64_t *__restrict__ seeds, uint64_t first, uint32_t count,
+                                                                    uint32_t *__restrict__ queue, uint32_t *__restrict__ counters, int queue_slot) {
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if(i == 0U) {
+            counters[queue_slot] = count;
+        }
+        if(i >= count) {
+            return;
+        }
+        const uint64_t g = first + i;
+        const int px = pixels[2 * g];
+        const int py = pixels[2 * g + 1];
+
+        PathRegs p;
+        initPath(p);
+        p.rng.xorshift = params.rng_xorshift;
+        p.rng.counter = 0U;
+        p.rng.state = params.rng_xorshift != 0U ? xorshiftSeed(seeds[g]) : seeds[g];
+
+        float x_camera;
+        float y_camera;
+        pixelToCamera(px, py, params.image_width, params.image_height, x_camera, y_camera);
+        shootRay(params.camera, x_camera, y_camera, 1.0F / static_cast<float>(params.image_width), 1.0F / static_cast<float>(params.image_height), p.rng,
+                 p.ray_o, p.ray_d);
+
+        storePath(pool, i, p, params.rng_xorshift != 0U ? kFlagXorshift : 0U);
+        pool.dest[i] = i;
+        queue[i] = i;
+    }
+
+    // ------------------------------------------------------------------------------------------------ trace
+
+    // Persistent warps: each warp claims 32 queue entries at a time from a device-side cursor until the queue is
+    // drained, so a warp stuck on one long traversal does not strand the rest of a statically assigned range.
+    template<bool COUNT>
+    __global__ void __launch_bounds__(kBlock) traceClosestKernel(DeviceScene scene, PathPool pool, const uint32_t *__restrict__ queue,
+                                                                 uint32_t *__restrict__ counters, int queue_slot, VisitCounters *visits) {
+        const uint32_t count = counters[queue_slot];
+        for(;;) {
+            uint32_t base = 0U;
+            if(laneId() == 0U) {
+                base = atomicAdd(&counters[kCountFetchClosest], 32U);
+            }
+            base = __shfl_sync(0xFFFFFFFFU, base, 0);
+            if(base >= count) {
+                return;
+            }
+            const uint32_t k = base + laneId();
+            if(k < count) {
+                const uint32_t i = queue[k];
+                const float4 o = pool.ray_o[i];
+                const float4 d = pool.ray_d[i];
+                const RayInv r = makeRay(mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z));
+                const Hit h = traverse<false, COUNT>(scene, r, 0.0F, visits);
+                pool.hit[i] = make_float2(h.t, __int_as_float(h.slot));
+            }
+        }
+    }
+
+    template<bool COUNT>
+    __global__ void __launch_bounds__(kBlock) traceShadowKernel(DeviceScene scene, PathPool pool, const uint32_t *__restrict__ shadow_queue,
+                                                                uint32_t *__restrict__ counters, uint32_t any_hit, VisitCounters *visits) {
+        const uint32_t count = counters[kCountShadow];
+        for(;;) {
+            uint32_t base = 0U;
+            if(laneId() == 0U) {
+                base = atomicAdd(&counters[kCountFetchShadow], 32U);
+            }
+            base = __shfl_sync(0xFFFFFFFFU, base, 0);
+            if(base >= count) {
+                return;
+            }
+            const uint32_t k = base + laneId();
+            if(k < count) {
+                const uint32_t slot = shadow_queue[k];
+                const float4 o = pool.shadow_o[slot];
+                const float4 d = pool.shadow_d[slot];
+                const RayInv r = makeRay(mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z));
+                bool visible;
+                if(any_hit != 0U) {
+                    const Hit h = traverse<true, COUNT>(scene, r, o.w, visits);
+                    visible = h.slot < 0;
+                }
+                else {
+                    // the reference's full closest-hit query (worker.cpp:84-86)
+                    const Hit h = traverse<false, COUNT>(scene, r, 0.0F, visits);
+                    visible = h.t < 0.0F || h.t >= o.w;
+                }
+                pool.shadow_c[slot].w = visible ? 1.0F : 0.0F;
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------------ shade
+
+    __global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene scene, PathPool pool, RenderParams params, const uint32_t *__restrict__ queue,
+                                                          uint32_t *__restrict__ counters, int queue_slot, uint32_t *__restrict__ shadow_queue) {
+        const uint32_t count = counters[queue_slot];
+        const uint32_t stride = gridDim.x * blockDim.x;
+        // whole warps iterate together so that the warp-aggregated appends see converged lanes
+        const uint32_t rounded = (count + 31U) & ~31U;
+        for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < rounded; k += stride) {
+            const bool active = k < count;
+            uint32_t i = 0U;
+            PathRegs p;
+            uint32_t flags = 0U;
+            bool hit_surface = false;
+            float t = -1.0F;
+            uint32_t slot = 0U;
+            if(active) {
+                i = queue[k];
+                loadPath(pool, i, p, flags);
+                const float2 h = pool.hit[i];
+                t = h.x;
+                slot = static_cast<uint32_t>(__float_as_int(h.y));
+                hit_surface = !(t < 0.0F);
+            }
+
+            uint32_t n_shadow = 0U;
+            uint32_t n_skipped = 0U;
+            bool continues = false;
+            const uint32_t shadow_base = i * pool.shadow_stride;
+            if(hit_surface) {
+                continues = shadeVertex(scene, params.epsilon, params.max_depth, p, t, slot, [&](const ShadowCandidate &c, bool is_null) {
+                    // candidates without weight are traced only to reproduce the reference's ray count
+                    if(is_null && params.skip_null_shadows != 0U) {
+                        n_skipped++;
+                        return;
+                    }
+                    if(n_shadow < pool.shadow_stride) {
+                        const uint32_t s = shadow_base + n_shadow;
+                        pool.shadow_o[s] = make_float4(c.o.x, c.o.y, c.o.z, c.limit);
+                        pool.shadow_d[s] = make_float4(c.d.x, c.d.y, c.d.z, 0.0F);
+                        pool.shadow_c[s] = make_float4(c.contribution.x, c.contribution.y, c.contribution.z, 0.0F);
+                        n_shadow++;
+                    }
+                });
+            }
+
+            if(active) {
+                if(!continues) {
+                    flags |= kFlagTerminated;
+                }
+                storePath(pool, i, p, flags);
+                pool.shadow_count[i] = n_shadow;
+            }
+
+            for(uint32_t j = 0U; j < pool.shadow_stride; j++) {
+                const bool has = active && j < n_shadow;
+                if(__ballot_sync(0xFFFFFFFFU, has) == 0U) {
+                    break;
+                }
+                const uint32_t at = warpAppend(&counters[kCountShadow], has);
+                if(has) {
+                    shadow_queue[at] = shadow_base + j;
+                }
+            }
+
+            // statistics: one atomic per warp
+            const uint32_t hit_mask = __ballot_sync(0xFFFFFFFFU, active && hit_surface);
+            uint32_t skipped = n_skipped;
+            for(int offset = 16; offset > 0; offset >>= 1) {
+                skipped += __shfl_xor_sync(0xFFFFFFFFU, skipped, offset);
+            }
+            if(laneId() == 0U) {
+                if(hit_mask != 0U) {
+                    atomicAdd(&counters[kCountVertices], static_cast<uint32_t>(__popc(hit_mask)));
+                }
+                if(skipped != 0U) {
+                    atomicAdd(&counters[kCountSkippedShadows], skipped);
+                }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------------ accumulate
+
+    __global__ void __launch_bounds__(kBlock) accumulateKernel(PathPool pool, const uint32_t *__restrict__ queue, uint32_t *__restrict__ counters,
+                                                               int queue_slot, uint32_t *__restrict__ next_queue, int next_slot, float4 *__restrict__ samples) {
+        const uint32_t count = counters[queue_slot];
+        const uint32_t stride = gridDim.x * blockDim.x;
+        const uint32_t rounded = (count + 31U) & ~31U;
+        for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < rounded; k += stride) {
+            const bool active = k < count;
+            bool survives = false;
+            uint32_t i = 0U;
+            if(active) {
+                i = queue[k];
+                const uint32_t n_shadow = pool.shadow_count[i];
+                float4 radiance = pool.radiance[i];
+                if(n_shadow > 0U) {
+                    const uint32_t base = i * pool.shadow_stride;
+                    for(uint32_t j = 0U; j < n_shadow; j++) {
+                        const float4 c = pool.shadow_c[base + j];
+                        if(c.w != 0.0F) {
+                            radiance.x = radiance.x + c.x;
+                            radiance.y = radiance.y + c.y;
+                            radiance.z = radiance.z + c.z;
+                        }
+                    }
+                    pool.radiance[i] = radiance;
+                    pool.shadow_count[i] = 0U;
+                }
+                const uint32_t st = pool.state[i];
+                if((st & kFlagTerminated) != 0U) {
+                    // out_color[3] = sample_collected ? 1 : 0 (worker.cpp:141-143)
+                    const bool collected = (st >> 8) > 0U;
+                    samples[pool.dest[i]] = make_float4(radiance.x, radiance.y, radiance.z, collected ? 1.0F : 0.0F);
+                }
+                else {
+                    survives = true;
+                }
+            }
+            const uint32_t at = warpAppend(&counters[next_slot], survives);
+            if(survives) {
+                next_queue[at] = i;
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------------ resolve
+
+    struct ResolveParams {
+        int32_t min_sample_count;
+        int32_t max_sample_count;
+        uint32_t n_pixels; // pixels in the group; samples[s * n_pixels + q]
+        int32_t rect_x0;
+        int32_t rect_y0;
+        int32_t rect_w;
+    };
+
+    constexpr int kMaxCandidates = 8;
+
+    PTB_DEV V4 sub4(V4 a, V4 b) {
+        return V4{a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w};
+    }
+
+    // processItem's per-pixel loop (worker.cpp:172-319) over the already-computed samples of one pixel.
+    __global__ void __launch_bounds__(kBlock) resolveKernel(ResolveParams rp, const float4 *__restrict__ samples, const uint32_t *__restrict__ pixel_list,
+                                                            float4 *__restrict__ out) {
+        const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+        if(q >= rp.n_pixels) {
+            return;
+        }
+
+        const int min_samples = rp.min_sample_count;
+        const int max_samples = rp.max_sample_count;
+        const int stats_sample_count = min(max(min_samples / 4, 1), 64);
+        const int candidate_batch_count = max(max(min_samples, max_samples / 4) / stats_sample_count, 2);
+        const int check_sample_count = min(max(max(min_samples / 2, (max_samples - min_samples) / 8), max(8, stats_sample_count)), 1024) / stats_sample_count;
+
+        const V4 zero = V4{0.0F, 0.0F, 0.0F, 0.0F};
+        V4 pixel_value = zero;
+        int collected_sample_count = 0;
+        V4 contribution_mean = zero;
+        V4 contribution_m2 = zero;
+        int contribution_count = 0;
+        int stats_sample_index = 0;
+        V4 sample_aggregate = zero;
+
+        V4 candidate_means[kMaxCandidates];
+        V4 candidate_m2s[kMaxCandidates];
+        int candidate_counts[kMaxCandidates];
+        int n_candidates = 0;
+
+        V4 candidate_mean = zero;
+        V4 candidate_m2 = zero;
+        int candidate_count = 0;
+
+        int remaining_checks = check_sample_count;
+        bool accepted_candidate = false;
+
+        for(int pixel_sample = 0; pixel_sample < max_samples; pixel_sample++) {
+            const float4 raw = samples[static_cast<size_t>(pixel_sample) * rp.n_pixels + q];
+            if(raw.w == 0.0F) {
+                continue; // sample not collected: the primary ray missed everything
+            }
+            const V4 color = V4{raw.x, raw.y, raw.z, 1.0F};
+
+            contribution_count++;
+            stats_sample_index++;
+            sample_aggregate = sample_aggregate + color;
+
+            if(stats_sample_index == stats_sample_count) {
+                sample_aggregate = sample_aggregate / static_cast<float>(stats_sample_count);
+
+                const V4 delta = sub4(sample_aggregate, contribution_mean);
+                contribution_mean = contribution_mean + delta / static_cast<float>(contribution_count / stats_sample_count);
+                const V4 delta2 = sub4(sample_aggregate, contribution_mean);
+                contribution_m2 = contribution_m2 + delta * delta2;
+
+                if(candidate_count == candidate_batch_count) {
+                    if(n_candidates < kMaxCandidates) {
+                        candidate_means[n_candidates] = candidate_mean;
+                        candidate_m2s[n_candidates] = candidate_m2;
+                        candidate_counts[n_candidates] = candidate_count;
+                        n_candidates++;
+                    }
+                    candidate_mean = zero;
+                    candidate_m2 = zero;
+                    candidate_count = 0;
+                }
+
+                candidate_count++;
+                const V4 candidate_delta = sub4(sample_aggregate, candidate_mean);
+                candidate_mean = candidate_mean + candidate_delta / static_cast<float>(candidate_count);
+                const V4 candidate_delta2 = sub4(sample_aggregate, candidate_mean);
+                candidate_m2 = candidate_m2 + candidate_delta * candidate_delta2;
+
+                stats_sample_index = 0;
+                sample_aggregate = zero;
+            }
+
+            pixel_value = pixel_value + color;
+            collected_sample_count++;
+
+            if(stats_sample_index == 0 && collected_sample_count >= max(min_samples, 2)) {
+                bool passed_check = false;
+                if(contribution_count / stats_sample_count >= 2) {
+                    const V4 m2_weighted = contribution_m2 / static_cast<float>(contribution_count / stats_sample_count - 1);
+                    const float stddev = sqrtf((m2_weighted.x + m2_weighted.y) + m2_weighted.z);
+                    const float mean_contribution = ((contribution_mean.x + contribution_mean.y) + contribution_mean.z) / 3.0F;
+                    // `stddev / (3 * 3 * getContribution(mean) + 1E-5) < 0.2F` is evaluated in double (worker.cpp:243)
+                    const double relative = static_cast<double>(stddev) / (static_cast<double>(9.0F * mean_contribution) + 1E-5);
+                    if(stddev < 1E-4F || relative < static_cast<double>(0.2F)) {
+                        passed_check = true;
+                        remaining_checks--;
+                        if(remaining_checks <= 0) {
+                            accepted_candidate = true;
+                            break;
+                        }
+                    }
+                }
+                if(!passed_check) {
+                    remaining_checks = check_sample_count;
+                }
+            }
+        }
+
+        if(collected_sample_count > 0) {
+            pixel_value = pixel_value * (1.0F / static_cast<float>(collected_sample_count));
+        }
+
+        if(candidate_count > 0 && n_candidates < kMaxCandidates) {
+            candidate_means[n_candidates] = candidate_mean;
+            candidate_m2s[n_candidates] = candidate_m2;
+            candidate_counts[n_candidates] = candidate_count;
+            n_candidates++;
+        }
+
+        if(!accepted_candidate) {
+            V4 colors[kMaxCandidates];
+            float stddevs[kMaxCandidates];
+            int n = 0;
+            const int needed = max((candidate_batch_count * 3) / 4, 2);
+            for(int c = 0; c < n_candidates; c++) {
+                if(candidate_counts[c] < needed) {
+                    continue;
+                }
+                const V4 m2_weighted = candidate_m2s[c] / static_cast<float>(candidate_counts[c]);
+                const float stddev = sqrtf((m2_weighted.x + m2_weighted.y) + m2_weighted.z);
+                // stable insertion (std::sort on fewer than 16 elements is a stable insertion sort in libstdc++)
+                int at = n;
+                while(at > 0 && stddev < stddevs[at - 1]) {
+                    stddevs[at] = stddevs[at - 1];
+                    colors[at] = colors[at - 1];
+                    at--;
+                }
+                stddevs[at] = stddev;
+                colors[at] = candidate_means[c];
+                n++;
+            }
+            if(n > 0) {
+                pixel_value = colors[0];
+                float stddev = stddevs[0];
+                for(int c = 1; c < n; c++) {
+                    const float other = stddevs[c];
+                    if(other < stdmax(stddev + 0.005F, stddev * 1.01F)) {
+                        pixel_value = pixel_value + sub4(colors[c], pixel_value) / static_cast<float>(c + 1);
+                        stddev = other;
+                    }
+                    else {
+                        break;
+                    }
+                }
+            }
+        }
+
+        const uint32_t packed = pixel_list[q];
+        const int px = static_cast<int>(packed & 0xFFFFU) - rp.rect_x0;
+        const int py = static_cast<int>(packed >> 16) - rp.rect_y0;
+        out[static_cast<size_t>(py) * rp.rect_w + px] = f4(pixel_value);
+    }
+
+    // ------------------------------------------------------------------------------------------------ unit kernels
+
+    template<bool COUNT>
+    __global__ void __launch_bounds__(kBlock) intersectKernel(DeviceScene scene, const float *__restrict__ rays, uint64_t n, float *__restrict__ t_out,
+                                                              int32_t *__restrict__ prim_out, uint32_t *__restrict__ fetch, VisitCounters *visits) {
+        for(;;) {
+            unsigned long long base = 0ULL;
+            if(laneId() == 0U) {
+                base = atomicAdd(reinterpret_cast<unsigned long long *>(fetch), 32ULL);
+            }
+            base = __shfl_sync(0xFFFFFFFFU, base, 0);
+            if(base >= n) {
+                return;
+            }
+            const uint64_t k = base + laneId();
+            if(k < n) {
+                const float *p = rays + 6 * k;
+                const RayInv r = makeRay(mk3(p[0], p[1], p[2]), mk3(p[3], p[4], p[5]));
+                const Hit h = traverse<false, COUNT>(scene, r, 0.0F, visits);
+                t_out[k] = h.t;
+                prim_out[k] = (h.slot >= 0 && h.t >= 0.0F) ? static_cast<int32_t>(scene.slot_to_prim[h.slot]) : -1;
+            }
+        }
+    }
+
+    template<bool COUNT>
+    __global__ void __launch_bounds__(kBlock) occludedKernel(DeviceScene scene, const float *__restrict__ rays, uint64_t n, uint8_t *__restrict__ out,
+                                                             uint32_t *__restrict__ fetch, VisitCounters *visits) {
+        for(;;) {
+            unsigned long long base = 0ULL;
+            if(laneId() == 0U) {
+                base = atomicAdd(reinterpret_cast<unsigned long long *>(fetch), 32ULL);
+            }
+            base = __shfl_sync(0xFFFFFFFFU, base, 0);
+            if(base >= n) {
+                return;
+            }
+            const uint64_t k = base + laneId();
+            if(k < n) {
+                const float *p = rays + 7 * k;
+                const RayInv r = makeRay(mk3(p[0], p[1], p[2]), mk3(p[3], p[4], p[5]));
+                const Hit h = traverse<true, COUNT>(scene, r, p[6], visits);
+                out[k] = h.slot >= 0 ? 1 : 0;
+            }
+        }
+    }
+
+    __global__ void aabbKernel(float lox, float loy, float loz, float hix, float hiy, float hiz, const float *__restrict__ rays, uint64_t n,
+                               float *__restrict__ t_out) {
+        const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if(k >= n) {
+            return;
+        }
+        const float *p = rays + 6 * k;
+        const RayInv r = makeRay(mk3(p[0], p[1], p[2]), mk3(p[3], p[4], p[5]));
+        t_out[k] = slab(r, lox, loy, loz, hix, hiy, hiz);
+    }
+
+    __global__ void primKernel(DeviceScene scene, const float *__restrict__ rays, uint64_t n, float *__restrict__ t_out) {
+        const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if(k >= n) {
+            return;
+        }
+        const float *p = rays + 6 * k;
+        const RayInv r = makeRay(mk3(p[0], p[1], p[2]), mk3(p[3], p[4], p[5]));
+        t_out[k] = hitSlot(scene, r, 0U);
+    }
+
+    PTB_DEV Rng engineFromState(uint64_t state) {
+        Rng rng;
+        rng.xorshift = 1U;
+        rng.counter = 0U;
+        rng.state = state;
+        return rng;
+    }
+
+    __global__ void cameraKernel(ptb_camera camera, uint64_t n, const float *__restrict__ xy, float pixel_width, float pixel_height,
+                                 uint64_t *__restrict__ states, float *__restrict__ out) {
+        const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if(k >= n) {
+            return;
+        }
+        Rng rng = engineFromState(states[k]);
+        V3 o;
+        V3 d;
+        shootRay(camera, xy[2 * k], xy[2 * k + 1], pixel_width, pixel_height, rng, o, d);
+        states[k] = rng.state;
+        float *w = out + 6 * k;
+        w[0] = o.x;
+        w[1] = o.y;
+        w[2] = o.z;
+        w[3] = d.x;
+        w[4] = d.y;
+        w[5] = d.z;
+    }
+
+    __global__ void apertureKernel(ptb_camera camera, uint64_t n, uint64_t *__restrict__ states, float *__restrict__ out) {
+        const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if(k >= n) {
+            return;
+        }
+        Rng rng = engineFromState(states[k]);
+        float sx;
+        float sy;
+        sampleAperture(camera, rng, sx, sy);
+        states[k] = rng.state;
+        out[2 * k] = sx;
+        out[2 * k + 1] = sy;
+    }
+
+    // out[0] = number of samples; samples follow at out + 4, 8 floats each; *state is advanced
+    __global__ void sampleLightsKernel(DeviceScene scene, float px, float py, float pz, uint64_t *__restrict__ state, uint32_t max_out,
+                                       float *__restrict__ out) {
+        if(blockIdx.x != 0U || threadIdx.x != 0U) {
+            return;
+        }
+        Rng rng = engineFromState(*state);
+        uint32_t n = 0U;
+        sampleLights(scene, mk3(px, py, pz), rng, [&](const LightSample &ls) {
+            if(n < max_out) {
+                float *w = out + 4 + 8 * n;
+                w[0] = ls.pos.x;
+                w[1] = ls.pos.y;
+                w[2] = ls.pos.z;
+                w[3] = ls.spectrum.x;
+                w[4] = ls.spectrum.y;
+                w[5] = ls.spectrum.z;
+                w[6] = ls.spectrum.w;
+                w[7] = ls.pd;
+            }
+            n++;
+        });
+        *state = rng.state;
+        out[0] = __uint_as_float(n);
+    }
+
+    // `scene` holds exactly one primitive in slot 0 (geometry + shading lanes)
+    __global__ void primNormalKernel(DeviceScene scene, uint64_t n, const float *__restrict__ positions, float *__restrict__ out) {
+        const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if(k >= n) {
+            return;
+        }
+        uint32_t material;
+        const V3 normal = surfaceNormal(scene, 0U, mk3(positions[3 * k], positions[3 * k + 1], positions[3 * k + 2]), material);
+        out[3 * k] = normal.x;
+        out[3 * k + 1] = normal.y;
+        out[3 * k + 2] = normal.z;
+    }
+
+    // lanes: the three un-differenced lanes of the primitive (emissive-table layout)
+    __global__ void primSampleKernel(float4 e0, float4 e1, float4 e2, uint32_t flags, uint64_t n, uint64_t *__restrict__ states, float *__restrict__ out) {
+        const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if(k >= n) {
+            return;
+        }
+        Rng rng = engineFromState(states[k]);
+        V3 pos;
+        float density;
+        bool cull;
+        samplePrimSurface(e0, e1, e2, flags, rng, pos, density, cull);
+        states[k] = rng.state;
+        float *w = out + 5 * k;
+        w[0] = pos.x;
+        w[1] = pos.y;
+        w[2] = pos.z;
+        w[3] = density;
+        w[4] = cull ? 1.0F : 0.0F;
+    }
+
+    PTB_DEV Material materialFromPod(const ptb_material &m) {
+        Material out;
+        out.diffuse = V4{m.diffuse[0], m.diffuse[1], m.diffuse[2], m.diffuse[3]};
+        out.emission = V4{m.emission[0], m.emission[1], m.emission[2], m.emission[3]};
+        out.ior = m.refractive_index;
+        out.bsdf = m.bsdf;
+        out.one_way = m.one_way != 0U;
+        return out;
+    }
+
+    __global__ void bsdfPropagateKernel(ptb_material material, float epsilon, uint64_t n, const float *__restrict__ in, uint64_t *__restrict__ states,
+                                        float *__restrict__ out) {
+        const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if(k >= n) {
+            return;
+        }
+        const float *p = in + 9 * k;
+        Rng rng = engineFromState(states[k]);
+        V3 o;
+        V3 d;
+        float factor;
+        float pd;
+        propagateRay(materialFromPod(material), mk3(p[0], p[1], p[2]), mk3(p[3], p[4], p[5]), mk3(p[6], p[7], p[8]), epsilon, rng, o, d, factor, pd);
+        states[k] = rng.state;
+        float *w = out + 8 * k;
+        w[0] = o.x;
+        w[1] = o.y;
+        w[2] = o.z;
+        w[3] = d.x;
+        w[4] = d.y;
+        w[5] = d.z;
+        w[6] = factor;
+        w[7] = pd;
+    }
+
+    __global__ void bsdfSpectrumKernel(ptb_material material, uint32_t synthetic, uint64_t n, const float *__restrict__ in, float *__restrict__ out) {
+        const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if(k >= n) {
+            return;
+        }
+        const float *p = in + 13 * k;
+        V4 spectrum;
+        float shade;
+        float pd;
+        bsdfSpectrum(materialFromPod(material), mk3(p[0], p[1], p[2]), mk3(p[3], p[4], p[5]), mk3(p[6], p[7], p[8]), V4{p[9], p[10], p[11], p[12]},
+                     synthetic != 0U, spectrum, shade, pd);
+        float *w = out + 6 * k;
+        w[0] = spectrum.x;
+        w[1] = spectrum.y;
+        w[2] = spectrum.z;
+        w[3] = spectrum.w;
+        w[4] = shade;
+        w[5] = pd;
+    }
+
+}
+
+#endif

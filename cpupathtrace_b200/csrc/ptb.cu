@@ -1,0 +1,1326 @@
+// C-ABI implementation (include/ptb.h): context, scene upload and the host driver of the wavefront pipeline.
+// Everything that computes goes through the kernels in kernels.cuh; there is no host implementation of the hot path.
+#include "../../include/ptb.h"
+
+#include "bvh_build.h"
+#include "host_math.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+    thread_local std::string g_last_error;
+
+    int fail(int status, const std::string &message) {
+        g_last_error = message;
+        return status;
+    }
+
+#define PTB_CUDA(call)                                                                                                                                        \
+    do {                                                                                                                                                      \
+        cudaError_t err__ = (call);                                                                                                                           \
+        if(err__ != cudaSuccess) {                                                                                                                            \
+            cudaGetLastError();                                                                                                                               \
+            return fail(err__ == cudaErrorMemoryAllocation ? PTB_ERR_OUT_OF_MEMORY : PTB_ERR_CUDA,                                                            \
+                        std::string(#call) + ": " + cudaGetErrorString(err__));                                                                               \
+        }                                                                                                                                                     \
+    } while(0)
+
+    double nowSeconds() {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
+
+    long envLong(const char *name, long fallback) {
+        const char *v = std::getenv(name);
+        if(v == nullptr || *v == '\0') {
+            return fallback;
+        }
+        return std::atol(v);
+    }
+
+    // A device allocation that grows on demand and is reused across calls
+    struct Buffer {
+        void *ptr = nullptr;
+        size_t bytes = 0;
+
+        int reserve(size_t wanted) {
+            if(wanted <= bytes) {
+                return PTB_OK;
+            }
+            if(ptr != nullptr) {
+                cudaFree(ptr);
+                ptr = nullptr;
+                bytes = 0;
+            }
+            PTB_CUDA(cudaMalloc(&ptr, wanted));
+            bytes = wanted;
+            return PTB_OK;
+        }
+
+        void release() {
+            if(ptr != nullptr) {
+                cudaFree(ptr);
+            }
+            ptr = nullptr;
+            bytes = 0;
+        }
+
+        template<typename T>
+        T *as() const {
+            return static_cast<T *>(ptr);
+        }
+    };
+
+    constexpr int kEventPairs = 2048;
+
+}
+
+struct ptb_context {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+
+    // wavefront workspace
+    Buffer pool_mem;
+    Buffer queue_a;
+    Buffer queue_b;
+    Buffer shadow_queue;
+    Buffer counters;
+    Buffer visits;
+    Buffer samples;
+    Buffer pixel_list;
+    Buffer io_a; // staging for host<->device bulk arrays
+    Buffer io_b;
+    Buffer io_c;
+    Buffer io_d;
+    uint32_t *host_counters = nullptr; // pinned
+
+    // profiling events: [pair][0 = start, 1 = stop], class 0 = trace, 1 = everything else
+    cudaEvent_t events[kEventPairs][2];
+    int event_class[kEventPairs];
+    int events_used = 0;
+    bool events_ready = false;
+    cudaEvent_t call_start = nullptr;
+    cudaEvent_t call_stop = nullptr;
+};
+
+struct ptb_scene {
+    ptb_context *ctx = nullptr;
+    ptb::DeviceScene dev{};
+    Buffer nodes;
+    Buffer geom;
+    Buffer shade;
+    Buffer mats;
+    Buffer lights;
+    Buffer emis;
+    Buffer cdf;
+    Buffer slot_to_prim;
+    ptb_scene_info info{};
+    uint32_t shadow_stride = 1;
+};
+
+namespace {
+
+    using namespace ptb;
+
+    int useDevice(const ptb_context *ctx) {
+        PTB_CUDA(cudaSetDevice(ctx->device));
+        return PTB_OK;
+    }
+
+    int gridFor(const ptb_context *ctx, int blocks_per_sm) {
+        return std::max(1, ctx->sm_count) * blocks_per_sm;
+    }
+
+    // ---- profiling helpers: every launch is bracketed by an event pair on the launching stream
+
+    struct LaunchTimer {
+        ptb_context *ctx;
+        int pair;
+        LaunchTimer(ptb_context *c, int klass) : ctx(c), pair(-1) {
+            if(ctx->events_ready && ctx->events_used < kEventPairs) {
+                pair = ctx->events_used++;
+                ctx->event_class[pair] = klass;
+                cudaEventRecord(ctx->events[pair][0], ctx->stream);
+            }
+        }
+        ~LaunchTimer() {
+            if(pair >= 0) {
+                cudaEventRecord(ctx->events[pair][1], ctx->stream);
+            }
+        }
+    };
+
+    void collectTimers(ptb_context *ctx, ptb_render_stats *stats) {
+        for(int i = 0; i < ctx->events_used; i++) {
+            float ms = 0.0F;
+            if(cudaEventElapsedTime(&ms, ctx->events[i][0], ctx->events[i][1]) == cudaSuccess && stats != nullptr) {
+                if(ctx->event_class[i] == 0) {
+                    stats->device_ms_trace += ms;
+                }
+                else {
+                    stats->device_ms_shade += ms;
+                }
+            }
+        }
+        ctx->events_used = 0;
+    }
+
+    // When the event pool runs dry mid-call the remaining launches go untimed; callers that need complete
+    // per-kernel sums (bench.py) keep calls short enough (see PTB_POOL_PATHS) or read device_ms_total.
+
+    int carvePool(ptb_context *ctx, uint32_t capacity, uint32_t shadow_stride, PathPool &pool) {
+        const size_t n = capacity;
+        const size_t ns = n * shadow_stride;
+        size_t offset = 0;
+        auto take = [&](size_t bytes) {
+            const size_t at = offset;
+            offset += (bytes + 255) & ~static_cast<size_t>(255);
+            return at;
+        };
+        const size_t o_ray_o = take(n * sizeof(float4));
+        const size_t o_ray_d = take(n * sizeof(float4));
+        const size_t o_hit = take(n * sizeof(float2));
+        const size_t o_thr = take(n * sizeof(float4));
+        const size_t o_rad = take(n * sizeof(float4));
+        const size_t o_div = take(n * sizeof(double));
+        const size_t o_bpd = take(n * sizeof(double));
+        const size_t o_con = take(n * sizeof(float));
+        const size_t o_state = take(n * sizeof(uint32_t));
+        const size_t o_rng = take(n * sizeof(uint64_t));
+        const size_t o_dest = take(n * sizeof(uint32_t));
+        const size_t o_scount = take(n * sizeof(uint32_t));
+        const size_t o_so = take(ns * sizeof(float4));
+        const size_t o_sd = take(ns * sizeof(float4));
+        const size_t o_sc = take(ns * sizeof(float4));
+
+        int status = ctx->pool_mem.reserve(offset);
+        if(status != PTB_OK) {
+            return status;
+        }
+        char *base = ctx->pool_mem.as<char>();
+        pool.ray_o = reinterpret_cast<float4 *>(base + o_ray_o);
+        pool.ray_d = reinterpret_cast<float4 *>(base + o_ray_d);
+        pool.hit = reinterpret_cast<float2 *>(base + o_hit);
+        pool.throughput = reinterpret_cast<float4 *>(base + o_thr);
+        pool.radiance = reinterpret_cast<float4 *>(base + o_rad);
+        pool.divisor = reinterpret_cast<double *>(base + o_div);
+        pool.bounce_pd = reinterpret_cast<double *>(base + o_bpd);
+        pool.contribution = reinterpret_cast<float *>(base + o_con);
+        pool.state = reinterpret_cast<uint32_t *>(base + o_state);
+        pool.rng = reinterpret_cast<uint64_t *>(base + o_rng);
+        pool.dest = reinterpret_cast<uint32_t *>(base + o_dest);
+        pool.shadow_count = reinterpret_cast<uint32_t *>(base + o_scount);
+        pool.shadow_o = reinterpret_cast<float4 *>(base + o_so);
+        pool.shadow_d = reinterpret_cast<float4 *>(base + o_sd);
+        pool.shadow_c = reinterpret_cast<float4 *>(base + o_sc);
+        pool.shadow_stride = shadow_stride;
+        pool.capacity = capacity;
+
+        if((status = ctx->queue_a.reserve(n * sizeof(uint32_t))) != PTB_OK) {
+            return status;
+        }
+        if((status = ctx->queue_b.reserve(n * sizeof(uint32_t))) != PTB_OK) {
+            return status;
+        }
+        if((status = ctx->shadow_queue.reserve(ns * sizeof(uint32_t))) != PTB_OK) {
+            return status;
+        }
+        if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK) {
+            return status;
+        }
+        if((status = ctx->visits.reserve(sizeof(VisitCounters))) != PTB_OK) {
+            return status;
+        }
+        return PTB_OK;
+    }
+
+    RenderParams makeParams(const ptb_camera &camera, const ptb_render_opts &opts) {
+        RenderParams p{};
+        p.camera = camera;
+        p.image_width = opts.image_width;
+        p.image_height = opts.image_height;
+        p.epsilon = opts.epsilon;
+        p.max_depth = opts.max_depth;
+        p.rng_xorshift = opts.rng_mode == PTB_RNG_REFERENCE_XORSHIFT ? 1U : 0U;
+        p.any_hit_shadows = (opts.flags & PTB_FLAG_ANY_HIT_SHADOWS) != 0U ? 1U : 0U;
+        p.skip_null_shadows = (opts.flags & PTB_FLAG_SKIP_NULL_SHADOWS) != 0U ? 1U : 0U;
+        p.seed = opts.seed;
+        return p;
+    }
+
+    // Runs the bounce loop for a batch whose primary rays are already generated into queue A.
+    int runBounces(ptb_scene *scene, const PathPool &pool, const RenderParams &params, uint32_t batch, float4 *samples, bool count_visits,
+                   ptb_render_stats *stats) {
+        ptb_context *ctx = scene->ctx;
+        uint32_t *counters = ctx->counters.as<uint32_t>();
+        uint32_t *queues[2] = {ctx->queue_a.as<uint32_t>(), ctx->queue_b.as<uint32_t>()};
+        uint32_t *shadow_queue = ctx->shadow_queue.as<uint32_t>();
+        VisitCounters *visits = ctx->visits.as<VisitCounters>();
+
+        const int trace_grid = gridFor(ctx, 16);
+        int cur = 0;
+        uint32_t n_cur = batch;
+
+        while(n_cur > 0U) {
+            const int nxt = cur ^ 1;
+            // zero: next queue length; shadow queue length, both fetch cursors and the per-iteration statistics (slots 2..6)
+            PTB_CUDA(cudaMemsetAsync(counters + nxt, 0, sizeof(uint32_t), ctx->stream));
+            PTB_CUDA(cudaMemsetAsync(counters + kCountShadow, 0, 5 * sizeof(uint32_t), ctx->stream));
+
+            const int flat_grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_cur) + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 32))));
+            {
+                LaunchTimer timer(ctx, 0);
+                if(count_visits) {
+                    traceClosestKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, queues[cur], counters, cur, visits);
+                }
+                else {
+                    traceClosestKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, queues[cur], counters, cur, visits);
+                }
+            }
+            {
+                LaunchTimer timer(ctx, 1);
+                shadeKernel<<<flat_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, cur, shadow_queue);
+            }
+            {
+                LaunchTimer timer(ctx, 0);
+                if(count_visits) {
+                    traceShadowKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, shadow_queue, counters, params.any_hit_shadows, visits);
+                }
+                else {
+                    traceShadowKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, shadow_queue, counters, params.any_hit_shadows, visits);
+                }
+            }
+            {
+                LaunchTimer timer(ctx, 1);
+                accumulateKernel<<<flat_grid, kBlock, 0, ctx->stream>>>(pool, queues[cur], counters, cur, queues[nxt], nxt, samples);
+            }
+            PTB_CUDA(cudaMemcpyAsync(ctx->host_counters, counters, kCounterSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+            PTB_CUDA(cudaGetLastError());
+
+            if(stats != nullptr) {
+                stats->closest_rays += n_cur;
+                stats->shadow_rays += ctx->host_counters[kCountShadow];
+                stats->shadow_rays_skipped += ctx->host_counters[kCountSkippedShadows];
+                stats->path_vertices += ctx->host_counters[kCountVertices];
+                stats->bounce_iterations += 1;
+                stats->kernel_launches += 4;
+            }
+            collectTimers(ctx, stats);
+            n_cur = ctx->host_counters[nxt];
+            cur = nxt;
+        }
+        return PTB_OK;
+    }
+
+    int beginCall(ptb_context *ctx, ptb_render_stats *stats) {
+        int status = useDevice(ctx);
+        if(status != PTB_OK) {
+            return status;
+        }
+        if(stats != nullptr) {
+            std::memset(stats, 0, sizeof(*stats));
+        }
+        ctx->events_used = 0;
+        PTB_CUDA(cudaEventRecord(ctx->call_start, ctx->stream));
+        return PTB_OK;
+    }
+
+    int endCall(ptb_context *ctx, ptb_render_stats *stats) {
+        PTB_CUDA(cudaEventRecord(ctx->call_stop, ctx->stream));
+        PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+        PTB_CUDA(cudaGetLastError());
+        if(stats != nullptr) {
+            float ms = 0.0F;
+            cudaEventElapsedTime(&ms, ctx->call_start, ctx->call_stop);
+            stats->device_ms_total = ms;
+        }
+        collectTimers(ctx, stats);
+        return PTB_OK;
+    }
+
+    int finishStats(ptb_context *ctx, bool count_visits, ptb_render_stats *stats) {
+        if(stats == nullptr) {
+            return PTB_OK;
+        }
+        if(count_visits) {
+            VisitCounters v{};
+            PTB_CUDA(cudaMemcpy(&v, ctx->visits.ptr, sizeof(v), cudaMemcpyDeviceToHost));
+            stats->inner_visits = v.inner;
+            stats->leaf_visits = v.leaf;
+        }
+        return PTB_OK;
+    }
+
+}
+
+extern "C" {
+
+int ptb_abi_version(void) {
+    return PTB_ABI_VERSION;
+}
+
+const char *ptb_last_error(void) {
+    return g_last_error.c_str();
+}
+
+int ptb_camera_init(ptb_camera *out, const float origin[3], const float look_at[3], const float up[3], float focal_length, float height, float aspect_ratio,
+                    float aperture_width, float aperture_height, uint32_t aperture_kind, float hexagon_horizontal_ratio, float focal_plane_dist) {
+    if(out == nullptr || origin == nullptr || look_at == nullptr || up == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_camera_init: null argument");
+    }
+    ptb::cameraInit(out, origin, look_at, up, focal_length, height, aspect_ratio, aperture_width, aperture_height, aperture_kind, hexagon_horizontal_ratio,
+                    focal_plane_dist);
+    return PTB_OK;
+}
+
+int ptb_context_create(int device, ptb_context **out) {
+    if(out == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_context_create: out is null");
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if(err != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(PTB_ERR_NO_DEVICE, std::string("no CUDA device available (") + (err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0") +
+                                         "); this library has no CPU fallback");
+    }
+    if(device < 0) {
+        device = static_cast<int>(envLong("PTB_DEVICE", envLong("LOCAL_RANK", 0)));
+    }
+    if(device >= count) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_context_create: device index out of range");
+    }
+    PTB_CUDA(cudaSetDevice(device));
+
+    auto *ctx = new(std::nothrow) ptb_context();
+    if(ctx == nullptr) {
+        return fail(PTB_ERR_OUT_OF_MEMORY, "ptb_context_create: host allocation failed");
+    }
+    ctx->device = device;
+    cudaDeviceProp prop{};
+    PTB_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    if(prop.major < 10) {
+        delete ctx;
+        return fail(PTB_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100-class; the kernels are built for sm_100a only");
+    }
+    PTB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    PTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->host_counters), kCounterSlots * sizeof(uint32_t)));
+    for(auto &pair : ctx->events) {
+        PTB_CUDA(cudaEventCreate(&pair[0]));
+        PTB_CUDA(cudaEventCreate(&pair[1]));
+    }
+    PTB_CUDA(cudaEventCreate(&ctx->call_start));
+    PTB_CUDA(cudaEventCreate(&ctx->call_stop));
+    ctx->events_ready = envLong("PTB_PROFILE", 1) != 0;
+    *out = ctx;
+    return PTB_OK;
+}
+
+int ptb_context_destroy(ptb_context *ctx) {
+    if(ctx == nullptr) {
+        return PTB_OK;
+    }
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->counters, &ctx->visits, &ctx->samples, &ctx->pixel_list,
+                     &ctx->io_a, &ctx->io_b, &ctx->io_c, &ctx->io_d}) {
+        b->release();
+    }
+    if(ctx->host_counters != nullptr) {
+        cudaFreeHost(ctx->host_counters);
+    }
+    for(auto &pair : ctx->events) {
+        cudaEventDestroy(pair[0]);
+        cudaEventDestroy(pair[1]);
+    }
+    cudaEventDestroy(ctx->call_start);
+    cudaEventDestroy(ctx->call_stop);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PTB_OK;
+}
+
+int ptb_context_device(const ptb_context *ctx, int *device_out) {
+    if(ctx == nullptr || device_out == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_context_device: null argument");
+    }
+    *device_out = ctx->device;
+    return PTB_OK;
+}
+
+int ptb_context_synchronize(ptb_context *ctx) {
+    if(ctx == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_context_synchronize: null context");
+    }
+    int status = useDevice(ctx);
+    if(status != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- scene
+
+int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **out) {
+    if(ctx == nullptr || desc == nullptr || out == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_scene_create: null argument");
+    }
+    *out = nullptr;
+    if(desc->n_prims > 0 && (desc->prims == nullptr || desc->materials == nullptr || desc->n_materials == 0)) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_scene_create: primitives need a material table");
+    }
+    if(desc->n_prims >= (1ULL << 31) - 1) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_scene_create: more than 2^31 - 2 primitives");
+    }
+    if(desc->bvh_mode != PTB_BVH_REFERENCE) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_scene_create: unknown bvh_mode");
+    }
+    for(uint64_t i = 0; i < desc->n_prims; i++) {
+        const ptb_prim &prim = desc->prims[i];
+        if(prim.kind > PTB_PRIM_NULL) {
+            return fail(PTB_ERR_UNSUPPORTED, "ptb_scene_create: unknown primitive kind");
+        }
+        if(prim.material >= desc->n_materials) {
+            return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_scene_create: material index out of range");
+        }
+    }
+    for(uint32_t i = 0; i < desc->n_materials; i++) {
+        if(desc->materials[i].bsdf > PTB_BSDF_MIRROR) {
+            return fail(PTB_ERR_UNSUPPORTED, "ptb_scene_create: unknown BSDF kind");
+        }
+    }
+    int status = useDevice(ctx);
+    if(status != PTB_OK) {
+        return status;
+    }
+
+    const double t0 = nowSeconds();
+    const int threads = static_cast<int>(envLong("PTB_BUILD_THREADS", 0));
+    FlatBvh bvh = buildReferenceBvh(desc->prims, desc->n_prims, threads);
+    if(bvh.depth > static_cast<uint32_t>(kStackCapacity)) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_scene_create: BVH deeper than the traversal stack (" + std::to_string(bvh.depth) + ")");
+    }
+
+    const uint64_t n = desc->n_prims;
+    std::vector<float4> geom(3 * n);
+    std::vector<float4> shade(3 * n);
+    for(uint64_t slot = 0; slot < n; slot++) {
+        const ptb_prim &prim = desc->prims[bvh.slot_to_prim[slot]];
+        const float *p = prim.p;
+        uint32_t flags = prim.kind & kKindMask;
+        if(prim.kind == PTB_PRIM_TRIANGLE && prim.cull_backface != 0U) {
+            flags |= kCullBit;
+        }
+        float4 *g = &geom[3 * slot];
+        float4 *s = &shade[3 * slot];
+        if(prim.kind == PTB_PRIM_TRIANGLE) {
+            // edges are differenced on the host exactly as Triangle::getIntersection does per call (object.cpp:149-150)
+            g[0] = make_float4(p[0], p[1], p[2], 0.0F);
+            g[1] = make_float4(p[3] - p[0], p[4] - p[1], p[5] - p[2], 0.0F);
+            g[2] = make_float4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0F);
+            s[0] = make_float4(p[9], p[10], p[11], 0.0F);
+            s[1] = make_float4(p[12], p[13], p[14], 0.0F);
+            s[2] = make_float4(p[15], p[16], p[17], 0.0F);
+        }
+        else if(prim.kind == PTB_PRIM_SPHERE) {
+            g[0] = make_float4(p[0], p[1], p[2], 0.0F);
+            g[1] = make_float4(p[3], p[3] * p[3], 0.0F, 0.0F);
+            g[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+            s[0] = s[1] = s[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+        }
+        else {
+            g[0] = g[1] = g[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+            s[0] = s[1] = s[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+        }
+        std::memcpy(&g[0].w, &flags, sizeof(flags));
+        std::memcpy(&s[0].w, &prim.material, sizeof(uint32_t));
+    }
+
+    std::vector<float4> mats(3 * static_cast<size_t>(desc->n_materials));
+    for(uint32_t i = 0; i < desc->n_materials; i++) {
+        const ptb_material &m = desc->materials[i];
+        mats[3 * i] = make_float4(m.diffuse[0], m.diffuse[1], m.diffuse[2], m.diffuse[3]);
+        mats[3 * i + 1] = make_float4(m.emission[0], m.emission[1], m.emission[2], m.emission[3]);
+        float4 misc = make_float4(m.refractive_index, 0.0F, 0.0F, 0.0F);
+        std::memcpy(&misc.y, &m.bsdf, sizeof(uint32_t));
+        const uint32_t one_way = m.one_way != 0U ? 1U : 0U;
+        std::memcpy(&misc.z, &one_way, sizeof(uint32_t));
+        mats[3 * i + 2] = misc;
+    }
+
+    std::vector<float4> lights(2 * static_cast<size_t>(desc->n_lights));
+    for(uint32_t i = 0; i < desc->n_lights; i++) {
+        const ptb_point_light &l = desc->lights[i];
+        lights[2 * i] = make_float4(l.pos[0], l.pos[1], l.pos[2], 0.0F);
+        lights[2 * i + 1] = make_float4(l.rgba[0], l.rgba[1], l.rgba[2], l.rgba[3]);
+    }
+
+    EmissiveTable emissive = buildEmissiveTable(desc->prims, desc->materials, bvh.slot_to_prim.data(), n);
+    std::vector<float4> emis(3 * emissive.slots.size());
+    for(size_t i = 0; i < emissive.slots.size(); i++) {
+        const uint32_t slot = emissive.slots[i];
+        const ptb_prim &prim = desc->prims[bvh.slot_to_prim[slot]];
+        const float *p = prim.p;
+        float4 e0;
+        float4 e1;
+        float4 e2;
+        if(prim.kind == PTB_PRIM_TRIANGLE) {
+            e0 = make_float4(p[0], p[1], p[2], 0.0F);
+            e1 = make_float4(p[3], p[4], p[5], 0.0F);
+            e2 = make_float4(p[6], p[7], p[8], 0.0F);
+        }
+        else {
+            e0 = make_float4(p[0], p[1], p[2], 0.0F);
+            e1 = make_float4(p[3], p[3] * p[3], 0.0F, 0.0F);
+            e2 = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+        }
+        std::memcpy(&e0.w, &slot, sizeof(uint32_t));
+        emis[3 * i] = e0;
+        emis[3 * i + 1] = e1;
+        emis[3 * i + 2] = e2;
+    }
+    const double t1 = nowSeconds();
+
+    auto *scene = new(std::nothrow) ptb_scene();
+    if(scene == nullptr) {
+        return fail(PTB_ERR_OUT_OF_MEMORY, "ptb_scene_create: host allocation failed");
+    }
+    scene->ctx = ctx;
+
+    auto upload = [&](Buffer &buffer, const void *src, size_t bytes) -> int {
+        int st = buffer.reserve(std::max<size_t>(bytes, 16));
+        if(st != PTB_OK) {
+            return st;
+        }
+        if(bytes > 0) {
+            PTB_CUDA(cudaMemcpy(buffer.ptr, src, bytes, cudaMemcpyHostToDevice));
+        }
+        return PTB_OK;
+    };
+    status = upload(scene->nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(NodeRecord));
+    status = status != PTB_OK ? status : upload(scene->geom, geom.data(), geom.size() * sizeof(float4));
+    status = status != PTB_OK ? status : upload(scene->shade, shade.data(), shade.size() * sizeof(float4));
+    status = status != PTB_OK ? status : upload(scene->mats, mats.data(), mats.size() * sizeof(float4));
+    status = status != PTB_OK ? status : upload(scene->lights, lights.data(), lights.size() * sizeof(float4));
+    status = status != PTB_OK ? status : upload(scene->emis, emis.data(), emis.size() * sizeof(float4));
+    status = status != PTB_OK ? status : upload(scene->cdf, emissive.cdf.data(), emissive.cdf.size() * sizeof(float));
+    status = status != PTB_OK ? status : upload(scene->slot_to_prim, bvh.slot_to_prim.data(), bvh.slot_to_prim.size() * sizeof(uint32_t));
+    if(status != PTB_OK) {
+        ptb_scene_destroy(scene);
+        return status;
+    }
+    const double t2 = nowSeconds();
+
+    DeviceScene &d = scene->dev;
+    d.nodes = scene->nodes.as<float4>();
+    d.geom = scene->geom.as<float4>();
+    d.shade = scene->shade.as<float4>();
+    d.mats = scene->mats.as<float4>();
+    d.lights = scene->lights.as<float4>();
+    d.emis = scene->emis.as<float4>();
+    d.cdf = scene->cdf.as<float>();
+    d.slot_to_prim = scene->slot_to_prim.as<uint32_t>();
+    d.n_prims = static_cast<uint32_t>(n);
+    d.n_lights = desc->n_lights;
+    d.n_emissive = static_cast<uint32_t>(emissive.slots.size());
+    d.object_sample_count = emissive.object_sample_count;
+    d.root_ref = bvh.root_ref;
+    for(int c = 0; c < 3; c++) {
+        d.root_lo[c] = bvh.root_low[c];
+        d.root_hi[c] = bvh.root_high[c];
+    }
+
+    scene->shadow_stride = std::max<uint32_t>(1U, desc->n_lights + emissive.object_sample_count);
+
+    ptb_scene_info &info = scene->info;
+    info.n_prims = n;
+    info.n_inner_nodes = bvh.nodes.size();
+    info.bvh_depth = bvh.depth;
+    info.n_emissive = d.n_emissive;
+    info.object_sample_count = d.object_sample_count;
+    info.n_lights = desc->n_lights;
+    info.device_bytes = scene->nodes.bytes + scene->geom.bytes + scene->shade.bytes + scene->mats.bytes + scene->lights.bytes + scene->emis.bytes +
+                        scene->cdf.bytes + scene->slot_to_prim.bytes;
+    info.build_seconds = t1 - t0;
+    info.upload_seconds = t2 - t1;
+    for(int c = 0; c < 3; c++) {
+        info.root_low[c] = bvh.root_low[c];
+        info.root_high[c] = bvh.root_high[c];
+    }
+
+    *out = scene;
+    return PTB_OK;
+}
+
+int ptb_scene_destroy(ptb_scene *scene) {
+    if(scene == nullptr) {
+        return PTB_OK;
+    }
+    if(scene->ctx != nullptr) {
+        cudaSetDevice(scene->ctx->device);
+        cudaStreamSynchronize(scene->ctx->stream);
+    }
+    for(Buffer *b : {&scene->nodes, &scene->geom, &scene->shade, &scene->mats, &scene->lights, &scene->emis, &scene->cdf, &scene->slot_to_prim}) {
+        b->release();
+    }
+    delete scene;
+    return PTB_OK;
+}
+
+int ptb_scene_get_info(const ptb_scene *scene, ptb_scene_info *out) {
+    if(scene == nullptr || out == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_scene_get_info: null argument");
+    }
+    *out = scene->info;
+    return PTB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- intersect
+
+int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t_out, int32_t *prim_out, uint32_t flags, ptb_render_stats *stats) {
+    if(scene == nullptr || (n_rays > 0 && (rays == nullptr || t_out == nullptr || prim_out == nullptr))) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_intersect: null argument");
+    }
+    ptb_context *ctx = scene->ctx;
+    int status = beginCall(ctx, stats);
+    if(status != PTB_OK) {
+        return status;
+    }
+    if(n_rays == 0) {
+        return endCall(ctx, stats);
+    }
+    const bool device_io = (flags & PTB_FLAG_DEVICE_IO) != 0U;
+    const bool count_visits = (flags & PTB_FLAG_COUNT_VISITS) != 0U;
+
+    const float *d_rays = rays;
+    float *d_t = t_out;
+    int32_t *d_prim = prim_out;
+    if(!device_io) {
+        if((status = ctx->io_a.reserve(n_rays * 6 * sizeof(float))) != PTB_OK || (status = ctx->io_b.reserve(n_rays * sizeof(float))) != PTB_OK ||
+           (status = ctx->io_c.reserve(n_rays * sizeof(int32_t))) != PTB_OK) {
+            return status;
+        }
+        PTB_CUDA(cudaMemcpyAsync(ctx->io_a.ptr, rays, n_rays * 6 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        d_rays = ctx->io_a.as<float>();
+        d_t = ctx->io_b.as<float>();
+        d_prim = ctx->io_c.as<int32_t>();
+    }
+    if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK || (status = ctx->visits.reserve(sizeof(VisitCounters))) != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
+    PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, sizeof(VisitCounters), ctx->stream));
+
+    const int grid = static_cast<int>(std::min<uint64_t>((n_rays + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 16))));
+    {
+        LaunchTimer timer(ctx, 0);
+        if(count_visits) {
+            intersectKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays, n_rays, d_t, d_prim, ctx->counters.as<uint32_t>(),
+                                                                     ctx->visits.as<VisitCounters>());
+        }
+        else {
+            intersectKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays, n_rays, d_t, d_prim, ctx->counters.as<uint32_t>(),
+                                                                      ctx->visits.as<VisitCounters>());
+        }
+    }
+    PTB_CUDA(cudaGetLastError());
+    if(!device_io) {
+        PTB_CUDA(cudaMemcpyAsync(t_out, d_t, n_rays * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        PTB_CUDA(cudaMemcpyAsync(prim_out, d_prim, n_rays * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    status = endCall(ctx, stats);
+    if(status != PTB_OK) {
+        return status;
+    }
+    if(stats != nullptr) {
+        stats->closest_rays = n_rays;
+        stats->kernel_launches = 1;
+    }
+    return finishStats(ctx, count_visits, stats);
+}
+
+int ptb_occluded(ptb_scene *scene, const float *rays, uint64_t n_rays, uint8_t *occluded_out, uint32_t flags, ptb_render_stats *stats) {
+    if(scene == nullptr || (n_rays > 0 && (rays == nullptr || occluded_out == nullptr))) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_occluded: null argument");
+    }
+    ptb_context *ctx = scene->ctx;
+    int status = beginCall(ctx, stats);
+    if(status != PTB_OK) {
+        return status;
+    }
+    if(n_rays == 0) {
+        return endCall(ctx, stats);
+    }
+    const bool device_io = (flags & PTB_FLAG_DEVICE_IO) != 0U;
+    const bool count_visits = (flags & PTB_FLAG_COUNT_VISITS) != 0U;
+
+    const float *d_rays = rays;
+    uint8_t *d_out = occluded_out;
+    if(!device_io) {
+        if((status = ctx->io_a.reserve(n_rays * 7 * sizeof(float))) != PTB_OK || (status = ctx->io_b.reserve(n_rays)) != PTB_OK) {
+            return status;
+        }
+        PTB_CUDA(cudaMemcpyAsync(ctx->io_a.ptr, rays, n_rays * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        d_rays = ctx->io_a.as<float>();
+        d_out = ctx->io_b.as<uint8_t>();
+    }
+    if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK || (status = ctx->visits.reserve(sizeof(VisitCounters))) != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
+    PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, sizeof(VisitCounters), ctx->stream));
+
+    const int grid = static_cast<int>(std::min<uint64_t>((n_rays + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 16))));
+    {
+        LaunchTimer timer(ctx, 0);
+        if(count_visits) {
+            occludedKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays, n_rays, d_out, ctx->counters.as<uint32_t>(),
+                                                                    ctx->visits.as<VisitCounters>());
+        }
+        else {
+            occludedKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays, n_rays, d_out, ctx->counters.as<uint32_t>(),
+                                                                     ctx->visits.as<VisitCounters>());
+        }
+    }
+    PTB_CUDA(cudaGetLastError());
+    if(!device_io) {
+        PTB_CUDA(cudaMemcpyAsync(occluded_out, d_out, n_rays, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    status = endCall(ctx, stats);
+    if(status != PTB_OK) {
+        return status;
+    }
+    if(stats != nullptr) {
+        stats->shadow_rays = n_rays;
+        stats->kernel_launches = 1;
+    }
+    return finishStats(ctx, count_visits, stats);
+}
+
+// ---------------------------------------------------------------------------------------------------- render
+
+int ptb_render_samples(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts *opts, uint64_t n, const int32_t *pixels, const uint64_t *seeds,
+                       float *out_rgba, ptb_render_stats *stats) {
+    if(scene == nullptr || camera == nullptr || opts == nullptr || (n > 0 && (pixels == nullptr || seeds == nullptr || out_rgba == nullptr))) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render_samples: null argument");
+    }
+    if(opts->image_width <= 0 || opts->image_height <= 0) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render_samples: empty image");
+    }
+    ptb_context *ctx = scene->ctx;
+    int status = beginCall(ctx, stats);
+    if(status != PTB_OK) {
+        return status;
+    }
+    if(n == 0) {
+        return endCall(ctx, stats);
+    }
+    const bool device_io = (opts->flags & PTB_FLAG_DEVICE_IO) != 0U;
+    const bool count_visits = (opts->flags & PTB_FLAG_COUNT_VISITS) != 0U;
+    const uint32_t capacity = static_cast<uint32_t>(std::min<uint64_t>(n, static_cast<uint64_t>(envLong("PTB_POOL_PATHS", 1L << 22))));
+
+    PathPool pool{};
+    if((status = carvePool(ctx, capacity, scene->shadow_stride, pool)) != PTB_OK) {
+        return status;
+    }
+    const int32_t *d_pixels = pixels;
+    const uint64_t *d_seeds = seeds;
+    float4 *d_out = reinterpret_cast<float4 *>(out_rgba);
+    if(!device_io) {
+        if((status = ctx->io_a.reserve(n * 2 * sizeof(int32_t))) != PTB_OK || (status = ctx->io_b.reserve(n * sizeof(uint64_t))) != PTB_OK ||
+           (status = ctx->io_c.reserve(n * sizeof(float4))) != PTB_OK) {
+            return status;
+        }
+        PTB_CUDA(cudaMemcpyAsync(ctx->io_a.ptr, pixels, n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        PTB_CUDA(cudaMemcpyAsync(ctx->io_b.ptr, seeds, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        d_pixels = ctx->io_a.as<int32_t>();
+        d_seeds = ctx->io_b.as<uint64_t>();
+        d_out = ctx->io_c.as<float4>();
+    }
+    PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
+    PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, sizeof(VisitCounters), ctx->stream));
+
+    const RenderParams params = makeParams(*camera, *opts);
+    for(uint64_t first = 0; first < n; first += capacity) {
+        const uint32_t batch = static_cast<uint32_t>(std::min<uint64_t>(capacity, n - first));
+        const int grid = static_cast<int>((batch + kBlock - 1) / kBlock);
+        {
+            LaunchTimer timer(ctx, 1);
+            generateSamplesKernel<<<grid, kBlock, 0, ctx->stream>>>(pool, params, d_pixels, d_seeds, first, batch, ctx->queue_a.as<uint32_t>(),
+                                                                    ctx->counters.as<uint32_t>(), kCountQueueA);
+        }
+        PTB_CUDA(cudaGetLastError());
+        if(stats != nullptr) {
+            stats->samples += batch;
+            stats->kernel_launches += 1;
+        }
+        // destinations are batch-local; offset the output pointer
+        if((status = runBounces(scene, pool, params, batch, d_out + first, count_visits, stats)) != PTB_OK) {
+            return status;
+        }
+    }
+    if(!device_io) {
+        PTB_CUDA(cudaMemcpyAsync(out_rgba, d_out, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    status = endCall(ctx, stats);
+    if(status != PTB_OK) {
+        return status;
+    }
+    return finishStats(ctx, count_visits, stats);
+}
+
+int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts *opts, int32_t x0, int32_t y0, int32_t w, int32_t h, float *out_rgba,
+               ptb_render_stats *stats) {
+    if(scene == nullptr || camera == nullptr || opts == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render: null argument");
+    }
+    if(w < 0 || h < 0 || x0 < 0 || y0 < 0 || x0 + w > 65535 || y0 + h > 65535) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render: rectangle out of range (coordinates are limited to 16 bits)");
+    }
+    if(opts->image_width <= 0 || opts->image_height <= 0) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render: empty image");
+    }
+    ptb_context *ctx = scene->ctx;
+    int status = beginCall(ctx, stats);
+    if(status != PTB_OK) {
+        return status;
+    }
+    if(w == 0 || h == 0) {
+        return endCall(ctx, stats);
+    }
+    if(out_rgba == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render: out_rgba is null");
+    }
+    const bool device_io = (opts->flags & PTB_FLAG_DEVICE_IO) != 0U;
+    const bool count_visits = (opts->flags & PTB_FLAG_COUNT_VISITS) != 0U;
+    const int spp = std::max(opts->max_sample_count, 0);
+
+    // tile grid over the rectangle; the reference's tile size when the rectangle is the whole image (worker.cpp:398)
+    int tile = opts->tile_size;
+    if(tile <= 0) {
+        tile = std::max(std::min(std::min(w, h) / 4, 32), 1);
+    }
+    const int tiles_x = (w + tile - 1) / tile;
+    const int tiles_y = (h + tile - 1) / tile;
+    const int shard_count = std::max(opts->shard_count, 1);
+    const int shard_index = std::min(std::max(opts->shard_index, 0), shard_count - 1);
+
+    std::vector<int> owned;
+    for(int t = 0; t < tiles_x * tiles_y; t++) {
+        if(t % shard_count == shard_index) {
+            owned.push_back(t);
+        }
+    }
+
+    const size_t out_bytes = static_cast<size_t>(w) * h * sizeof(float4);
+    float4 *d_out = reinterpret_cast<float4 *>(out_rgba);
+    if(!device_io) {
+        if((status = ctx->io_d.reserve(out_bytes)) != PTB_OK) {
+            return status;
+        }
+        d_out = ctx->io_d.as<float4>();
+    }
+    // pixels of tiles owned by other shards (and everything when spp == 0) stay 0
+    PTB_CUDA(cudaMemsetAsync(d_out, 0, out_bytes, ctx->stream));
+
+    // pixel groups: as many whole tiles as fit the per-sample buffer budget
+    const uint64_t budget_bytes = static_cast<uint64_t>(envLong("PTB_SAMPLE_BUFFER_MB", 16384)) << 20;
+    const uint64_t per_tile_bytes = static_cast<uint64_t>(tile) * tile * std::max(spp, 1) * sizeof(float4);
+    uint64_t tiles_per_group = std::max<uint64_t>(1, budget_bytes / per_tile_bytes);
+    // destinations are 32-bit
+    tiles_per_group = std::min<uint64_t>(tiles_per_group, std::max<uint64_t>(1, (0xFFFFFFFFULL / std::max(spp, 1)) / (static_cast<uint64_t>(tile) * tile)));
+
+    const uint64_t pool_limit = static_cast<uint64_t>(envLong("PTB_POOL_PATHS", 1L << 22));
+    const RenderParams params = makeParams(*camera, *opts);
+    if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK || (status = ctx->visits.reserve(sizeof(VisitCounters))) != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, sizeof(VisitCounters), ctx->stream));
+    PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
+
+    std::vector<uint32_t> pixel_list;
+    for(size_t group_begin = 0; group_begin < owned.size() && spp > 0; group_begin += tiles_per_group) {
+        const size_t group_end = std::min<size_t>(owned.size(), group_begin + tiles_per_group);
+        pixel_list.clear();
+        for(size_t k = group_begin; k < group_end; k++) {
+            const int t = owned[k];
+            const int tx0 = (t % tiles_x) * tile;
+            const int ty0 = (t / tiles_x) * tile;
+            const int tx1 = std::min(tx0 + tile, w);
+            const int ty1 = std::min(ty0 + tile, h);
+            for(int y = ty0; y < ty1; y++) {
+                for(int x = tx0; x < tx1; x++) {
+                    pixel_list.push_back(static_cast<uint32_t>(x0 + x) | (static_cast<uint32_t>(y0 + y) << 16));
+                }
+            }
+        }
+        const uint32_t n_pixels = static_cast<uint32_t>(pixel_list.size());
+        if(n_pixels == 0U) {
+            continue;
+        }
+        const uint64_t total = static_cast<uint64_t>(n_pixels) * spp;
+
+        if((status = ctx->pixel_list.reserve(n_pixels * sizeof(uint32_t))) != PTB_OK || (status = ctx->samples.reserve(total * sizeof(float4))) != PTB_OK) {
+            return status;
+        }
+        // the list is consumed by kernels of this group only; a pageable copy on the stream is ordered before them
+        PTB_CUDA(cudaMemcpyAsync(ctx->pixel_list.ptr, pixel_list.data(), n_pixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+
+        const uint32_t capacity = static_cast<uint32_t>(std::min<uint64_t>(total, pool_limit));
+        PathPool pool{};
+        if((status = carvePool(ctx, capacity, scene->shadow_stride, pool)) != PTB_OK) {
+            return status;
+        }
+
+        for(uint64_t first = 0; first < total; first += capacity) {
+            const uint32_t batch = static_cast<uint32_t>(std::min<uint64_t>(capacity, total - first));
+            const int grid = static_cast<int>((batch + kBlock - 1) / kBlock);
+            {
+                LaunchTimer timer(ctx, 1);
+                generateKernel<<<grid, kBlock, 0, ctx->stream>>>(pool, params, ctx->pixel_list.as<uint32_t>(), n_pixels, first, batch,
+                                                                 ctx->queue_a.as<uint32_t>(), ctx->counters.as<uint32_t>(), kCountQueueA);
+            }
+            PTB_CUDA(cudaGetLastError());
+            if(stats != nullptr) {
+                stats->samples += batch;
+                stats->kernel_launches += 1;
+            }
+            if((status = runBounces(scene, pool, params, batch, ctx->samples.as<float4>(), count_visits, stats)) != PTB_OK) {
+                return status;
+            }
+        }
+
+        ResolveParams rp{};
+        rp.min_sample_count = opts->min_sample_count;
+        rp.max_sample_count = spp;
+        rp.n_pixels = n_pixels;
+        rp.rect_x0 = x0;
+        rp.rect_y0 = y0;
+        rp.rect_w = w;
+        {
+            LaunchTimer timer(ctx, 1);
+            resolveKernel<<<(n_pixels + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(rp, ctx->samples.as<float4>(), ctx->pixel_list.as<uint32_t>(), d_out);
+        }
+        PTB_CUDA(cudaGetLastError());
+        if(stats != nullptr) {
+            stats->kernel_launches += 1;
+        }
+    }
+
+    if(!device_io) {
+        PTB_CUDA(cudaMemcpyAsync(out_rgba, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    status = endCall(ctx, stats);
+    if(status != PTB_OK) {
+        return status;
+    }
+    return finishStats(ctx, count_visits, stats);
+}
+
+// ---------------------------------------------------------------------------------------------------- unit entries
+
+int ptb_camera_shoot(ptb_context *ctx, const ptb_camera *camera, uint64_t n, const float *xy, float pixel_width, float pixel_height,
+                     uint64_t *engine_states, float *rays_out) {
+    if(ctx == nullptr || camera == nullptr || (n > 0 && (xy == nullptr || engine_states == nullptr || rays_out == nullptr))) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_camera_shoot: null argument");
+    }
+    int status = useDevice(ctx);
+    if(status != PTB_OK || n == 0) {
+        return status;
+    }
+    if((status = ctx->io_a.reserve(n * 2 * sizeof(float))) != PTB_OK || (status = ctx->io_b.reserve(n * sizeof(uint64_t))) != PTB_OK ||
+       (status = ctx->io_c.reserve(n * 6 * sizeof(float))) != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_a.ptr, xy, n * 2 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_b.ptr, engine_states, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    cameraKernel<<<static_cast<unsigned>((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(*camera, n, ctx->io_a.as<float>(), pixel_width, pixel_height,
+                                                                                                 ctx->io_b.as<uint64_t>(), ctx->io_c.as<float>());
+    PTB_CUDA(cudaGetLastError());
+    PTB_CUDA(cudaMemcpyAsync(rays_out, ctx->io_c.ptr, n * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaMemcpyAsync(engine_states, ctx->io_b.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+int ptb_aperture_sample(ptb_context *ctx, uint32_t aperture_kind, float hexagon_horizontal_ratio, uint64_t n, uint64_t *engine_states, float *out) {
+    if(ctx == nullptr || (n > 0 && (engine_states == nullptr || out == nullptr))) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_aperture_sample: null argument");
+    }
+    if(aperture_kind != PTB_APERTURE_CIRCULAR && aperture_kind != PTB_APERTURE_HEXAGONAL) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_aperture_sample: unknown aperture kind");
+    }
+    int status = useDevice(ctx);
+    if(status != PTB_OK || n == 0) {
+        return status;
+    }
+    if((status = ctx->io_b.reserve(n * sizeof(uint64_t))) != PTB_OK || (status = ctx->io_c.reserve(n * 2 * sizeof(float))) != PTB_OK) {
+        return status;
+    }
+    ptb_camera camera{};
+    camera.aperture_kind = aperture_kind;
+    camera.hexagon_horizontal_ratio = std::min(std::max(hexagon_horizontal_ratio, 0.0F), 1.0F);
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_b.ptr, engine_states, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    apertureKernel<<<static_cast<unsigned>((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(camera, n, ctx->io_b.as<uint64_t>(), ctx->io_c.as<float>());
+    PTB_CUDA(cudaGetLastError());
+    PTB_CUDA(cudaMemcpyAsync(out, ctx->io_c.ptr, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaMemcpyAsync(engine_states, ctx->io_b.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+int ptb_sample_lights(ptb_scene *scene, const float pos[3], uint64_t *engine_state, uint32_t max_out, float *out, uint32_t *n_out) {
+    if(scene == nullptr || pos == nullptr || engine_state == nullptr || n_out == nullptr || (max_out > 0 && out == nullptr)) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_sample_lights: null argument");
+    }
+    ptb_context *ctx = scene->ctx;
+    int status = useDevice(ctx);
+    if(status != PTB_OK) {
+        return status;
+    }
+    const size_t floats = 4 + 8 * static_cast<size_t>(max_out);
+    if((status = ctx->io_a.reserve(floats * sizeof(float))) != PTB_OK || (status = ctx->io_b.reserve(sizeof(uint64_t))) != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_b.ptr, engine_state, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    sampleLightsKernel<<<1, 32, 0, ctx->stream>>>(scene->dev, pos[0], pos[1], pos[2], ctx->io_b.as<uint64_t>(), max_out, ctx->io_a.as<float>());
+    PTB_CUDA(cudaGetLastError());
+    std::vector<float> host(floats);
+    PTB_CUDA(cudaMemcpyAsync(host.data(), ctx->io_a.ptr, floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaMemcpyAsync(engine_state, ctx->io_b.ptr, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint32_t n = 0;
+    std::memcpy(&n, &host[0], sizeof(uint32_t));
+    *n_out = n;
+    const uint32_t copy = std::min(n, max_out);
+    if(copy > 0) {
+        std::memcpy(out, &host[4], 8 * static_cast<size_t>(copy) * sizeof(float));
+    }
+    return PTB_OK;
+}
+
+int ptb_aabb_intersect(ptb_context *ctx, const float low[3], const float high[3], uint64_t n_rays, const float *rays, float *t_out) {
+    if(ctx == nullptr || low == nullptr || high == nullptr || (n_rays > 0 && (rays == nullptr || t_out == nullptr))) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_aabb_intersect: null argument");
+    }
+    int status = useDevice(ctx);
+    if(status != PTB_OK || n_rays == 0) {
+        return status;
+    }
+    if((status = ctx->io_a.reserve(n_rays * 6 * sizeof(float))) != PTB_OK || (status = ctx->io_b.reserve(n_rays * sizeof(float))) != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_a.ptr, rays, n_rays * 6 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    aabbKernel<<<static_cast<unsigned>((n_rays + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(low[0], low[1], low[2], high[0], high[1], high[2],
+                                                                                                    ctx->io_a.as<float>(), n_rays, ctx->io_b.as<float>());
+    PTB_CUDA(cudaGetLastError());
+    PTB_CUDA(cudaMemcpyAsync(t_out, ctx->io_b.ptr, n_rays * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+int ptb_prim_intersect(ptb_context *ctx, const ptb_prim *prim, uint64_t n_rays, const float *rays, float *t_out) {
+    if(ctx == nullptr || prim == nullptr || (n_rays > 0 && (rays == nullptr || t_out == nullptr))) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_prim_intersect: null argument");
+    }
+    if(prim->kind > PTB_PRIM_NULL) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_prim_intersect: unknown primitive kind");
+    }
+    int status = useDevice(ctx);
+    if(status != PTB_OK || n_rays == 0) {
+        return status;
+    }
+    const float *p = prim->p;
+    float4 geom[3];
+    uint32_t flags = prim->kind & kKindMask;
+    if(prim->kind == PTB_PRIM_TRIANGLE) {
+        if(prim->cull_backface != 0U) {
+            flags |= kCullBit;
+        }
+        geom[0] = make_float4(p[0], p[1], p[2], 0.0F);
+        geom[1] = make_float4(p[3] - p[0], p[4] - p[1], p[5] - p[2], 0.0F);
+        geom[2] = make_float4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0F);
+    }
+    else {
+        geom[0] = make_float4(p[0], p[1], p[2], 0.0F);
+        geom[1] = make_float4(p[3], p[3] * p[3], 0.0F, 0.0F);
+        geom[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+    }
+    std::memcpy(&geom[0].w, &flags, sizeof(flags));
+    if((status = ctx->io_a.reserve(n_rays * 6 * sizeof(float))) != PTB_OK || (status = ctx->io_b.reserve(n_rays * sizeof(float))) != PTB_OK ||
+       (status = ctx->io_c.reserve(sizeof(geom))) != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_a.ptr, rays, n_rays * 6 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_c.ptr, geom, sizeof(geom), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    DeviceScene one{};
+    one.geom = ctx->io_c.as<float4>();
+    one.n_prims = 1;
+    primKernel<<<static_cast<unsigned>((n_rays + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(one, ctx->io_a.as<float>(), n_rays, ctx->io_b.as<float>());
+    PTB_CUDA(cudaGetLastError());
+    PTB_CUDA(cudaMemcpyAsync(t_out, ctx->io_b.ptr, n_rays * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+namespace {
+
+    // geometry lanes (differenced edges), shading lanes and un-differenced lanes of one primitive
+    struct PrimLanes {
+        float4 geom[3];
+        float4 shade[3];
+        float4 raw[3];
+        uint32_t flags;
+    };
+
+    PrimLanes lanesOf(const ptb_prim &prim) {
+        PrimLanes l{};
+        const float *p = prim.p;
+        l.flags = prim.kind & kKindMask;
+        if(prim.kind == PTB_PRIM_TRIANGLE) {
+            if(prim.cull_backface != 0U) {
+                l.flags |= kCullBit;
+            }
+            l.geom[0] = make_float4(p[0], p[1], p[2], 0.0F);
+            l.geom[1] = make_float4(p[3] - p[0], p[4] - p[1], p[5] - p[2], 0.0F);
+            l.geom[2] = make_float4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0F);
+            l.shade[0] = make_float4(p[9], p[10], p[11], 0.0F);
+            l.shade[1] = make_float4(p[12], p[13], p[14], 0.0F);
+            l.shade[2] = make_float4(p[15], p[16], p[17], 0.0F);
+            l.raw[0] = make_float4(p[0], p[1], p[2], 0.0F);
+            l.raw[1] = make_float4(p[3], p[4], p[5], 0.0F);
+            l.raw[2] = make_float4(p[6], p[7], p[8], 0.0F);
+        }
+        else if(prim.kind == PTB_PRIM_SPHERE) {
+            l.geom[0] = make_float4(p[0], p[1], p[2], 0.0F);
+            l.geom[1] = make_float4(p[3], p[3] * p[3], 0.0F, 0.0F);
+            l.raw[0] = l.geom[0];
+            l.raw[1] = l.geom[1];
+        }
+        std::memcpy(&l.geom[0].w, &l.flags, sizeof(uint32_t));
+        return l;
+    }
+
+}
+
+int ptb_prim_normal(ptb_context *ctx, const ptb_prim *prim, uint64_t n, const float *positions, float *normals_out) {
+    if(ctx == nullptr || prim == nullptr || (n > 0 && (positions == nullptr || normals_out == nullptr))) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_prim_normal: null argument");
+    }
+    if(prim->kind > PTB_PRIM_NULL) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_prim_normal: unknown primitive kind");
+    }
+    int status = useDevice(ctx);
+    if(status != PTB_OK || n == 0) {
+        return status;
+    }
+    const PrimLanes lanes = lanesOf(*prim);
+    if((status = ctx->io_a.reserve(n * 3 * sizeof(float))) != PTB_OK || (status = ctx->io_b.reserve(n * 3 * sizeof(float))) != PTB_OK ||
+       (status = ctx->io_c.reserve(6 * sizeof(float4))) != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_a.ptr, positions, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_c.ptr, lanes.geom, 3 * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_c.as<float4>() + 3, lanes.shade, 3 * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    DeviceScene one{};
+    one.geom = ctx->io_c.as<float4>();
+    one.shade = ctx->io_c.as<float4>() + 3;
+    one.n_prims = 1;
+    primNormalKernel<<<static_cast<unsigned>((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(one, n, ctx->io_a.as<float>(), ctx->io_b.as<float>());
+    PTB_CUDA(cudaGetLastError());
+    PTB_CUDA(cudaMemcpyAsync(normals_out, ctx->io_b.ptr, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+int ptb_prim_sample(ptb_context *ctx, const ptb_prim *prim, uint64_t n, uint64_t *engine_states, float *out) {
+    if(ctx == nullptr || prim == nullptr || (n > 0 && (engine_states == nullptr || out == nullptr))) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_prim_sample: null argument");
+    }
+    if(prim->kind > PTB_PRIM_NULL) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_prim_sample: unknown primitive kind");
+    }
+    int status = useDevice(ctx);
+    if(status != PTB_OK || n == 0) {
+        return status;
+    }
+    const PrimLanes lanes = lanesOf(*prim);
+    if((status = ctx->io_a.reserve(n * sizeof(uint64_t))) != PTB_OK || (status = ctx->io_b.reserve(n * 5 * sizeof(float))) != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_a.ptr, engine_states, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    primSampleKernel<<<static_cast<unsigned>((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(lanes.raw[0], lanes.raw[1], lanes.raw[2], lanes.flags, n,
+                                                                                                     ctx->io_a.as<uint64_t>(), ctx->io_b.as<float>());
+    PTB_CUDA(cudaGetLastError());
+    PTB_CUDA(cudaMemcpyAsync(out, ctx->io_b.ptr, n * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaMemcpyAsync(engine_states, ctx->io_a.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+int ptb_bsdf_propagate(ptb_context *ctx, const ptb_material *material, float epsilon, uint64_t n, const float *in, uint64_t *engine_states, float *out) {
+    if(ctx == nullptr || material == nullptr || (n > 0 && (in == nullptr || engine_states == nullptr || out == nullptr))) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_bsdf_propagate: null argument");
+    }
+    if(material->bsdf > PTB_BSDF_MIRROR) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_bsdf_propagate: unknown BSDF kind");
+    }
+    int status = useDevice(ctx);
+    if(status != PTB_OK || n == 0) {
+        return status;
+    }
+    if((status = ctx->io_a.reserve(n * 9 * sizeof(float))) != PTB_OK || (status = ctx->io_b.reserve(n * sizeof(uint64_t))) != PTB_OK ||
+       (status = ctx->io_c.reserve(n * 8 * sizeof(float))) != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_a.ptr, in, n * 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_b.ptr, engine_states, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    bsdfPropagateKernel<<<static_cast<unsigned>((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(*material, epsilon, n, ctx->io_a.as<float>(),
+                                                                                                        ctx->io_b.as<uint64_t>(), ctx->io_c.as<float>());
+    PTB_CUDA(cudaGetLastError());
+    PTB_CUDA(cudaMemcpyAsync(out, ctx->io_c.ptr, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaMemcpyAsync(engine_states, ctx->io_b.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+int ptb_bsdf_spectrum(ptb_context *ctx, const ptb_material *material, uint32_t synthetic, uint64_t n, const float *in, float *out) {
+    if(ctx == nullptr || material == nullptr || (n > 0 && (in == nullptr || out == nullptr))) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_bsdf_spectrum: null argument");
+    }
+    if(material->bsdf > PTB_BSDF_MIRROR) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_bsdf_spectrum: unknown BSDF kind");
+    }
+    int status = useDevice(ctx);
+    if(status != PTB_OK || n == 0) {
+        return status;
+    }
+    if((status = ctx->io_a.reserve(n * 13 * sizeof(float))) != PTB_OK || (status = ctx->io_c.reserve(n * 6 * sizeof(float))) != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_a.ptr, in, n * 13 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    bsdfSpectrumKernel<<<static_cast<unsigned>((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(*material, synthetic, n, ctx->io_a.as<float>(),
+                                                                                                       ctx->io_c.as<float>());
+    PTB_CUDA(cudaGetLastError());
+    PTB_CUDA(cudaMemcpyAsync(out, ctx->io_c.ptr, n * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,229 @@
+// BVH traversal + primitive tests on the flattened scene.
+//
+// Result-identical restatement of
+//   Scene::getIntersection          reference src/scene/scene.cpp:210-220
+//   impl::getChildIntersection      reference src/scene/scene.cpp:104-150   (recursive, near child first)
+//   AABB::getIntersection           reference src/scene/bounding_box.cpp:38-73
+//   Triangle::getIntersection       reference src/scene/object.cpp:146-182  (Moeller-Trumbore, |det| <= 1e-6 rejected)
+//   Sphere::getIntersection         reference src/scene/object.cpp:72-84    (near root only)
+// as an iterative loop with a short per-thread stack of deferred far children:
+//   - both child boxes of an inner record are tested; the child with the smaller entry distance is "close",
+//     the RIGHT child on ties (scene.cpp:122-123 uses `left_t < right_t`);
+//   - a child is entered iff 0 <= entry < best_t (strict); a deferred far child is re-tested against the current
+//     best_t when popped (the recursion's `far_t < t_max` after `t_max = min(t_max, close_t)`, scene.cpp:130-138);
+//   - a leaf hit replaces the best iff t >= 0 and (no best yet or t <= best_t): the later-visited primitive wins
+//     ties, as the recursion's `close_t < far_hit_t ? close : far` does (scene.cpp:141-146).
+#ifndef PTB_TRAVERSE_CUH
+#define PTB_TRAVERSE_CUH
+
+#include "device_scene.cuh"
+
+namespace ptb {
+
+    constexpr int kStackCapacity = 64; // deferred far siblings only; the host asserts bvh depth <= capacity
+
+    struct RayInv {
+        V3 o;
+        V3 d;
+        V3 inv; // 1/d, or FLT_MAX where d == 0 (bounding_box.cpp:43-45)
+    };
+
+    PTB_DEV float slabReciprocal(float d) {
+        return fabsf(d) > 0.0F ? 1.0F / d : kFloatMax;
+    }
+
+    PTB_DEV RayInv makeRay(V3 o, V3 d) {
+        RayInv r;
+        r.o = o;
+        r.d = d;
+        r.inv = mk3(slabReciprocal(d.x), slabReciprocal(d.y), slabReciprocal(d.z));
+        return r;
+    }
+
+    // entry distance, 0 if the origin is inside, -1 on a miss (bounding_box.cpp:47-72)
+    PTB_DEV float slab(const RayInv &r, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+        const float t1 = (lox - r.o.x) * r.inv.x;
+        const float t2 = (hix - r.o.x) * r.inv.x;
+        const float t3 = (loy - r.o.y) * r.inv.y;
+        const float t4 = (hiy - r.o.y) * r.inv.y;
+        const float t5 = (loz - r.o.z) * r.inv.z;
+        const float t6 = (hiz - r.o.z) * r.inv.z;
+        const float t_min = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+        const float t_max = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+        if(t_max < 0.0F || t_min > t_max) {
+            return -1.0F;
+        }
+        return t_min < 0.0F ? 0.0F : t_min;
+    }
+
+    // object.cpp:146-182 with ab = b - a and ac = c - a taken from the geometry lanes
+    PTB_DEV float hitTriangle(const RayInv &r, V3 a, V3 ab, V3 ac, bool cull) {
+        const V3 pvec = cross(r.d, ac);
+        const float det = dot(ab, pvec);
+        if(cull) {
+            if(det <= 1E-6F) {
+                return -1.0F;
+            }
+        }
+        else {
+            if(fabsf(det) <= 1E-6F) {
+                return -1.0F;
+            }
+        }
+        const float inv_det = 1.0F / det;
+        const V3 tvec = r.o - a;
+        const float u = dot(tvec, pvec) * inv_det;
+        if(u < 0.0F || u > 1.0F) {
+            return -1.0F;
+        }
+        const V3 qvec = cross(tvec, ab);
+        const float v = dot(r.d, qvec) * inv_det;
+        if(v < 0.0F || u + v > 1.0F) {
+            return -1.0F;
+        }
+        return dot(ac, qvec) * inv_det;
+    }
+
+    // object.cpp:72-84
+    PTB_DEV float hitSphere(const RayInv &r, V3 origin, float radius2) {
+        const V3 co = r.o - origin;
+        const float d = dot(r.d, co);
+        const float discriminant = d * d - length2(co) + radius2;
+        if(discriminant >= 0.0F) {
+            return -(d + sqrtf(discriminant));
+        }
+        return -1.0F;
+    }
+
+    PTB_DEV float hitSlot(const DeviceScene &s, const RayInv &r, uint32_t slot) {
+        const float4 *g = s.geom + 3 * static_cast<size_t>(slot);
+        const float4 g0 = __ldg(g);
+        const float4 g1 = __ldg(g + 1);
+        const uint32_t flags = __float_as_uint(g0.w);
+        const uint32_t kind = flags & kKindMask;
+        if(kind == PTB_PRIM_TRIANGLE) {
+            const float4 g2 = __ldg(g + 2);
+            return hitTriangle(r, mk3(g0.x, g0.y, g0.z), mk3(g1.x, g1.y, g1.z), mk3(g2.x, g2.y, g2.z), (flags & kCullBit) != 0U);
+        }
+        if(kind == PTB_PRIM_SPHERE) {
+            return hitSphere(r, mk3(g0.x, g0.y, g0.z), g1.y);
+        }
+        return -1.0F; // NullObject (object.cpp:52-54)
+    }
+
+    struct Hit {
+        float t;      // < 0: miss
+        int32_t slot; // -1: none
+    };
+
+    // ANY_HIT = false: closest hit, limit ignored.
+    // ANY_HIT = true : returns at the first primitive with 0 <= t < limit (slot = that primitive, t = its distance).
+    template<bool ANY_HIT, bool COUNT>
+    PTB_DEV Hit traverse(const DeviceScene &s, const RayInv &r, float limit, VisitCounters *counters) {
+        Hit hit;
+        hit.t = -1.0F;
+        hit.slot = -1;
+        if(s.n_prims == 0U) {
+            return hit;
+        }
+
+        // Scene::getIntersection tests the root box first and passes its (negative) result through on a miss
+        const float root_t = slab(r, s.root_lo[0], s.root_lo[1], s.root_lo[2], s.root_hi[0], s.root_hi[1], s.root_hi[2]);
+        if(!(root_t >= 0.0F)) {
+            hit.t = root_t;
+            return hit;
+        }
+
+        float best_t = ANY_HIT ? limit : kFloatMax;
+        int32_t stack_node[kStackCapacity];
+        float stack_t[kStackCapacity];
+        int sp = 0;
+        int32_t node = s.root_ref;
+        unsigned long long n_inner = 0;
+        unsigned long long n_leaf = 0;
+
+        for(;;) {
+            while(node >= 0) {
+                const float4 *rec = s.nodes + 4 * static_cast<size_t>(node);
+                const float4 n0 = __ldg(rec);
+                const float4 n1 = __ldg(rec + 1);
+                const float4 n2 = __ldg(rec + 2);
+                const float4 n3 = __ldg(rec + 3);
+                if(COUNT) {
+                    n_inner++;
+                }
+                const float lt = slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+                const float rt = slab(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+                const int32_t left = __float_as_int(n3.x);
+                const int32_t right = __float_as_int(n3.y);
+                const bool left_first = lt < rt;
+                const float ct = left_first ? lt : rt;
+                const float ft = left_first ? rt : lt;
+                const int32_t cnode = left_first ? left : right;
+                const int32_t fnode = left_first ? right : left;
+                const bool vc = ct >= 0.0F && ct < best_t;
+                const bool vf = ft >= 0.0F && ft < best_t;
+                if(vc) {
+                    if(vf) {
+                        stack_node[sp] = fnode;
+                        stack_t[sp] = ft;
+                        sp++;
+                    }
+                    node = cnode;
+                }
+                else if(vf) {
+                    node = fnode;
+                }
+                else {
+                    node = INT32_MIN; // nothing to enter: pop
+                    break;
+                }
+            }
+
+            if(node != INT32_MIN) {
+                const uint32_t slot = static_cast<uint32_t>(~node);
+                if(COUNT) {
+                    n_leaf++;
+                }
+                const float t = hitSlot(s, r, slot);
+                if(ANY_HIT) {
+                    if(t >= 0.0F && t < limit) {
+                        hit.t = t;
+                        hit.slot = static_cast<int32_t>(slot);
+                        break;
+                    }
+                }
+                else {
+                    if(t >= 0.0F && (hit.slot < 0 || t <= best_t)) {
+                        best_t = t;
+                        hit.t = t;
+                        hit.slot = static_cast<int32_t>(slot);
+                    }
+                }
+            }
+
+            // pop the next deferred far child that still beats the best distance
+            bool found = false;
+            while(sp > 0) {
+                sp--;
+                if(stack_t[sp] < best_t) {
+                    node = stack_node[sp];
+                    found = true;
+                    break;
+                }
+            }
+            if(!found) {
+                break;
+            }
+        }
+
+        if(COUNT && counters != nullptr) {
+            atomicAdd(&counters->inner, n_inner);
+            atomicAdd(&counters->leaf, n_leaf);
+        }
+        return hit;
+    }
+
+}
+
+#endif

@@ -1,0 +1,296 @@
+// PNG reading/writing on zlib (no libpng in this toolchain).  Host-side, off the render path.
+//
+// Writer contract (reference src/image/image_io.cpp:109-152): non-interlaced 8-bit RGBA, each channel
+// round(255 * v) clamped to [0, 255].  Reader contract (:31-85): 8-bit images are expanded to RGBA and mapped to
+// value / 255; colour types grey, grey+alpha, RGB, RGBA and palette are accepted.  Failures throw std::logic_error.
+#include <PathTrace/image/image_io.h>
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+#include <stdexcept>
+#include <vector>
+
+namespace {
+
+    constexpr unsigned char kSignature[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+
+    void putBE32(std::vector<unsigned char> &out, uint32_t v) {
+        out.push_back(static_cast<unsigned char>(v >> 24));
+        out.push_back(static_cast<unsigned char>(v >> 16));
+        out.push_back(static_cast<unsigned char>(v >> 8));
+        out.push_back(static_cast<unsigned char>(v));
+    }
+
+    uint32_t getBE32(const unsigned char *p) {
+        return (static_cast<uint32_t>(p[0]) << 24) | (static_cast<uint32_t>(p[1]) << 16) | (static_cast<uint32_t>(p[2]) << 8) | p[3];
+    }
+
+    void putChunk(std::vector<unsigned char> &out, const char type[4], const unsigned char *payload, std::size_t length) {
+        putBE32(out, static_cast<uint32_t>(length));
+        const std::size_t type_at = out.size();
+        out.insert(out.end(), type, type + 4);
+        out.insert(out.end(), payload, payload + length);
+        const uint32_t crc = static_cast<uint32_t>(crc32(0L, out.data() + type_at, static_cast<uInt>(4 + length)));
+        putBE32(out, crc);
+    }
+
+    unsigned char quantise(float v) {
+        const float scaled = std::round(v * 255.0F);
+        if(!(scaled > 0.0F)) {
+            return 0;
+        }
+        return scaled >= 255.0F ? 255 : static_cast<unsigned char>(scaled);
+    }
+
+    int paeth(int a, int b, int c) {
+        const int p = a + b - c;
+        const int pa = std::abs(p - a);
+        const int pb = std::abs(p - b);
+        const int pc = std::abs(p - c);
+        if(pa <= pb && pa <= pc) {
+            return a;
+        }
+        return pb <= pc ? b : c;
+    }
+
+}
+
+namespace io {
+
+    void writeRGBImage(std::basic_ostream<char> &stream, const Image<Color<float>> &image) noexcept(false) {
+        const int width = image.getWidth();
+        const int height = image.getHeight();
+        if(width <= 0 || height <= 0) {
+            throw std::logic_error("writeRGBImage: empty image");
+        }
+
+        // filter type 0 scanlines
+        std::vector<unsigned char> raw(static_cast<std::size_t>(height) * (1 + 4 * static_cast<std::size_t>(width)));
+        std::size_t w = 0;
+        for(int y = 0; y < height; y++) {
+            raw[w++] = 0;
+            for(int x = 0; x < width; x++) {
+                const Color<float> pixel = image(x, y);
+                for(int channel = 0; channel < 4; channel++) {
+                    raw[w++] = quantise(pixel[channel]);
+                }
+            }
+        }
+
+        uLongf packed_size = compressBound(static_cast<uLong>(raw.size()));
+        std::vector<unsigned char> packed(packed_size);
+        if(compress2(packed.data(), &packed_size, raw.data(), static_cast<uLong>(raw.size()), Z_DEFAULT_COMPRESSION) != Z_OK) {
+            throw std::logic_error("writeRGBImage: deflate failed");
+        }
+
+        std::vector<unsigned char> out(kSignature, kSignature + 8);
+        std::vector<unsigned char> header;
+        putBE32(header, static_cast<uint32_t>(width));
+        putBE32(header, static_cast<uint32_t>(height));
+        header.push_back(8); // bit depth
+        header.push_back(6); // RGBA
+        header.push_back(0); // deflate
+        header.push_back(0); // adaptive filtering
+        header.push_back(0); // no interlace
+        putChunk(out, "IHDR", header.data(), header.size());
+        putChunk(out, "IDAT", packed.data(), packed_size);
+        putChunk(out, "IEND", nullptr, 0);
+
+        stream.write(reinterpret_cast<const char *>(out.data()), static_cast<std::streamsize>(out.size()));
+        if(!stream) {
+            throw std::logic_error("writeRGBImage: stream write failed");
+        }
+    }
+
+    void writeRGBImage(const std::string &path, const Image<Color<float>> &image) noexcept(false) {
+        std::ofstream stream(path, std::ios_base::out | std::ios_base::binary);
+        if(!stream) {
+            throw std::logic_error("writeRGBImage: cannot open " + path);
+        }
+        writeRGBImage(stream, image);
+    }
+
+    void writeRGBImage(const std::filesystem::path &path, const Image<Color<float>> &image) noexcept(false) {
+        writeRGBImage(path.string(), image);
+    }
+
+    Image<Color<float>> readRGBImage(std::basic_istream<char> &stream) noexcept(false) {
+        const std::vector<unsigned char> file((std::istreambuf_iterator<char>(stream)), std::istreambuf_iterator<char>());
+        if(file.size() < 8 || std::memcmp(file.data(), kSignature, 8) != 0) {
+            throw std::logic_error("readRGBImage: not a PNG stream");
+        }
+
+        uint32_t width = 0;
+        uint32_t height = 0;
+        int bit_depth = 0;
+        int colour_type = -1;
+        int interlace = 0;
+        std::vector<unsigned char> palette;
+        std::vector<unsigned char> transparency;
+        std::vector<unsigned char> packed;
+        bool ended = false;
+
+        std::size_t at = 8;
+        while(!ended && at + 12 <= file.size()) {
+            const uint32_t length = getBE32(&file[at]);
+            if(at + 12 + static_cast<std::size_t>(length) > file.size()) {
+                throw std::logic_error("readRGBImage: truncated chunk");
+            }
+            const unsigned char *type = &file[at + 4];
+            const unsigned char *payload = &file[at + 8];
+            const uint32_t crc = getBE32(&file[at + 8 + length]);
+            if(crc != static_cast<uint32_t>(crc32(0L, type, static_cast<uInt>(4 + length)))) {
+                throw std::logic_error("readRGBImage: chunk checksum mismatch");
+            }
+            if(std::memcmp(type, "IHDR", 4) == 0) {
+                if(length != 13) {
+                    throw std::logic_error("readRGBImage: bad header");
+                }
+                width = getBE32(payload);
+                height = getBE32(payload + 4);
+                bit_depth = payload[8];
+                colour_type = payload[9];
+                interlace = payload[12];
+            }
+            else if(std::memcmp(type, "PLTE", 4) == 0) {
+                palette.assign(payload, payload + length);
+            }
+            else if(std::memcmp(type, "tRNS", 4) == 0) {
+                transparency.assign(payload, payload + length);
+            }
+            else if(std::memcmp(type, "IDAT", 4) == 0) {
+                packed.insert(packed.end(), payload, payload + length);
+            }
+            else if(std::memcmp(type, "IEND", 4) == 0) {
+                ended = true;
+            }
+            at += 12 + static_cast<std::size_t>(length);
+        }
+
+        int channels = 0;
+        switch(colour_type) {
+            case 0:
+                channels = 1;
+                break;
+            case 2:
+                channels = 3;
+                break;
+            case 3:
+                channels = 1;
+                break;
+            case 4:
+                channels = 2;
+                break;
+            case 6:
+                channels = 4;
+                break;
+            default:
+                throw std::logic_error("readRGBImage: unsupported colour type");
+        }
+        if(width == 0 || height == 0 || width > 65535U || height > 65535U || bit_depth != 8 || interlace != 0) {
+            throw std::logic_error("readRGBImage: only non-interlaced 8-bit images are supported");
+        }
+
+        const std::size_t stride = static_cast<std::size_t>(width) * channels;
+        std::vector<unsigned char> raw(static_cast<std::size_t>(height) * (stride + 1));
+        uLongf raw_size = static_cast<uLongf>(raw.size());
+        if(uncompress(raw.data(), &raw_size, packed.data(), static_cast<uLong>(packed.size())) != Z_OK || raw_size != raw.size()) {
+            throw std::logic_error("readRGBImage: inflate failed");
+        }
+
+        // undo the scanline filters in place
+        std::vector<unsigned char> pixels(static_cast<std::size_t>(height) * stride);
+        for(uint32_t y = 0; y < height; y++) {
+            const unsigned char filter = raw[y * (stride + 1)];
+            const unsigned char *in = &raw[y * (stride + 1) + 1];
+            unsigned char *row = &pixels[y * stride];
+            const unsigned char *above = y > 0 ? &pixels[(y - 1) * stride] : nullptr;
+            for(std::size_t i = 0; i < stride; i++) {
+                const int left = i >= static_cast<std::size_t>(channels) ? row[i - channels] : 0;
+                const int up = above != nullptr ? above[i] : 0;
+                const int up_left = (above != nullptr && i >= static_cast<std::size_t>(channels)) ? above[i - channels] : 0;
+                int predicted = 0;
+                switch(filter) {
+                    case 0:
+                        predicted = 0;
+                        break;
+                    case 1:
+                        predicted = left;
+                        break;
+                    case 2:
+                        predicted = up;
+                        break;
+                    case 3:
+                        predicted = (left + up) / 2;
+                        break;
+                    case 4:
+                        predicted = paeth(left, up, up_left);
+                        break;
+                    default:
+                        throw std::logic_error("readRGBImage: unknown scanline filter");
+                }
+                row[i] = static_cast<unsigned char>(in[i] + predicted);
+            }
+        }
+
+        Image<Color<float>> image(static_cast<int>(width), static_cast<int>(height));
+        for(uint32_t y = 0; y < height; y++) {
+            for(uint32_t x = 0; x < width; x++) {
+                const unsigned char *p = &pixels[y * stride + static_cast<std::size_t>(x) * channels];
+                unsigned char rgba[4] = {0, 0, 0, 255};
+                switch(colour_type) {
+                    case 0:
+                        rgba[0] = rgba[1] = rgba[2] = p[0];
+                        break;
+                    case 2:
+                        rgba[0] = p[0];
+                        rgba[1] = p[1];
+                        rgba[2] = p[2];
+                        break;
+                    case 3: {
+                        const std::size_t entry = p[0];
+                        if(3 * entry + 2 >= palette.size()) {
+                            throw std::logic_error("readRGBImage: palette index out of range");
+                        }
+                        rgba[0] = palette[3 * entry];
+                        rgba[1] = palette[3 * entry + 1];
+                        rgba[2] = palette[3 * entry + 2];
+                        if(entry < transparency.size()) {
+                            rgba[3] = transparency[entry];
+                        }
+                        break;
+                    }
+                    case 4:
+                        rgba[0] = rgba[1] = rgba[2] = p[0];
+                        rgba[3] = p[1];
+                        break;
+                    default:
+                        std::memcpy(rgba, p, 4);
+                        break;
+                }
+                image(static_cast<int>(x), static_cast<int>(y)) =
+                  Color<float>(rgba[0] / 255.0F, rgba[1] / 255.0F, rgba[2] / 255.0F, rgba[3] / 255.0F);
+            }
+        }
+        return image;
+    }
+
+    Image<Color<float>> readRGBImage(const std::string &path) noexcept(false) {
+        std::ifstream stream(path, std::ios_base::in | std::ios_base::binary);
+        if(!stream) {
+            throw std::logic_error("readRGBImage: cannot open " + path);
+        }
+        return readRGBImage(stream);
+    }
+
+    Image<Color<float>> readRGBImage(const std::filesystem::path &path) noexcept(false) {
+        return readRGBImage(path.string());
+    }
+
+}

@@ -1,0 +1,126 @@
+// Render entry points on top of ptb_render (the wavefront path tracer).
+//
+// Mapping of the reference's control flow (src/worker.cpp:328-424):
+//   processJob   tile grid + thread pool + per-thread engines  ->  one ptb_render over the whole frame (the GPU grid
+//                is the worker pool); the progress callback fires from the calling thread once per tile, in order
+//   processItem  sequential per-pixel sampling with one engine ->  ptb_render over the tile's rectangle; the engine
+//                supplies the job key of the device's counter-based generator
+// The per-pixel statistics (batch Welford, adaptive acceptance, candidate merge) run in the resolve kernel.
+#include "device.h"
+
+#include <PathTrace/worker.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <stdexcept>
+
+namespace {
+
+    long envLong(const char *name, long fallback) {
+        const char *v = std::getenv(name);
+        return (v == nullptr || *v == '\0') ? fallback : std::atol(v);
+    }
+
+    ptb_render_opts makeOpts(const RenderOptions &options, uint64_t seed, uint32_t rng_mode) {
+        const ptb::RenderControl &control = ptb::renderControl();
+        ptb_render_opts opts{};
+        opts.image_width = options.image_width;
+        opts.image_height = options.image_height;
+        opts.min_sample_count = options.min_sample_count;
+        opts.max_sample_count = options.max_sample_count;
+        opts.epsilon = options.epsilon;
+        opts.max_depth = control.max_depth;
+        opts.rng_mode = rng_mode;
+        opts.flags = (control.any_hit_shadows ? PTB_FLAG_ANY_HIT_SHADOWS : 0U) | (control.skip_null_shadows ? PTB_FLAG_SKIP_NULL_SHADOWS : 0U);
+        opts.seed = seed;
+        opts.shard_count = 1;
+        return opts;
+    }
+
+    ptb_camera lowerCamera(const Camera &camera) {
+        ptb_camera pod;
+        if(!camera.lower(pod)) {
+            throw std::logic_error("PathTrace (B200): the camera uses a user ApertureSampler subclass, which cannot run on the GPU");
+        }
+        return pod;
+    }
+
+    Image<> renderRect(const FrameRenderJob &job, int x0, int y0, int w, int h, int tile_size, uint64_t seed) {
+        Image<> image(std::max(w, 0), std::max(h, 0));
+        if(w <= 0 || h <= 0) {
+            return image;
+        }
+        static_assert(sizeof(Color<float>) == 4 * sizeof(float), "Color<float> must be four packed floats");
+        const ptb_camera camera = lowerCamera(job.camera);
+        ptb_render_opts opts = makeOpts(job.options, seed, PTB_RNG_COUNTER);
+        opts.tile_size = tile_size;
+        ptb::host::check(ptb_render(job.scene.deviceScene(), &camera, &opts, x0, y0, w, h, reinterpret_cast<float *>(image.data()), nullptr), "render");
+        return image;
+    }
+
+}
+
+namespace ptb {
+
+    RenderControl &renderControl() {
+        static RenderControl control = [] {
+            RenderControl c;
+            c.max_depth = static_cast<int>(envLong("PTB_MAX_DEPTH", 0));
+            c.any_hit_shadows = envLong("PTB_ANY_HIT_SHADOWS", 0) != 0;
+            c.skip_null_shadows = envLong("PTB_SKIP_NULL_SHADOWS", 0) != 0;
+            c.fixed_seed = static_cast<uint64_t>(envLong("PTB_SEED", 0));
+            return c;
+        }();
+        return control;
+    }
+
+    void renderSamples(const FrameRenderJob &job, std::size_t count, const int *pixels, const uint64_t *seeds, float *out_rgba) {
+        const ptb_camera camera = lowerCamera(job.camera);
+        const ptb_render_opts opts = makeOpts(job.options, 0, PTB_RNG_REFERENCE_XORSHIFT);
+        host::check(ptb_render_samples(job.scene.deviceScene(), &camera, &opts, count, pixels, seeds, out_rgba, nullptr), "renderSamples");
+    }
+
+}
+
+WorkItem::WorkItem() noexcept : job(nullptr), offset_x(0), offset_y(0), width(0), height(0) {}
+
+WorkItem::WorkItem(const FrameRenderJob *job, int offset_x, int offset_y, int width, int height) noexcept :
+  job(job), offset_x(offset_x), offset_y(offset_y), width(width), height(height) {}
+
+Image<> processItem(const WorkItem &item, RandomEngine &re) {
+    const uint64_t low = re();
+    const uint64_t high = re();
+    const uint64_t seed = (high << 32) | low;
+    // one tile: a single group of pixels, no further subdivision
+    return renderRect(*item.job, item.offset_x, item.offset_y, item.width, item.height, std::max(std::max(item.width, item.height), 1), seed);
+}
+
+Image<> processJob(const FrameRenderJob &job, const std::function<void(int, int)> &progress_callback, int /*worker_count*/) {
+    const int width = std::max(job.options.image_width, 0);
+    const int height = std::max(job.options.image_height, 0);
+    if(width == 0 || height == 0) {
+        return Image<>(width, height);
+    }
+
+    uint64_t seed = ptb::renderControl().fixed_seed;
+    if(seed == 0) {
+        std::random_device device;
+        seed = (static_cast<uint64_t>(device()) << 32) | device();
+    }
+
+    // the reference's tile grid (worker.cpp:398-402) decides how many progress callbacks fire
+    const int tile_size = std::max(std::min(std::min(width, height) / 4, 32), 1);
+    const int horizontal_tiles = (width + tile_size - 1) / tile_size;
+    const int vertical_tiles = (height + tile_size - 1) / tile_size;
+    const int total_tiles = horizontal_tiles * vertical_tiles;
+
+    Image<> image = renderRect(job, 0, 0, width, height, tile_size, seed);
+
+    for(int tile = 0; tile < total_tiles; tile++) {
+        progress_callback(tile + 1, total_tiles);
+    }
+    return image;
+}

@@ -1,0 +1,281 @@
+/*
+ * ptb.h — C-ABI of the B200-native render core ("PathTrace on B200").
+ *
+ * This is the drop-in boundary for ONE hot path of johannesschaeufele/CPUPathTrace:
+ *
+ *     processJob -> processItem -> impl::getSample -> Scene::getIntersection / Scene::sampleLights / BSDF
+ *
+ * The reference has no plugin/FFI layer; its boundary is the public C++ API in include/PathTrace/** (reference
+ * include/PathTrace/worker.h:69,83-84, include/PathTrace/scene/scene.h:32,41,54, include/PathTrace/camera.h:92,108,123).
+ * The C++ host layer of this repository (include/PathTrace/** + cpupathtrace_b200/host/**) re-provides exactly that
+ * API and forwards the hot path through the entry points declared below.  A binding from any other language
+ * (ctypes, cgo, JNI, N-API) binds these functions directly; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, POD only, no exceptions cross this boundary; every function returns a ptb_status (0 = ok) and
+ *     ptb_last_error() returns a thread-local, human readable description of the last failure;
+ *   - the caller owns every host buffer it passes; a ptb_scene owns its device memory;
+ *   - there is NO CPU fallback: without a CUDA device (or without the sm_100a kernels) every compute entry point
+ *     fails with PTB_ERR_NO_DEVICE / PTB_ERR_CUDA;
+ *   - pointers are host pointers unless the call's `flags` carry PTB_FLAG_DEVICE_IO, in which case the bulk
+ *     input/output arrays are device pointers (same process, same device) and no host<->device copy is made.
+ */
+#ifndef PTB_H
+#define PTB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_ABI_VERSION 1
+
+typedef enum ptb_status {
+    PTB_OK = 0,
+    PTB_ERR_INVALID_ARGUMENT = 1,
+    PTB_ERR_NO_DEVICE = 2,      /* no usable CUDA device: the library never falls back to the CPU */
+    PTB_ERR_CUDA = 3,           /* a CUDA runtime call or kernel failed; see ptb_last_error()       */
+    PTB_ERR_OUT_OF_MEMORY = 4,
+    PTB_ERR_UNSUPPORTED = 5     /* e.g. a primitive / BSDF kind the device code does not know       */
+} ptb_status;
+
+typedef struct ptb_context ptb_context; /* one per (host thread, GPU) */
+typedef struct ptb_scene ptb_scene;     /* immutable device-resident scene: BVH + primitives + materials + lights */
+
+/* ------------------------------------------------------------------------------------------------ scene POD */
+
+/* replaces the virtual Object hierarchy (reference include/PathTrace/scene/object.h:54-169) */
+typedef enum ptb_prim_kind {
+    PTB_PRIM_TRIANGLE = 0, /* Triangle  (object.h:145-169, src/scene/object.cpp:118-207) */
+    PTB_PRIM_SPHERE = 1,   /* Sphere    (object.h:127-143, src/scene/object.cpp:68-116)  */
+    PTB_PRIM_NULL = 2      /* NullObject (object.h:112-122): never hit, no area           */
+} ptb_prim_kind;
+
+typedef struct ptb_prim {
+    uint32_t kind;          /* ptb_prim_kind */
+    uint32_t material;      /* index into ptb_scene_desc.materials */
+    uint32_t cull_backface; /* Triangle::cull_backface (object.h:157) */
+    uint32_t reserved;
+    /* triangle: a, b, c, normal_a, normal_b, normal_c (object.h:149-154); sphere: origin xyz, radius */
+    float p[18];
+} ptb_prim;
+
+/* replaces BSDF subclasses (reference include/PathTrace/scene/propagation.h:55-104) */
+typedef enum ptb_bsdf_kind {
+    PTB_BSDF_LAMBERT = 0, /* LambertianBRDF (src/scene/propagation.cpp:87-116)  */
+    PTB_BSDF_GLASS = 1,   /* GlassBDF       (src/scene/propagation.cpp:118-176) */
+    PTB_BSDF_MIRROR = 2   /* MirrorBRDF     (src/scene/propagation.cpp:178-217) */
+} ptb_bsdf_kind;
+
+/* replaces ConstantMaterialHandler + ConstantMaterial + BSDF (object.h:35-47, material.h:62-77); the specular
+ * colour is the Material default, white (src/scene/material.cpp:15-17) */
+typedef struct ptb_material {
+    float diffuse[4];
+    float emission[4];
+    float refractive_index;
+    uint32_t bsdf;    /* ptb_bsdf_kind */
+    uint32_t one_way; /* MirrorBRDF::one_way (propagation.h:86-87) */
+    uint32_t reserved;
+} ptb_material;
+
+/* replaces PointLightSource (reference include/PathTrace/scene/light.h:53-66) */
+typedef struct ptb_point_light {
+    float pos[3];
+    float rgba[4];
+} ptb_point_light;
+
+typedef enum ptb_bvh_mode {
+    /* topology identical to impl::constructBVH (src/scene/scene.cpp:12-102): needed for bit-exact closest-hit parity */
+    PTB_BVH_REFERENCE = 0
+} ptb_bvh_mode;
+
+typedef struct ptb_scene_desc {
+    const ptb_prim *prims; /* in the order of the `objects` vector given to Scene::Scene (scene.h:32) */
+    uint64_t n_prims;
+    const ptb_material *materials;
+    uint32_t n_materials;
+    const ptb_point_light *lights; /* in the order of the `light_sources` vector */
+    uint32_t n_lights;
+    uint32_t bvh_mode; /* ptb_bvh_mode */
+    uint32_t reserved;
+} ptb_scene_desc;
+
+typedef struct ptb_scene_info {
+    uint64_t n_prims;
+    uint64_t n_inner_nodes;       /* 64-byte two-child records */
+    uint32_t bvh_depth;           /* leaf depth maximum, root = 1 */
+    uint32_t n_emissive;          /* Scene::object_light_sources (scene.h:19) */
+    uint32_t object_sample_count; /* scene.cpp:226 */
+    uint32_t n_lights;
+    uint64_t device_bytes;        /* scene data resident in HBM */
+    double build_seconds;         /* host BVH build + flatten */
+    double upload_seconds;
+    float root_low[3];
+    float root_high[3];
+} ptb_scene_info;
+
+/* ------------------------------------------------------------------------------------------------ camera POD */
+
+typedef enum ptb_aperture_kind {
+    PTB_APERTURE_NONE = 0,
+    PTB_APERTURE_CIRCULAR = 1, /* CircularApertureSampler  (src/camera.cpp:7-19)  */
+    PTB_APERTURE_HEXAGONAL = 2 /* HexagonalApertureSampler (src/camera.cpp:21-49) */
+} ptb_aperture_kind;
+
+/* The private state of Camera after its constructor ran (reference include/PathTrace/camera.h:68-78,
+ * src/camera.cpp:54-76): `forward` is already scaled by the focal length, `up`/`right` by the half extents. */
+typedef struct ptb_camera {
+    float origin[3];
+    float forward[3];
+    float up[3];
+    float right[3];
+    float aperture_width_half;
+    float aperture_height_half;
+    uint32_t aperture_kind; /* ptb_aperture_kind */
+    float hexagon_horizontal_ratio;
+    float focal_plane_dist;
+} ptb_camera;
+
+/* Camera::Camera (src/camera.cpp:54-76) on the host, for bindings that have no C++ Camera object */
+int ptb_camera_init(ptb_camera *out, const float origin[3], const float look_at[3], const float up[3], float focal_length, float height,
+                    float aspect_ratio, float aperture_width, float aperture_height, uint32_t aperture_kind, float hexagon_horizontal_ratio,
+                    float focal_plane_dist);
+
+/* ------------------------------------------------------------------------------------------------ options */
+
+typedef enum ptb_rng_mode {
+    /* production: stateless counter-based generator keyed on (job seed, pixel, sample), counter = (bounce, draw) */
+    PTB_RNG_COUNTER = 0,
+    /* validation: one reference engine per (pixel, sample) — xorshift (reference include/PathTrace/base.h:24-41)
+     * seeded by the caller, consumed through libstdc++'s distribution arithmetic, draw for draw as the reference */
+    PTB_RNG_REFERENCE_XORSHIFT = 1
+} ptb_rng_mode;
+
+#define PTB_FLAG_DEVICE_IO 0x1u      /* bulk in/out arrays are device pointers                                          */
+#define PTB_FLAG_ANY_HIT_SHADOWS 0x2u /* shadow rays stop at the first occluder (result-identical up to ulp-level box/   */
+                                      /* primitive disagreement) instead of the reference's full closest-hit query       */
+#define PTB_FLAG_SKIP_NULL_SHADOWS 0x4u /* do not trace shadow rays whose BSDF returns pd 0 for synthetic rays (Glass,   */
+                                        /* Mirror: worker.cpp:84-92 traces them and discards the result)                  */
+#define PTB_FLAG_COUNT_VISITS 0x8u   /* count BVH node / primitive fetches (slower; feeds the bytes-per-ray figure)      */
+
+/* RenderOptions (reference include/PathTrace/worker.h:14-31) + the knobs that exist only on this side */
+typedef struct ptb_render_opts {
+    int32_t image_width;
+    int32_t image_height;
+    int32_t min_sample_count;
+    int32_t max_sample_count;
+    float epsilon;
+    int32_t max_depth;    /* 0 = unlimited like the reference (paths end by Russian roulette, worker.cpp:67-70) */
+    uint32_t rng_mode;    /* ptb_rng_mode */
+    uint32_t flags;       /* PTB_FLAG_* */
+    uint64_t seed;        /* job key for PTB_RNG_COUNTER */
+    /* multi-GPU sharding by interleaved tiles (reference tile grid: worker.cpp:398-414): tile k (row-major) is
+     * rendered iff k % shard_count == shard_index; pixels of other tiles are written as 0 so that a sum-reduce of
+     * the per-rank images is the full image.  shard_count <= 1 renders everything. */
+    int32_t tile_size;    /* 0 = the reference's clamp(min(W,H)/4, 1, 32) */
+    int32_t shard_index;
+    int32_t shard_count;
+    uint32_t reserved;
+} ptb_render_opts;
+
+typedef struct ptb_render_stats {
+    uint64_t samples;        /* pixel-samples started (primary rays)                     */
+    uint64_t closest_rays;   /* Scene::getIntersection-equivalent closest-hit queries    */
+    uint64_t shadow_rays;    /* shadow queries traced                                     */
+    uint64_t shadow_rays_skipped; /* shadow queries the reference traces but PTB_FLAG_SKIP_NULL_SHADOWS dropped */
+    uint64_t path_vertices;  /* surface hits shaded                                       */
+    uint64_t inner_visits;   /* 64-byte inner records fetched (PTB_FLAG_COUNT_VISITS)    */
+    uint64_t leaf_visits;    /* 48-byte primitive records fetched (PTB_FLAG_COUNT_VISITS) */
+    uint64_t bounce_iterations;
+    uint64_t kernel_launches;
+    double device_ms_total;  /* CUDA-event time of the whole call on the context's stream */
+    double device_ms_trace;  /* closest + shadow traversal kernels                         */
+    double device_ms_shade;  /* generate + shade + accumulate + resolve                    */
+} ptb_render_stats;
+
+/* ------------------------------------------------------------------------------------------------ entry points */
+
+int ptb_abi_version(void);
+const char *ptb_last_error(void);
+
+/* device < 0 selects $PTB_DEVICE, else $LOCAL_RANK, else 0 */
+int ptb_context_create(int device, ptb_context **out);
+int ptb_context_destroy(ptb_context *ctx);
+int ptb_context_device(const ptb_context *ctx, int *device_out);
+int ptb_context_synchronize(ptb_context *ctx);
+
+/* Scene::Scene (src/scene/scene.cpp:153-181): BVH build, emissive registration, CDF; then flatten + upload */
+int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **out);
+int ptb_scene_destroy(ptb_scene *scene);
+int ptb_scene_get_info(const ptb_scene *scene, ptb_scene_info *out);
+
+/* Scene::getIntersection (src/scene/scene.cpp:210-220) for a batch.
+ * rays: 6 floats each (origin xyz, unit direction xyz).  t_out[i] < 0 = miss (prim_out[i] = -1), else the
+ * distance and the index of the primitive in ptb_scene_desc.prims. */
+int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t_out, int32_t *prim_out, uint32_t flags, ptb_render_stats *stats);
+
+/* The shadow query of impl::getSample (src/worker.cpp:80-86) as an any-hit test.
+ * rays: 7 floats each (origin, unit direction, limit); occluded_out[i] = 1 iff some primitive is hit with
+ * 0 <= t < limit. */
+int ptb_occluded(ptb_scene *scene, const float *rays, uint64_t n_rays, uint8_t *occluded_out, uint32_t flags, ptb_render_stats *stats);
+
+/* processItem / processJob (src/worker.cpp:149-326, 389-424) for the pixel rectangle [x0, x0+w) x [y0, y0+h):
+ * out_rgba receives w*h*4 floats, row-major, the per-pixel value processItem computes (incl. the Welford batch
+ * statistics, adaptive acceptance and candidate merge when min != max). */
+int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts *opts, int32_t x0, int32_t y0, int32_t w, int32_t h, float *out_rgba,
+               ptb_render_stats *stats);
+
+/* Validation entry: one impl::getSample (src/worker.cpp:26-146) per (pixel, seed) with rng_mode
+ * PTB_RNG_REFERENCE_XORSHIFT == RandomEngine(seed).  pixels: 2 ints each; out_rgba: 4 floats each (alpha = collected). */
+int ptb_render_samples(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts *opts, uint64_t n, const int32_t *pixels,
+                       const uint64_t *seeds, float *out_rgba, ptb_render_stats *stats);
+
+/* ------------------------------------------------------------------------------------------------ unit entries
+ *
+ * The reference exposes every stage of the path as a public (virtual) method that host code may call one element at a
+ * time: Camera::shootRay, ApertureSampler::sampleAperture, AABB::getIntersection, Object::getIntersection /
+ * getSurfaceNormal / sampleSurface, Scene::sampleLights, BSDF::propagateRay / getSpectrum.  The host layer answers
+ * those calls with the batch entries below, which launch the SAME device functions the wavefront kernels use.
+ *
+ * engine_states: raw 64-bit xorshift states (reference include/PathTrace/base.h:24-41; a fresh RandomEngine(seed) has
+ * state seed ^ (~seed << 32)), one per element, updated in place to the state after the element's draws.
+ */
+
+/* Camera::shootRay (src/camera.cpp:78-113); xy: 2 floats, rays_out: 6 floats per element */
+int ptb_camera_shoot(ptb_context *ctx, const ptb_camera *camera, uint64_t n, const float *xy, float pixel_width, float pixel_height,
+                     uint64_t *engine_states, float *rays_out);
+
+/* ApertureSampler::sampleAperture (src/camera.cpp:7-49); out: 2 floats per element */
+int ptb_aperture_sample(ptb_context *ctx, uint32_t aperture_kind, float hexagon_horizontal_ratio, uint64_t n, uint64_t *engine_states, float *out);
+
+/* Scene::sampleLights (src/scene/scene.cpp:222-289) at one position.
+ * out: 8 floats per sample (pos xyz, spectrum rgba, pd); *n_out = number of samples produced (may exceed max_out). */
+int ptb_sample_lights(ptb_scene *scene, const float pos[3], uint64_t *engine_state, uint32_t max_out, float *out, uint32_t *n_out);
+
+/* AABB::getIntersection (src/scene/bounding_box.cpp:38-73) for one box and a batch of rays (6 floats each) */
+int ptb_aabb_intersect(ptb_context *ctx, const float low[3], const float high[3], uint64_t n_rays, const float *rays, float *t_out);
+
+/* Object::getIntersection for one primitive and a batch of rays (Triangle: object.cpp:146-182, Sphere: :72-84) */
+int ptb_prim_intersect(ptb_context *ctx, const ptb_prim *prim, uint64_t n_rays, const float *rays, float *t_out);
+
+/* Object::getSurfaceNormal (Triangle: object.cpp:126-144, Sphere: :86-88); positions / normals_out: 3 floats each */
+int ptb_prim_normal(ptb_context *ctx, const ptb_prim *prim, uint64_t n, const float *positions, float *normals_out);
+
+/* Object::sampleSurface (Triangle: object.cpp:192-207, Sphere: :101-116); out: 5 floats (pos xyz, density, cull) */
+int ptb_prim_sample(ptb_context *ctx, const ptb_prim *prim, uint64_t n, uint64_t *engine_states, float *out);
+
+/* BSDF::propagateRay (src/scene/propagation.cpp:89-99, 120-160, 180-204).
+ * in: 9 floats (incoming direction, position, normal); out: 8 floats (origin, direction, factor, density) */
+int ptb_bsdf_propagate(ptb_context *ctx, const ptb_material *material, float epsilon, uint64_t n, const float *in, uint64_t *engine_states, float *out);
+
+/* BSDF::getSpectrum (src/scene/propagation.cpp:101-116, 162-176, 206-217).
+ * in: 13 floats (from-camera direction, to-light direction, normal, light rgba); out: 6 floats (rgba, shade, density) */
+int ptb_bsdf_spectrum(ptb_context *ctx, const ptb_material *material, uint32_t synthetic, uint64_t n, const float *in, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PTB_H */
