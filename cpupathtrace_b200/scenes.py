@@ -76,6 +76,71 @@ class SceneSpec:
         b.close()
         return scene
 
+    def to_pod(self, pth):
+        """Lowers the spec to the C-ABI's POD arrays (capi.PRIM_DTYPE / MATERIAL_DTYPE / LIGHT_DTYPE).
+
+        Geometry is produced by the given harness library's own mesh code (makePlane, makeBox, io::loadMesh) and read
+        back, so the POD scene is identical to what that library's Scene would contain, in the same object order."""
+        from . import capi
+
+        materials, lights, kinds, mats, spheres = [], [], [], [], []
+        b = pth.builder()
+        try:
+            for step in self.steps:
+                kind = step[0]
+                before = b.object_count()
+                material = -1
+                if kind == "material":
+                    b.material(*step[1:])
+                    materials.append(step[1:])
+                    continue
+                if kind == "point_light":
+                    lights.append((step[1], step[2]))
+                    continue
+                if kind == "plane":
+                    b.plane(step[1], step[2], step[3], step[4])
+                    material, cull = step[4], step[3]
+                elif kind == "box":
+                    b.box(step[1], step[2], step[3], step[4], step[5])
+                    material, cull = step[5], step[3]
+                elif kind == "triangles":
+                    b.triangles(step[1], step[2], step[3], step[4])
+                    material, cull = step[4], step[3]
+                elif kind == "mesh_obj":
+                    b.mesh_obj(step[1], step[2], step[3], step[4], step[5])
+                    material, cull = step[5], step[3]
+                elif kind == "spheres":
+                    b.spheres(step[1], step[2])
+                    material, cull = step[2], False
+                    spheres.extend(np.asarray(step[1], np.float32).reshape(-1, 4))
+                added = b.object_count() - before
+                kinds.extend([(capi.PTB_PRIM_SPHERE if kind == "spheres" else capi.PTB_PRIM_TRIANGLE, bool(cull))] * added)
+                mats.extend([material] * added)
+            tris = b.get_triangles()
+        finally:
+            b.close()
+
+        default_index = len(materials)
+        mat_arr = np.zeros(len(materials) + 1, capi.MATERIAL_DTYPE)
+        for i, (diffuse, ior, emission, bsdf, one_way) in enumerate(materials):
+            mat_arr[i] = (diffuse, emission, ior, bsdf, 1 if one_way else 0, 0)
+        mat_arr[default_index] = ((1, 1, 1, 1), (0, 0, 0, 0), 1.0, capi.PTB_BSDF_LAMBERT, 0, 0)
+
+        prims = np.zeros(len(kinds), capi.PRIM_DTYPE)
+        sphere_iter = iter(spheres)
+        for i, ((kind, cull), material) in enumerate(zip(kinds, mats)):
+            prims[i]["kind"] = kind
+            prims[i]["material"] = material if material >= 0 else default_index
+            prims[i]["cull_backface"] = 1 if cull else 0
+            if kind == capi.PTB_PRIM_TRIANGLE:
+                prims[i]["p"] = tris[i]
+            else:
+                prims[i]["p"][:4] = next(sphere_iter)
+        light_arr = np.zeros(len(lights), capi.LIGHT_DTYPE)
+        for i, (pos, rgba) in enumerate(lights):
+            light_arr[i] = (pos, rgba)
+        return prims, mat_arr, light_arr
+
 
 # ---------------------------------------------------------------------------------------------- stand-in mesh / soup
 
