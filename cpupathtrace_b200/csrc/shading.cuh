@@ -10,14 +10,15 @@
 //   Lambertian / Glass / Mirror              reference src/scene/propagation.cpp:89-217
 //   impl::getSample (one loop iteration)     reference src/worker.cpp:44-138
 //
-// libm: sqrt and division are IEEE-exact; sin/cos/acos are CUDA's fp32 routines (<= 1-2 ulp) where the reference
-// calls glibc's (<= 1 ulp); pow(x, 1) is x and pow(x, 0.5) is sqrt(x) (equal to glibc's powf on 99.93 % of inputs).
-// These ulp-level differences are the only source of non-bit-exact radiance in validation mode.
+// libm: sqrt and division are IEEE-exact; sin, cos, acos and pow(x, 0.5) are the bit-exact restatements of glibc's
+// routines in glibc_libm.cuh; pow(x, 1) is x (glibc's powf returns x exactly).  With identical random numbers the
+// radiance of a sample is therefore expected to be bit-identical to the reference's (DESIGN.md "Numerics").
 #ifndef PTB_SHADING_CUH
 #define PTB_SHADING_CUH
 
 #include "../../include/ptb.h"
 #include "device_scene.cuh"
+#include "glibc_libm.cuh"
 #include "rng.cuh"
 
 namespace ptb {
@@ -28,8 +29,8 @@ namespace ptb {
         if(c.aperture_kind == PTB_APERTURE_CIRCULAR) {
             const float r = sqrtf(rng.uniform01());
             const float theta = kTwoPi * rng.uniform01();
-            sx = r * cosf(theta);
-            sy = r * sinf(theta);
+            sx = r * glibcCosf(theta);
+            sy = r * glibcSinf(theta);
             return;
         }
         // hexagonal: rejection sample the upper-right quadrant, then two fair coin flips for the signs
@@ -175,10 +176,10 @@ namespace ptb {
             const float radius = e1.x;
             const float radius2 = e1.y;
             const float theta = kTwoPi * rng.uniform01();
-            const float phi = acosf(1.0F - 2.0F * rng.uniform01());
-            const float x = sinf(phi) * cosf(theta);
-            const float y = sinf(phi) * sinf(theta);
-            const float z = cosf(phi);
+            const float phi = glibcAcosf(1.0F - 2.0F * rng.uniform01());
+            const float x = glibcSinf(phi) * glibcCosf(theta);
+            const float y = glibcSinf(phi) * glibcSinf(theta);
+            const float z = glibcCosf(phi);
             surface_pos = origin + mk3(x, y, z) * radius;
             surface_p = 1.0F / ((4.0F * kPi) * radius2);
             surface_cull = false;
@@ -325,10 +326,10 @@ namespace ptb {
             // draw is r2 (the cos-theta variate) and the second is r1 (the azimuth)   [SURVEY.md App. B]
             const float r2 = rng.uniform01();
             const float r1 = rng.uniform01();
-            const float fac = sqrtf(1.0F - r2);     // pow(r2, 2/(e+1)) with e = 1
-            const float cos_theta = sqrtf(r2);      // pow(r2, 1/(e+1))
+            const float fac = sqrtf(1.0F - r2);         // pow(r2, 2/(e+1)) with e = 1: powf(x, 1) == x
+            const float cos_theta = glibcPowfHalf(r2);  // pow(r2, 1/(e+1))
             const float angle = kTwoPi * r1;
-            const V3 local = mk3(fac * cosf(angle), fac * sinf(angle), cos_theta);
+            const V3 local = mk3(fac * glibcCosf(angle), fac * glibcSinf(angle), cos_theta);
             const float p = 2.0F * cos_theta / kTwoPi; // (e+1) * pow(cos_theta, e) / (2 pi)
             const V3 dir = localToGlobal(local, normal);
             out_o = pos + dir * epsilon;
