@@ -196,64 +196,51 @@ namespace ptb {
 
     // ------------------------------------------------------------------------------------------------ trace
 
-    // Persistent warps: each warp claims 32 queue entries at a time from a device-side cursor until the queue is
-    // drained, so a warp stuck on one long traversal does not strand the rest of a statically assigned range.
+    // Persistent warps over the device-side queue; scheduling by warp votes, see warpTrace in traverse.cuh.
     template<bool COUNT>
     __global__ void __launch_bounds__(kBlock) traceClosestKernel(DeviceScene scene, PathPool pool, const uint32_t *__restrict__ queue,
                                                                  uint32_t *__restrict__ counters, int queue_slot, VisitCounters *visits) {
         const uint32_t count = counters[queue_slot];
-        for(;;) {
-            uint32_t base = 0U;
-            if(laneId() == 0U) {
-                base = atomicAdd(&counters[kCountFetchClosest], 32U);
-            }
-            base = __shfl_sync(0xFFFFFFFFU, base, 0);
-            if(base >= count) {
-                return;
-            }
-            const uint32_t k = base + laneId();
-            if(k < count) {
-                const uint32_t i = queue[k];
-                const float4 o = pool.ray_o[i];
-                const float4 d = pool.ray_d[i];
-                const RayInv r = makeRay(mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z));
-                const Hit h = traverse<false, COUNT>(scene, r, 0.0F, visits);
-                pool.hit[i] = make_float2(h.t, __int_as_float(h.slot));
-            }
-        }
+        warpTrace<false, COUNT>(
+          scene, &counters[kCountFetchClosest], count,
+          [&](uint32_t k, V3 &o, V3 &d, float &limit) {
+              const uint32_t i = queue[k];
+              const float4 ro = pool.ray_o[i];
+              const float4 rd = pool.ray_d[i];
+              o = mk3(ro.x, ro.y, ro.z);
+              d = mk3(rd.x, rd.y, rd.z);
+              limit = 0.0F;
+          },
+          [&](uint32_t k, const Hit &h) { pool.hit[queue[k]] = make_float2(h.t, __int_as_float(h.slot)); }, visits);
     }
 
     template<bool COUNT>
     __global__ void __launch_bounds__(kBlock) traceShadowKernel(DeviceScene scene, PathPool pool, const uint32_t *__restrict__ shadow_queue,
                                                                 uint32_t *__restrict__ counters, uint32_t any_hit, VisitCounters *visits) {
         const uint32_t count = counters[kCountShadow];
-        for(;;) {
-            uint32_t base = 0U;
-            if(laneId() == 0U) {
-                base = atomicAdd(&counters[kCountFetchShadow], 32U);
-            }
-            base = __shfl_sync(0xFFFFFFFFU, base, 0);
-            if(base >= count) {
-                return;
-            }
-            const uint32_t k = base + laneId();
-            if(k < count) {
-                const uint32_t slot = shadow_queue[k];
-                const float4 o = pool.shadow_o[slot];
-                const float4 d = pool.shadow_d[slot];
-                const RayInv r = makeRay(mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z));
-                bool visible;
-                if(any_hit != 0U) {
-                    const Hit h = traverse<true, COUNT>(scene, r, o.w, visits);
-                    visible = h.slot < 0;
-                }
-                else {
-                    // the reference's full closest-hit query (worker.cpp:84-86)
-                    const Hit h = traverse<false, COUNT>(scene, r, 0.0F, visits);
-                    visible = h.t < 0.0F || h.t >= o.w;
-                }
-                pool.shadow_c[slot].w = visible ? 1.0F : 0.0F;
-            }
+        auto fetch = [&](uint32_t k, V3 &o, V3 &d, float &limit) {
+            const uint32_t slot = shadow_queue[k];
+            const float4 so = pool.shadow_o[slot];
+            const float4 sd = pool.shadow_d[slot];
+            o = mk3(so.x, so.y, so.z);
+            d = mk3(sd.x, sd.y, sd.z);
+            limit = so.w;
+        };
+        if(any_hit != 0U) {
+            warpTrace<true, COUNT>(
+              scene, &counters[kCountFetchShadow], count, fetch,
+              [&](uint32_t k, const Hit &h) { pool.shadow_c[shadow_queue[k]].w = h.slot < 0 ? 1.0F : 0.0F; }, visits);
+        }
+        else {
+            // the reference's full closest-hit query (worker.cpp:84-86): unoccluded iff t < 0 or t >= |to_light| - epsilon
+            warpTrace<false, COUNT>(
+              scene, &counters[kCountFetchShadow], count, fetch,
+              [&](uint32_t k, const Hit &h) {
+                  const uint32_t slot = shadow_queue[k];
+                  const float limit = pool.shadow_o[slot].w;
+                  pool.shadow_c[slot].w = (h.t < 0.0F || h.t >= limit) ? 1.0F : 0.0F;
+              },
+              visits);
         }
     }
 
@@ -561,48 +548,35 @@ namespace ptb {
     // ------------------------------------------------------------------------------------------------ unit kernels
 
     template<bool COUNT>
-    __global__ void __launch_bounds__(kBlock) intersectKernel(DeviceScene scene, const float *__restrict__ rays, uint64_t n, float *__restrict__ t_out,
-                                                              int32_t *__restrict__ prim_out, uint32_t *__restrict__ fetch, VisitCounters *visits) {
-        for(;;) {
-            unsigned long long base = 0ULL;
-            if(laneId() == 0U) {
-                base = atomicAdd(reinterpret_cast<unsigned long long *>(fetch), 32ULL);
-            }
-            base = __shfl_sync(0xFFFFFFFFU, base, 0);
-            if(base >= n) {
-                return;
-            }
-            const uint64_t k = base + laneId();
-            if(k < n) {
-                const float *p = rays + 6 * k;
-                const RayInv r = makeRay(mk3(p[0], p[1], p[2]), mk3(p[3], p[4], p[5]));
-                const Hit h = traverse<false, COUNT>(scene, r, 0.0F, visits);
-                t_out[k] = h.t;
-                prim_out[k] = (h.slot >= 0 && h.t >= 0.0F) ? static_cast<int32_t>(scene.slot_to_prim[h.slot]) : -1;
-            }
-        }
+    __global__ void __launch_bounds__(kBlock) intersectKernel(DeviceScene scene, const float *__restrict__ rays, uint32_t n, float *__restrict__ t_out,
+                                                              int32_t *__restrict__ prim_out, uint32_t *__restrict__ cursor, VisitCounters *visits) {
+        warpTrace<false, COUNT>(
+          scene, cursor, n,
+          [&](uint32_t k, V3 &o, V3 &d, float &limit) {
+              const float *p = rays + 6 * static_cast<size_t>(k);
+              o = mk3(p[0], p[1], p[2]);
+              d = mk3(p[3], p[4], p[5]);
+              limit = 0.0F;
+          },
+          [&](uint32_t k, const Hit &h) {
+              t_out[k] = h.t;
+              prim_out[k] = (h.slot >= 0 && h.t >= 0.0F) ? static_cast<int32_t>(scene.slot_to_prim[h.slot]) : -1;
+          },
+          visits);
     }
 
     template<bool COUNT>
-    __global__ void __launch_bounds__(kBlock) occludedKernel(DeviceScene scene, const float *__restrict__ rays, uint64_t n, uint8_t *__restrict__ out,
-                                                             uint32_t *__restrict__ fetch, VisitCounters *visits) {
-        for(;;) {
-            unsigned long long base = 0ULL;
-            if(laneId() == 0U) {
-                base = atomicAdd(reinterpret_cast<unsigned long long *>(fetch), 32ULL);
-            }
-            base = __shfl_sync(0xFFFFFFFFU, base, 0);
-            if(base >= n) {
-                return;
-            }
-            const uint64_t k = base + laneId();
-            if(k < n) {
-                const float *p = rays + 7 * k;
-                const RayInv r = makeRay(mk3(p[0], p[1], p[2]), mk3(p[3], p[4], p[5]));
-                const Hit h = traverse<true, COUNT>(scene, r, p[6], visits);
-                out[k] = h.slot >= 0 ? 1 : 0;
-            }
-        }
+    __global__ void __launch_bounds__(kBlock) occludedKernel(DeviceScene scene, const float *__restrict__ rays, uint32_t n, uint8_t *__restrict__ out,
+                                                             uint32_t *__restrict__ cursor, VisitCounters *visits) {
+        warpTrace<true, COUNT>(
+          scene, cursor, n,
+          [&](uint32_t k, V3 &o, V3 &d, float &limit) {
+              const float *p = rays + 7 * static_cast<size_t>(k);
+              o = mk3(p[0], p[1], p[2]);
+              d = mk3(p[3], p[4], p[5]);
+              limit = p[6];
+          },
+          [&](uint32_t k, const Hit &h) { out[k] = h.slot >= 0 ? 1 : 0; }, visits);
     }
 
     __global__ void aabbKernel(float lox, float loy, float loz, float hix, float hiy, float hiz, const float *__restrict__ rays, uint64_t n,

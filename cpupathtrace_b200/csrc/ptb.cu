@@ -724,15 +724,18 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
     PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
     PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, sizeof(VisitCounters), ctx->stream));
 
-    const int grid = static_cast<int>(std::min<uint64_t>((n_rays + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 16))));
-    {
+    constexpr uint64_t kChunk = 1ULL << 30;
+    for(uint64_t first = 0; first < n_rays; first += kChunk) {
+        const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(kChunk, n_rays - first));
+        const int grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 16))));
+        PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(uint32_t), ctx->stream));
         LaunchTimer timer(ctx, 0);
         if(count_visits) {
-            intersectKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays, n_rays, d_t, d_prim, ctx->counters.as<uint32_t>(),
+            intersectKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays + 6 * first, n, d_t + first, d_prim + first, ctx->counters.as<uint32_t>(),
                                                                      ctx->visits.as<VisitCounters>());
         }
         else {
-            intersectKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays, n_rays, d_t, d_prim, ctx->counters.as<uint32_t>(),
+            intersectKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays + 6 * first, n, d_t + first, d_prim + first, ctx->counters.as<uint32_t>(),
                                                                       ctx->visits.as<VisitCounters>());
         }
     }
@@ -783,15 +786,18 @@ int ptb_occluded(ptb_scene *scene, const float *rays, uint64_t n_rays, uint8_t *
     PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
     PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, sizeof(VisitCounters), ctx->stream));
 
-    const int grid = static_cast<int>(std::min<uint64_t>((n_rays + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 16))));
-    {
+    constexpr uint64_t kChunk = 1ULL << 30;
+    for(uint64_t first = 0; first < n_rays; first += kChunk) {
+        const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(kChunk, n_rays - first));
+        const int grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 16))));
+        PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(uint32_t), ctx->stream));
         LaunchTimer timer(ctx, 0);
         if(count_visits) {
-            occludedKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays, n_rays, d_out, ctx->counters.as<uint32_t>(),
+            occludedKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
                                                                     ctx->visits.as<VisitCounters>());
         }
         else {
-            occludedKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays, n_rays, d_out, ctx->counters.as<uint32_t>(),
+            occludedKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
                                                                      ctx->visits.as<VisitCounters>());
         }
     }
