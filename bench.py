@@ -223,7 +223,7 @@ def run_b200_arm(args):
 
     import torch
 
-    from cpupathtrace_b200 import capi, pth, scenes
+    from cpupathtrace_b200 import capi, pth, scenes, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -277,7 +277,7 @@ def run_b200_arm(args):
             return 0.0
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
-        dist.reduce(image, dst=0, op=dist.ReduceOp.SUM)
+        sharding.reduce_image(image, dist, dst=0)
         stop.record()
         stop.synchronize()
         return start.elapsed_time(stop)

@@ -96,6 +96,15 @@ namespace ptb {
         return V4{v.x, v.y, v.z, v.w};
     }
 
+    // One 256-bit read-only load (LDG.E.256, sm_100+): 32 bytes, 32-byte aligned, two float4 lanes per request.
+    // Node records are fetched with two of these instead of four 128-bit loads, which halves the L1 wavefronts per
+    // node visit (profiles/r01_ncu_trace_vote.md: l1tex__data_pipe_lsu_wavefronts was the top limiter at 71 %).
+    PTB_DEV void ld256(const float4 *p, float4 &a, float4 &b) {
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                     : "l"(p));
+    }
+
     PTB_DEV float4 f4(V4 v) {
         return make_float4(v.x, v.y, v.z, v.w);
     }

@@ -3,9 +3,9 @@
 // HBM layout (every array 16-byte aligned, read with 128-bit loads through the read-only path):
 //
 //   nodes  : 4 x float4 per inner record (64 B), DFS preorder              <- AABB tree (scene/bounding_box.h:22-68)
-//   geom   : 3 x float4 per leaf slot  (48 B), leaf (DFS) order            <- Triangle / Sphere geometry (scene/object.h)
-//              triangle: (a, flags) (b - a, 0) (c - a, 0)       flags = kind | cull << 2
-//              sphere  : (origin, flags) (radius, radius^2, 0, 0) (0)
+//   geom   : 4 x float4 per leaf slot  (64 B, last lane padding), leaf order <- Triangle / Sphere geometry (scene/object.h)
+//              triangle: (a, flags) (b - a, 0) (c - a, 0) (pad)  flags = kind | cull << 2
+//              sphere  : (origin, flags) (radius, radius^2, 0, 0) (0) (pad)
 //   shade  : 3 x float4 per leaf slot  (48 B)                              <- shading normals + material index
 //              (normal_a, material) (normal_b, 0) (normal_c, 0)
 //   mats   : 3 x float4 per material   (48 B): diffuse, emission, (ior, bsdf, one_way, 0)
@@ -24,6 +24,7 @@
 
 namespace ptb {
 
+    constexpr uint32_t kGeomLanes = 4U; // 3 used + 1 pad: 64-byte records so that (lane0, lane1) is one 256-bit load
     constexpr uint32_t kKindMask = 3U;
     constexpr uint32_t kCullBit = 4U;
 

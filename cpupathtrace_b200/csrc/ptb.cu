@@ -515,7 +515,7 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
     }
 
     const uint64_t n = desc->n_prims;
-    std::vector<float4> geom(3 * n);
+    std::vector<float4> geom(kGeomLanes * n, make_float4(0.0F, 0.0F, 0.0F, 0.0F));
     std::vector<float4> shade(3 * n);
     for(uint64_t slot = 0; slot < n; slot++) {
         const ptb_prim &prim = desc->prims[bvh.slot_to_prim[slot]];
@@ -524,7 +524,7 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
         if(prim.kind == PTB_PRIM_TRIANGLE && prim.cull_backface != 0U) {
             flags |= kCullBit;
         }
-        float4 *g = &geom[3 * slot];
+        float4 *g = &geom[kGeomLanes * slot];
         float4 *s = &shade[3 * slot];
         if(prim.kind == PTB_PRIM_TRIANGLE) {
             // edges are differenced on the host exactly as Triangle::getIntersection does per call (object.cpp:149-150)
@@ -1151,7 +1151,7 @@ int ptb_prim_intersect(ptb_context *ctx, const ptb_prim *prim, uint64_t n_rays, 
         return status;
     }
     const float *p = prim->p;
-    float4 geom[3];
+    float4 geom[4] = {};
     uint32_t flags = prim->kind & kKindMask;
     if(prim->kind == PTB_PRIM_TRIANGLE) {
         if(prim->cull_backface != 0U) {
@@ -1188,7 +1188,7 @@ namespace {
 
     // geometry lanes (differenced edges), shading lanes and un-differenced lanes of one primitive
     struct PrimLanes {
-        float4 geom[3];
+        float4 geom[4];
         float4 shade[3];
         float4 raw[3];
         uint32_t flags;
@@ -1237,16 +1237,16 @@ int ptb_prim_normal(ptb_context *ctx, const ptb_prim *prim, uint64_t n, const fl
     }
     const PrimLanes lanes = lanesOf(*prim);
     if((status = ctx->io_a.reserve(n * 3 * sizeof(float))) != PTB_OK || (status = ctx->io_b.reserve(n * 3 * sizeof(float))) != PTB_OK ||
-       (status = ctx->io_c.reserve(6 * sizeof(float4))) != PTB_OK) {
+       (status = ctx->io_c.reserve(8 * sizeof(float4))) != PTB_OK) {
         return status;
     }
     PTB_CUDA(cudaMemcpyAsync(ctx->io_a.ptr, positions, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    PTB_CUDA(cudaMemcpyAsync(ctx->io_c.ptr, lanes.geom, 3 * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    PTB_CUDA(cudaMemcpyAsync(ctx->io_c.as<float4>() + 3, lanes.shade, 3 * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_c.ptr, lanes.geom, 4 * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(cudaMemcpyAsync(ctx->io_c.as<float4>() + 4, lanes.shade, 3 * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     PTB_CUDA(cudaStreamSynchronize(ctx->stream));
     DeviceScene one{};
     one.geom = ctx->io_c.as<float4>();
-    one.shade = ctx->io_c.as<float4>() + 3;
+    one.shade = ctx->io_c.as<float4>() + 4;
     one.n_prims = 1;
     primNormalKernel<<<static_cast<unsigned>((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(one, n, ctx->io_a.as<float>(), ctx->io_b.as<float>());
     PTB_CUDA(cudaGetLastError());

@@ -120,7 +120,7 @@ namespace ptb {
 
     // Object::getSurfaceNormal for the primitive in `slot`; also returns its material index
     PTB_DEV V3 surfaceNormal(const DeviceScene &s, uint32_t slot, V3 pos, uint32_t &material) {
-        const float4 *g = s.geom + 3 * static_cast<size_t>(slot);
+        const float4 *g = s.geom + kGeomLanes * static_cast<size_t>(slot);
         const float4 *sh = s.shade + 3 * static_cast<size_t>(slot);
         const float4 g0 = __ldg(g);
         const float4 s0 = __ldg(sh);
@@ -241,7 +241,7 @@ namespace ptb {
             const float4 e0 = __ldg(e);
             const float4 e1 = __ldg(e + 1);
             const uint32_t slot = __float_as_uint(e0.w);
-            const float4 g0 = __ldg(s.geom + 3 * static_cast<size_t>(slot));
+            const float4 g0 = __ldg(s.geom + kGeomLanes * static_cast<size_t>(slot));
             const uint32_t flags = __float_as_uint(g0.w);
 
             V3 surface_pos;

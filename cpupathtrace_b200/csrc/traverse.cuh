@@ -96,9 +96,10 @@ namespace ptb {
     }
 
     PTB_DEV float hitSlot(const DeviceScene &s, const RayInv &r, uint32_t slot) {
-        const float4 *g = s.geom + 3 * static_cast<size_t>(slot);
-        const float4 g0 = __ldg(g);
-        const float4 g1 = __ldg(g + 1);
+        const float4 *g = s.geom + kGeomLanes * static_cast<size_t>(slot);
+        float4 g0;
+        float4 g1;
+        ld256(g, g0, g1);
         const uint32_t flags = __float_as_uint(g0.w);
         const uint32_t kind = flags & kKindMask;
         if(kind == PTB_PRIM_TRIANGLE) {
@@ -145,10 +146,12 @@ namespace ptb {
         for(;;) {
             while(node >= 0) {
                 const float4 *rec = s.nodes + 4 * static_cast<size_t>(node);
-                const float4 n0 = __ldg(rec);
-                const float4 n1 = __ldg(rec + 1);
-                const float4 n2 = __ldg(rec + 2);
-                const float4 n3 = __ldg(rec + 3);
+                float4 n0;
+                float4 n1;
+                float4 n2;
+                float4 n3;
+                ld256(rec, n0, n1);
+                ld256(rec + 2, n2, n3);
                 if(COUNT) {
                     n_inner++;
                 }
@@ -340,10 +343,12 @@ namespace ptb {
             // ---- one inner-node step for every lane that has one
             if(status == kLaneInner) {
                 const float4 *rec = s.nodes + 4 * static_cast<size_t>(node);
-                const float4 n0 = __ldg(rec);
-                const float4 n1 = __ldg(rec + 1);
-                const float4 n2 = __ldg(rec + 2);
-                const float4 n3 = __ldg(rec + 3);
+                float4 n0;
+                float4 n1;
+                float4 n2;
+                float4 n3;
+                ld256(rec, n0, n1);
+                ld256(rec + 2, n2, n3);
                 if(COUNT) {
                     n_inner++;
                 }

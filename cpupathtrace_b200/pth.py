@@ -44,6 +44,7 @@ _PROTOTYPES = {
 }
 _OPTIONAL = {
     "pth_scene_device_handle": (_P, [_P]),
+    "pth_png_roundtrip": (C.c_long, [C.c_int, C.c_int, _P, _P]),
 }
 
 REF_PARITY = os.path.join(REPO_ROOT, "oracle", "_ref", "libpth_ref.so")
@@ -94,6 +95,14 @@ class Pth:
         h, w = img.shape[:2]
         self.lib.pth_post_process(mode, w, h, gamma, _ptr(img))
         return img
+
+    def png_roundtrip(self, image):
+        """b200 build only: encode with io::writeRGBImage, decode with io::readRGBImage; returns (decoded, n_bytes)."""
+        img = np.ascontiguousarray(image, dtype=np.float32)
+        h, w = img.shape[:2]
+        out = np.zeros_like(img)
+        n = self.lib.pth_png_roundtrip(w, h, _ptr(img), _ptr(out))
+        return out, n
 
     def builder(self):
         return PthBuilder(self)

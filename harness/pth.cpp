@@ -477,3 +477,27 @@ extern "C" void *pth_scene_device_handle(void *scene) {
     return static_cast<SceneBox *>(scene)->scene->deviceScene();
 }
 #endif
+
+#ifdef PATHTRACE_B200
+#include <PathTrace/image/image_io.h>
+// b200 build only (the reference's image_io.cpp needs libpng, absent here): PNG encode -> decode round trip of an RGBA
+// float image through io::writeRGBImage / io::readRGBImage.  Returns the encoded size in bytes, or -1 on failure.
+extern "C" long pth_png_roundtrip(int width, int height, const float *pixels_in, float *pixels_out) {
+    try {
+        Image<> image(width, height);
+        std::memcpy(image.data(), pixels_in, sizeof(float) * 4 * image.size());
+        std::stringstream stream(std::ios_base::in | std::ios_base::out | std::ios_base::binary);
+        io::writeRGBImage(stream, image);
+        const long bytes = static_cast<long>(stream.str().size());
+        Image<> decoded = io::readRGBImage(stream);
+        if(decoded.getWidth() != width || decoded.getHeight() != height) {
+            return -1;
+        }
+        std::memcpy(pixels_out, decoded.data(), sizeof(float) * 4 * decoded.size());
+        return bytes;
+    }
+    catch(const std::exception &) {
+        return -1;
+    }
+}
+#endif
