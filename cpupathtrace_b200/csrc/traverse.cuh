@@ -248,6 +248,22 @@ namespace ptb {
 
     enum LaneStatus : uint32_t { kLaneIdle = 0U, kLaneInner = 1U, kLaneLeaf = 2U };
 
+    // Hit test of one box in "visit" form: hit <=> the reference's slab result is >= 0, entry = that result.
+    // (bounding_box.cpp:61-72: -1 iff t_max < 0 or t_min > t_max; otherwise max(t_min, 0).)
+    PTB_DEV bool slabVisit(const RayInv &r, float lox, float loy, float loz, float hix, float hiy, float hiz, float best_t, float &entry) {
+        const float t1 = (lox - r.o.x) * r.inv.x;
+        const float t2 = (hix - r.o.x) * r.inv.x;
+        const float t3 = (loy - r.o.y) * r.inv.y;
+        const float t4 = (hiy - r.o.y) * r.inv.y;
+        const float t5 = (loz - r.o.z) * r.inv.z;
+        const float t6 = (hiz - r.o.z) * r.inv.z;
+        const float t_min = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+        const float t_max = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+        entry = fmaxf(t_min, 0.0F);
+        // child entered iff 0 <= slab result < best_t (scene.cpp:126, 137)
+        return t_max >= 0.0F && t_min <= t_max && entry < best_t;
+    }
+
     // fetch(k, o, d, limit) loads ray k; commit(k, hit) stores its result.  `cursor` is a zero-initialised device
     // counter shared by all warps of the launch; `count` the number of rays.
     template<bool ANY_HIT, bool COUNT, typename Fetch, typename Commit>
@@ -268,8 +284,7 @@ namespace ptb {
         hit.slot = -1;
         int32_t node = 0;
         int sp = 0;
-        int32_t stack_node[kStackCapacity];
-        float stack_t[kStackCapacity];
+        uint2 stack[kStackCapacity]; // (node ref, entry distance bits) of deferred far children
         bool exhausted = count == 0U;
         unsigned long long n_inner = 0;
         unsigned long long n_leaf = 0;
@@ -278,8 +293,9 @@ namespace ptb {
         auto advance = [&]() {
             while(sp > 0) {
                 sp--;
-                if(stack_t[sp] < best_t) {
-                    node = stack_node[sp];
+                const uint2 e = stack[sp];
+                if(__uint_as_float(e.y) < best_t) {
+                    node = static_cast<int32_t>(e.x);
                     status = node >= 0 ? kLaneInner : kLaneLeaf;
                     return;
                 }
@@ -289,8 +305,11 @@ namespace ptb {
         };
 
         for(;;) {
-            // ---- refill idle lanes
+            // ---- (A) refill idle lanes once enough of them wait
             const uint32_t idle_mask = __ballot_sync(0xFFFFFFFFU, status == kLaneIdle);
+            if(idle_mask == 0xFFFFFFFFU && exhausted) {
+                break;
+            }
             if(!exhausted && (__popc(idle_mask) >= kRefillVote || idle_mask == 0xFFFFFFFFU)) {
                 const uint32_t wanted = static_cast<uint32_t>(__popc(idle_mask));
                 uint32_t base = 0U;
@@ -331,85 +350,82 @@ namespace ptb {
                 }
             }
 
-            const uint32_t inner_mask = __ballot_sync(0xFFFFFFFFU, status == kLaneInner);
-            const uint32_t leaf_mask = __ballot_sync(0xFFFFFFFFU, status == kLaneLeaf);
-            if((inner_mask | leaf_mask) == 0U) {
-                if(exhausted) {
+            // ---- (B) descend: inner-node steps until enough lanes are parked at a leaf or waiting for a refill
+            for(;;) {
+                const uint32_t inner_mask = __ballot_sync(0xFFFFFFFFU, status == kLaneInner);
+                if(inner_mask == 0U) {
                     break;
                 }
-                continue;
-            }
-
-            // ---- one inner-node step for every lane that has one
-            if(status == kLaneInner) {
-                const float4 *rec = s.nodes + 4 * static_cast<size_t>(node);
-                float4 n0;
-                float4 n1;
-                float4 n2;
-                float4 n3;
-                ld256(rec, n0, n1);
-                ld256(rec + 2, n2, n3);
-                if(COUNT) {
-                    n_inner++;
-                }
-                const float lt = slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-                const float rt = slab(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
-                const int32_t left = __float_as_int(n3.x);
-                const int32_t right = __float_as_int(n3.y);
-                const bool left_first = lt < rt;
-                const float ct = left_first ? lt : rt;
-                const float ft = left_first ? rt : lt;
-                const int32_t cnode = left_first ? left : right;
-                const int32_t fnode = left_first ? right : left;
-                const bool vc = ct >= 0.0F && ct < best_t;
-                const bool vf = ft >= 0.0F && ft < best_t;
-                if(vc) {
-                    if(vf) {
-                        stack_node[sp] = fnode;
-                        stack_t[sp] = ft;
-                        sp++;
-                    }
-                    node = cnode;
-                    status = node >= 0 ? kLaneInner : kLaneLeaf;
-                }
-                else if(vf) {
-                    node = fnode;
-                    status = node >= 0 ? kLaneInner : kLaneLeaf;
-                }
-                else {
-                    advance();
-                }
-            }
-
-            // ---- primitive tests once enough lanes are parked at a leaf (or nothing else is left to do)
-            const uint32_t parked = __ballot_sync(0xFFFFFFFFU, status == kLaneLeaf);
-            const uint32_t descending = __ballot_sync(0xFFFFFFFFU, status == kLaneInner);
-            if(parked != 0U && (__popc(parked) >= kLeafVote || descending == 0U)) {
-                if(status == kLaneLeaf) {
-                    const uint32_t slot = static_cast<uint32_t>(~node);
+                if(status == kLaneInner) {
+                    const float4 *rec = s.nodes + 4 * static_cast<size_t>(node);
+                    float4 n0;
+                    float4 n1;
+                    float4 n2;
+                    float4 n3;
+                    ld256(rec, n0, n1);
+                    ld256(rec + 2, n2, n3);
                     if(COUNT) {
-                        n_leaf++;
+                        n_inner++;
                     }
-                    const float t = hitSlot(s, r, slot);
-                    if(ANY_HIT) {
-                        if(t >= 0.0F && t < limit) {
-                            hit.t = t;
-                            hit.slot = static_cast<int32_t>(slot);
-                            commit(k, hit);
-                            status = kLaneIdle;
-                        }
-                        else {
-                            advance();
-                        }
+                    float lt;
+                    float rt;
+                    const bool visit_left = slabVisit(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, best_t, lt);
+                    const bool visit_right = slabVisit(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, best_t, rt);
+                    const int32_t left = __float_as_int(n3.x);
+                    const int32_t right = __float_as_int(n3.y);
+                    if(visit_left && visit_right) {
+                        // nearer child first, the right one on ties (scene.cpp:122-123); the other is deferred
+                        const bool left_first = lt < rt;
+                        stack[sp] = make_uint2(static_cast<uint32_t>(left_first ? right : left), __float_as_uint(left_first ? rt : lt));
+                        sp++;
+                        node = left_first ? left : right;
+                        status = node >= 0 ? kLaneInner : kLaneLeaf;
+                    }
+                    else if(visit_left || visit_right) {
+                        node = visit_left ? left : right;
+                        status = node >= 0 ? kLaneInner : kLaneLeaf;
                     }
                     else {
-                        if(t >= 0.0F && (hit.slot < 0 || t <= best_t)) {
-                            best_t = t;
-                            hit.t = t;
-                            hit.slot = static_cast<int32_t>(slot);
-                        }
                         advance();
                     }
+                }
+                const uint32_t parked = __ballot_sync(0xFFFFFFFFU, status == kLaneLeaf);
+                if(__popc(parked) >= kLeafVote) {
+                    break;
+                }
+                if(!exhausted) {
+                    const uint32_t waiting = __ballot_sync(0xFFFFFFFFU, status == kLaneIdle);
+                    if(__popc(waiting) >= kRefillVote) {
+                        break;
+                    }
+                }
+            }
+
+            // ---- (C) primitive tests for every parked lane
+            if(status == kLaneLeaf) {
+                const uint32_t slot = static_cast<uint32_t>(~node);
+                if(COUNT) {
+                    n_leaf++;
+                }
+                const float t = hitSlot(s, r, slot);
+                if(ANY_HIT) {
+                    if(t >= 0.0F && t < limit) {
+                        hit.t = t;
+                        hit.slot = static_cast<int32_t>(slot);
+                        commit(k, hit);
+                        status = kLaneIdle;
+                    }
+                    else {
+                        advance();
+                    }
+                }
+                else {
+                    if(t >= 0.0F && (hit.slot < 0 || t <= best_t)) {
+                        best_t = t;
+                        hit.t = t;
+                        hit.slot = static_cast<int32_t>(slot);
+                    }
+                    advance();
                 }
             }
         }
