@@ -25,6 +25,9 @@
 namespace ptb {
 
     constexpr int kBlock = 128;
+#ifndef PTB_TRACE_MIN_BLOCKS
+#define PTB_TRACE_MIN_BLOCKS 12 // resident 128-thread CTAs per SM the trace kernels are compiled for (register cap 65536 / (12 * 128) = 42)
+#endif
 
     enum CounterSlot : int {
         kCountQueueA = 0,
@@ -198,11 +201,11 @@ namespace ptb {
 
     // Persistent warps over the device-side queue; scheduling by warp votes, see warpTrace in traverse.cuh.
     template<bool COUNT>
-    __global__ void __launch_bounds__(kBlock) traceClosestKernel(DeviceScene scene, PathPool pool, const uint32_t *__restrict__ queue,
+    __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) traceClosestKernel(DeviceScene scene, VoteParams vote, PathPool pool, const uint32_t *__restrict__ queue,
                                                                  uint32_t *__restrict__ counters, int queue_slot, VisitCounters *visits) {
         const uint32_t count = counters[queue_slot];
         warpTrace<false, COUNT>(
-          scene, &counters[kCountFetchClosest], count,
+          scene, vote, &counters[kCountFetchClosest], count,
           [&](uint32_t k, V3 &o, V3 &d, float &limit) {
               const uint32_t i = queue[k];
               const float4 ro = pool.ray_o[i];
@@ -215,7 +218,7 @@ namespace ptb {
     }
 
     template<bool COUNT>
-    __global__ void __launch_bounds__(kBlock) traceShadowKernel(DeviceScene scene, PathPool pool, const uint32_t *__restrict__ shadow_queue,
+    __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) traceShadowKernel(DeviceScene scene, VoteParams vote, PathPool pool, const uint32_t *__restrict__ shadow_queue,
                                                                 uint32_t *__restrict__ counters, uint32_t any_hit, VisitCounters *visits) {
         const uint32_t count = counters[kCountShadow];
         auto fetch = [&](uint32_t k, V3 &o, V3 &d, float &limit) {
@@ -228,13 +231,13 @@ namespace ptb {
         };
         if(any_hit != 0U) {
             warpTrace<true, COUNT>(
-              scene, &counters[kCountFetchShadow], count, fetch,
+              scene, vote, &counters[kCountFetchShadow], count, fetch,
               [&](uint32_t k, const Hit &h) { pool.shadow_c[shadow_queue[k]].w = h.slot < 0 ? 1.0F : 0.0F; }, visits);
         }
         else {
             // the reference's full closest-hit query (worker.cpp:84-86): unoccluded iff t < 0 or t >= |to_light| - epsilon
             warpTrace<false, COUNT>(
-              scene, &counters[kCountFetchShadow], count, fetch,
+              scene, vote, &counters[kCountFetchShadow], count, fetch,
               [&](uint32_t k, const Hit &h) {
                   const uint32_t slot = shadow_queue[k];
                   const float limit = pool.shadow_o[slot].w;
@@ -548,10 +551,10 @@ namespace ptb {
     // ------------------------------------------------------------------------------------------------ unit kernels
 
     template<bool COUNT>
-    __global__ void __launch_bounds__(kBlock) intersectKernel(DeviceScene scene, const float *__restrict__ rays, uint32_t n, float *__restrict__ t_out,
+    __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) intersectKernel(DeviceScene scene, VoteParams vote, const float *__restrict__ rays, uint32_t n, float *__restrict__ t_out,
                                                               int32_t *__restrict__ prim_out, uint32_t *__restrict__ cursor, VisitCounters *visits) {
         warpTrace<false, COUNT>(
-          scene, cursor, n,
+          scene, vote, cursor, n,
           [&](uint32_t k, V3 &o, V3 &d, float &limit) {
               const float *p = rays + 6 * static_cast<size_t>(k);
               o = mk3(p[0], p[1], p[2]);
@@ -566,10 +569,10 @@ namespace ptb {
     }
 
     template<bool COUNT>
-    __global__ void __launch_bounds__(kBlock) occludedKernel(DeviceScene scene, const float *__restrict__ rays, uint32_t n, uint8_t *__restrict__ out,
+    __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) occludedKernel(DeviceScene scene, VoteParams vote, const float *__restrict__ rays, uint32_t n, uint8_t *__restrict__ out,
                                                              uint32_t *__restrict__ cursor, VisitCounters *visits) {
         warpTrace<true, COUNT>(
-          scene, cursor, n,
+          scene, vote, cursor, n,
           [&](uint32_t k, V3 &o, V3 &d, float &limit) {
               const float *p = rays + 7 * static_cast<size_t>(k);
               o = mk3(p[0], p[1], p[2]);

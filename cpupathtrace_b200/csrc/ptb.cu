@@ -86,6 +86,8 @@ namespace {
 struct ptb_context {
     int device = 0;
     int sm_count = 0;
+    ptb::VoteParams vote{12, 6};
+    int trace_blocks_per_sm = 16;
     cudaStream_t stream = nullptr;
 
     // wavefront workspace
@@ -266,7 +268,7 @@ namespace {
         uint32_t *shadow_queue = ctx->shadow_queue.as<uint32_t>();
         VisitCounters *visits = ctx->visits.as<VisitCounters>();
 
-        const int trace_grid = gridFor(ctx, 16);
+        const int trace_grid = gridFor(ctx, ctx->trace_blocks_per_sm);
         int cur = 0;
         uint32_t n_cur = batch;
 
@@ -280,10 +282,10 @@ namespace {
             {
                 LaunchTimer timer(ctx, 0);
                 if(count_visits) {
-                    traceClosestKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, queues[cur], counters, cur, visits);
+                    traceClosestKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur, visits);
                 }
                 else {
-                    traceClosestKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, queues[cur], counters, cur, visits);
+                    traceClosestKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur, visits);
                 }
             }
             {
@@ -293,10 +295,10 @@ namespace {
             {
                 LaunchTimer timer(ctx, 0);
                 if(count_visits) {
-                    traceShadowKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, shadow_queue, counters, params.any_hit_shadows, visits);
+                    traceShadowKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, shadow_queue, counters, params.any_hit_shadows, visits);
                 }
                 else {
-                    traceShadowKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, shadow_queue, counters, params.any_hit_shadows, visits);
+                    traceShadowKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, shadow_queue, counters, params.any_hit_shadows, visits);
                 }
             }
             {
@@ -424,6 +426,9 @@ int ptb_context_create(int device, ptb_context **out) {
     PTB_CUDA(cudaEventCreate(&ctx->call_start));
     PTB_CUDA(cudaEventCreate(&ctx->call_stop));
     ctx->events_ready = envLong("PTB_PROFILE", 1) != 0;
+    ctx->vote.refill = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_REFILL_VOTE", 12))));
+    ctx->vote.leaf = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_LEAF_VOTE", 6))));
+    ctx->trace_blocks_per_sm = static_cast<int>(std::max(1L, envLong("PTB_TRACE_BLOCKS_PER_SM", 16)));
     *out = ctx;
     return PTB_OK;
 }
@@ -731,11 +736,11 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
         PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(uint32_t), ctx->stream));
         LaunchTimer timer(ctx, 0);
         if(count_visits) {
-            intersectKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays + 6 * first, n, d_t + first, d_prim + first, ctx->counters.as<uint32_t>(),
+            intersectKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, d_rays + 6 * first, n, d_t + first, d_prim + first, ctx->counters.as<uint32_t>(),
                                                                      ctx->visits.as<VisitCounters>());
         }
         else {
-            intersectKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays + 6 * first, n, d_t + first, d_prim + first, ctx->counters.as<uint32_t>(),
+            intersectKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, d_rays + 6 * first, n, d_t + first, d_prim + first, ctx->counters.as<uint32_t>(),
                                                                       ctx->visits.as<VisitCounters>());
         }
     }
@@ -793,11 +798,11 @@ int ptb_occluded(ptb_scene *scene, const float *rays, uint64_t n_rays, uint8_t *
         PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(uint32_t), ctx->stream));
         LaunchTimer timer(ctx, 0);
         if(count_visits) {
-            occludedKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
+            occludedKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
                                                                     ctx->visits.as<VisitCounters>());
         }
         else {
-            occludedKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
+            occludedKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
                                                                      ctx->visits.as<VisitCounters>());
         }
     }

@@ -237,14 +237,16 @@ namespace ptb {
     //   * a lane that has finished its ray does not wait for the slowest ray of a 32-ray batch: finished lanes are
     //     refilled from the device-side queue cursor as soon as kRefillVote of them are idle (one atomic per refill,
     //     claimed by ballot/popc/shfl);
-    //   * a lane that has arrived at a leaf parks until kLeafVote lanes are parked (or no lane has inner work left),
+    //   * a lane that has arrived at a leaf parks until vote.leaf (default 6) lanes are parked (or no lane has inner work left),
     //     then the parked lanes run the primitive test together; inner-node steps run for all unparked lanes.
     //
     // Measured with ncu before this change (profiles/r01_ncu_trace_baseline.md): 6.3 (closest) and 3.4 (shadow)
     // active threads per issued instruction with issue slots 75 % busy, i.e. the kernels were bound by SIMT divergence,
     // not by memory.
-    constexpr int kRefillVote = 8;
-    constexpr int kLeafVote = 8;
+    struct VoteParams {
+        int refill; // idle lanes that trigger a refill
+        int leaf;   // parked lanes that trigger the primitive tests
+    };
 
     enum LaneStatus : uint32_t { kLaneIdle = 0U, kLaneInner = 1U, kLaneLeaf = 2U };
 
@@ -267,7 +269,9 @@ namespace ptb {
     // fetch(k, o, d, limit) loads ray k; commit(k, hit) stores its result.  `cursor` is a zero-initialised device
     // counter shared by all warps of the launch; `count` the number of rays.
     template<bool ANY_HIT, bool COUNT, typename Fetch, typename Commit>
-    PTB_DEV void warpTrace(const DeviceScene &s, uint32_t *cursor, uint32_t count, Fetch fetch, Commit commit, VisitCounters *counters) {
+    PTB_DEV void warpTrace(const DeviceScene &s, VoteParams vote, uint32_t *cursor, uint32_t count, Fetch fetch, Commit commit, VisitCounters *counters) {
+        const int kRefillVote = vote.refill;
+        const int kLeafVote = vote.leaf;
         const uint32_t lane = threadIdx.x & 31U;
         const uint32_t lanes_below = (1U << lane) - 1U;
 
