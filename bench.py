@@ -441,6 +441,21 @@ def run_b200_arm(args):
 
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line (rank 0).  Libraries write there too (NCCL prints its version banner to
+    # stdout when NCCL_DEBUG=VERSION is set in the environment), so everything else is sent to stderr: file descriptor 1
+    # is pointed at stderr for the duration of the run and the JSON line goes to the saved original stdout.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved_stdout, "w")
+    global print
+    builtin_print = print
+
+    def print(*a, **k):  # noqa: A001 - only the final JSON line is printed in this module
+        k.setdefault("file", real_stdout)
+        builtin_print(*a, **k)
+        real_stdout.flush()
+
     if args.impl == "reference":
         run_reference_arm(args)
     else:
