@@ -128,28 +128,39 @@ namespace ptb {
 
     // ------------------------------------------------------------------------------------------------ generate
 
-    // Batch element i is global work item g = first + i of the pixel group: sample = g / n_pixels,
-    // pixel = pixel_list[g % n_pixels] (x | y << 16), destination = sample * n_pixels + pixel index.
-    __global__ void __launch_bounds__(kBlock) generateKernel(PathPool pool, RenderParams params, const uint32_t *__restrict__ pixel_list, uint32_t n_pixels,
-                                                             uint64_t first, uint32_t count, uint32_t *__restrict__ queue, uint32_t *__restrict__ counters,
-                                                             int queue_slot) {
-        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-        if(i == 0U) {
-            counters[queue_slot] = count;
+    // Where new paths come from.  Work item g of a call is
+    //   frame mode     : sample = g / n_pixels of pixel pixel_list[g % n_pixels] (x | y << 16), keyed on (seed, x, y, sample)
+    //   validation mode: the explicit (pixel, seed) pair g, engine RandomEngine(seeds[g])
+    // and its result goes to samples[g].
+    struct PathSource {
+        const uint32_t *pixel_list;
+        const int32_t *pixels;
+        const uint64_t *seeds;
+        uint32_t n_pixels;
+        uint32_t explicit_samples;
+        unsigned long long total;
+    };
+
+    // Camera::shootRay for work item g into pool slot i (worker.cpp:27-34, 168-170)
+    PTB_DEV void generatePath(const PathPool &pool, const RenderParams &params, const PathSource &src, uint32_t i, unsigned long long g) {
+        int px;
+        int py;
+        uint64_t key;
+        if(src.explicit_samples != 0U) {
+            px = src.pixels[2 * g];
+            py = src.pixels[2 * g + 1];
+            key = src.seeds[g];
         }
-        if(i >= count) {
-            return;
+        else {
+            const uint32_t sample = static_cast<uint32_t>(g / src.n_pixels);
+            const uint32_t packed = src.pixel_list[static_cast<uint32_t>(g % src.n_pixels)];
+            px = static_cast<int>(packed & 0xFFFFU);
+            py = static_cast<int>(packed >> 16);
+            key = counterKey(params.seed, static_cast<uint32_t>(px), static_cast<uint32_t>(py), sample);
         }
-        const uint64_t g = first + i;
-        const uint32_t sample = static_cast<uint32_t>(g / n_pixels);
-        const uint32_t q = static_cast<uint32_t>(g % n_pixels);
-        const uint32_t packed = pixel_list[q];
-        const int px = static_cast<int>(packed & 0xFFFFU);
-        const int py = static_cast<int>(packed >> 16);
 
         PathRegs p;
         initPath(p);
-        const uint64_t key = counterKey(params.seed, static_cast<uint32_t>(px), static_cast<uint32_t>(py), sample);
         p.rng.xorshift = params.rng_xorshift;
         p.rng.counter = 0U;
         p.rng.state = params.rng_xorshift != 0U ? xorshiftSeed(key) : key;
@@ -162,13 +173,14 @@ namespace ptb {
 
         storePath(pool, i, p, params.rng_xorshift != 0U ? kFlagXorshift : 0U);
         pool.dest[i] = static_cast<uint32_t>(g);
-        queue[i] = i;
+        pool.shadow_count[i] = 0U;
     }
 
-    // Validation batch: explicit (pixel, seed) pairs, RandomEngine(seed) per sample, destination = i
-    __global__ void __launch_bounds__(kBlock) generateSamplesKernel(PathPool pool, RenderParams params, const int32_t *__restrict__ pixels,
-                                                                    const uint64_t *__restrict__ seeds, uint64_t first, uint32_t count,
-                                                                    uint32_t *__restrict__ queue, uint32_t *__restrict__ counters, int queue_slot) {
+    // Fills pool slots [0, count) with work items [0, count) and queues them; later work items are started by the
+    // accumulate kernel in the slots of retired paths (path regeneration), so the pool stays full until the call's
+    // work runs out and only the very last bounce iterations of a call run on a thin queue.
+    __global__ void __launch_bounds__(kBlock) generateKernel(PathPool pool, RenderParams params, PathSource src, uint32_t count, uint32_t *__restrict__ queue,
+                                                             uint32_t *__restrict__ counters, int queue_slot) {
         const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
         if(i == 0U) {
             counters[queue_slot] = count;
@@ -176,24 +188,7 @@ namespace ptb {
         if(i >= count) {
             return;
         }
-        const uint64_t g = first + i;
-        const int px = pixels[2 * g];
-        const int py = pixels[2 * g + 1];
-
-        PathRegs p;
-        initPath(p);
-        p.rng.xorshift = params.rng_xorshift;
-        p.rng.counter = 0U;
-        p.rng.state = params.rng_xorshift != 0U ? xorshiftSeed(seeds[g]) : seeds[g];
-
-        float x_camera;
-        float y_camera;
-        pixelToCamera(px, py, params.image_width, params.image_height, x_camera, y_camera);
-        shootRay(params.camera, x_camera, y_camera, 1.0F / static_cast<float>(params.image_width), 1.0F / static_cast<float>(params.image_height), p.rng,
-                 p.ray_o, p.ray_d);
-
-        storePath(pool, i, p, params.rng_xorshift != 0U ? kFlagXorshift : 0U);
-        pool.dest[i] = i;
+        generatePath(pool, params, src, i, i);
         queue[i] = i;
     }
 
@@ -331,14 +326,16 @@ namespace ptb {
 
     // ------------------------------------------------------------------------------------------------ accumulate
 
-    __global__ void __launch_bounds__(kBlock) accumulateKernel(PathPool pool, const uint32_t *__restrict__ queue, uint32_t *__restrict__ counters,
-                                                               int queue_slot, uint32_t *__restrict__ next_queue, int next_slot, float4 *__restrict__ samples) {
+    __global__ void __launch_bounds__(kBlock) accumulateKernel(PathPool pool, RenderParams params, PathSource src, const uint32_t *__restrict__ queue,
+                                                               uint32_t *__restrict__ counters, int queue_slot, uint32_t *__restrict__ next_queue, int next_slot,
+                                                               float4 *__restrict__ samples, unsigned long long *__restrict__ work_cursor) {
         const uint32_t count = counters[queue_slot];
         const uint32_t stride = gridDim.x * blockDim.x;
         const uint32_t rounded = (count + 31U) & ~31U;
         for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < rounded; k += stride) {
             const bool active = k < count;
             bool survives = false;
+            bool retired = false;
             uint32_t i = 0U;
             if(active) {
                 i = queue[k];
@@ -362,11 +359,31 @@ namespace ptb {
                     // out_color[3] = sample_collected ? 1 : 0 (worker.cpp:141-143)
                     const bool collected = (st >> 8) > 0U;
                     samples[pool.dest[i]] = make_float4(radiance.x, radiance.y, radiance.z, collected ? 1.0F : 0.0F);
+                    retired = true;
                 }
                 else {
                     survives = true;
                 }
             }
+
+            // path regeneration: a retired path's slot takes the next unstarted work item of the call
+            const uint32_t retired_mask = __ballot_sync(0xFFFFFFFFU, retired);
+            if(retired_mask != 0U) {
+                const uint32_t leader = __ffs(retired_mask) - 1U;
+                unsigned long long base = 0ULL;
+                if(laneId() == leader) {
+                    base = atomicAdd(work_cursor, static_cast<unsigned long long>(__popc(retired_mask)));
+                }
+                base = __shfl_sync(0xFFFFFFFFU, base, leader);
+                if(retired) {
+                    const unsigned long long g = base + static_cast<unsigned long long>(__popc(retired_mask & ((1U << laneId()) - 1U)));
+                    if(g < src.total) {
+                        generatePath(pool, params, src, i, g);
+                        survives = true;
+                    }
+                }
+            }
+
             const uint32_t at = warpAppend(&counters[next_slot], survives);
             if(survives) {
                 next_queue[at] = i;

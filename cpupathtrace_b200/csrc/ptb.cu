@@ -97,6 +97,7 @@ struct ptb_context {
     Buffer shadow_queue;
     Buffer counters;
     Buffer visits;
+    Buffer work_cursor;
     Buffer samples;
     Buffer pixel_list;
     Buffer io_a; // staging for host<->device bulk arrays
@@ -242,6 +243,9 @@ namespace {
         if((status = ctx->visits.reserve(sizeof(VisitCounters))) != PTB_OK) {
             return status;
         }
+        if((status = ctx->work_cursor.reserve(sizeof(unsigned long long))) != PTB_OK) {
+            return status;
+        }
         return PTB_OK;
     }
 
@@ -259,8 +263,9 @@ namespace {
         return p;
     }
 
-    // Runs the bounce loop for a batch whose primary rays are already generated into queue A.
-    int runBounces(ptb_scene *scene, const PathPool &pool, const RenderParams &params, uint32_t batch, float4 *samples, bool count_visits,
+    // Starts the first `first_wave` work items of `src` in the pool and runs bounce iterations until every work item of
+    // the call has been retired into `samples` (retired slots are refilled by the accumulate kernel).
+    int runBounces(ptb_scene *scene, const PathPool &pool, const RenderParams &params, const PathSource &src, float4 *samples, bool count_visits,
                    ptb_render_stats *stats) {
         ptb_context *ctx = scene->ctx;
         uint32_t *counters = ctx->counters.as<uint32_t>();
@@ -269,8 +274,22 @@ namespace {
         VisitCounters *visits = ctx->visits.as<VisitCounters>();
 
         const int trace_grid = gridFor(ctx, ctx->trace_blocks_per_sm);
+        const uint32_t first_wave = static_cast<uint32_t>(std::min<unsigned long long>(pool.capacity, src.total));
+        unsigned long long *work_cursor = ctx->work_cursor.as<unsigned long long>();
+        {
+            const unsigned long long started = first_wave;
+            PTB_CUDA(cudaMemcpyAsync(work_cursor, &started, sizeof(started), cudaMemcpyHostToDevice, ctx->stream));
+            PTB_CUDA(cudaStreamSynchronize(ctx->stream)); // `started` lives on this stack frame
+            LaunchTimer timer(ctx, 1);
+            generateKernel<<<(first_wave + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(pool, params, src, first_wave, queues[0], counters, kCountQueueA);
+        }
+        PTB_CUDA(cudaGetLastError());
+        if(stats != nullptr) {
+            stats->samples += src.total;
+            stats->kernel_launches += 1;
+        }
         int cur = 0;
-        uint32_t n_cur = batch;
+        uint32_t n_cur = first_wave;
 
         while(n_cur > 0U) {
             const int nxt = cur ^ 1;
@@ -303,7 +322,7 @@ namespace {
             }
             {
                 LaunchTimer timer(ctx, 1);
-                accumulateKernel<<<flat_grid, kBlock, 0, ctx->stream>>>(pool, queues[cur], counters, cur, queues[nxt], nxt, samples);
+                accumulateKernel<<<flat_grid, kBlock, 0, ctx->stream>>>(pool, params, src, queues[cur], counters, cur, queues[nxt], nxt, samples, work_cursor);
             }
             PTB_CUDA(cudaMemcpyAsync(ctx->host_counters, counters, kCounterSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
             PTB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -439,7 +458,7 @@ int ptb_context_destroy(ptb_context *ctx) {
     }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->counters, &ctx->visits, &ctx->samples, &ctx->pixel_list,
+    for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->counters, &ctx->visits, &ctx->work_cursor, &ctx->samples, &ctx->pixel_list,
                      &ctx->io_a, &ctx->io_b, &ctx->io_c, &ctx->io_d}) {
         b->release();
     }
@@ -865,23 +884,16 @@ int ptb_render_samples(ptb_scene *scene, const ptb_camera *camera, const ptb_ren
     PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, sizeof(VisitCounters), ctx->stream));
 
     const RenderParams params = makeParams(*camera, *opts);
-    for(uint64_t first = 0; first < n; first += capacity) {
-        const uint32_t batch = static_cast<uint32_t>(std::min<uint64_t>(capacity, n - first));
-        const int grid = static_cast<int>((batch + kBlock - 1) / kBlock);
-        {
-            LaunchTimer timer(ctx, 1);
-            generateSamplesKernel<<<grid, kBlock, 0, ctx->stream>>>(pool, params, d_pixels, d_seeds, first, batch, ctx->queue_a.as<uint32_t>(),
-                                                                    ctx->counters.as<uint32_t>(), kCountQueueA);
-        }
-        PTB_CUDA(cudaGetLastError());
-        if(stats != nullptr) {
-            stats->samples += batch;
-            stats->kernel_launches += 1;
-        }
-        // destinations are batch-local; offset the output pointer
-        if((status = runBounces(scene, pool, params, batch, d_out + first, count_visits, stats)) != PTB_OK) {
-            return status;
-        }
+    if(n > 0xFFFFFFFFULL) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render_samples: more than 2^32 - 1 samples in one call");
+    }
+    PathSource src{};
+    src.pixels = d_pixels;
+    src.seeds = d_seeds;
+    src.explicit_samples = 1U;
+    src.total = n;
+    if((status = runBounces(scene, pool, params, src, d_out, count_visits, stats)) != PTB_OK) {
+        return status;
     }
     if(!device_io) {
         PTB_CUDA(cudaMemcpyAsync(out_rgba, d_out, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
@@ -997,22 +1009,13 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
             return status;
         }
 
-        for(uint64_t first = 0; first < total; first += capacity) {
-            const uint32_t batch = static_cast<uint32_t>(std::min<uint64_t>(capacity, total - first));
-            const int grid = static_cast<int>((batch + kBlock - 1) / kBlock);
-            {
-                LaunchTimer timer(ctx, 1);
-                generateKernel<<<grid, kBlock, 0, ctx->stream>>>(pool, params, ctx->pixel_list.as<uint32_t>(), n_pixels, first, batch,
-                                                                 ctx->queue_a.as<uint32_t>(), ctx->counters.as<uint32_t>(), kCountQueueA);
-            }
-            PTB_CUDA(cudaGetLastError());
-            if(stats != nullptr) {
-                stats->samples += batch;
-                stats->kernel_launches += 1;
-            }
-            if((status = runBounces(scene, pool, params, batch, ctx->samples.as<float4>(), count_visits, stats)) != PTB_OK) {
-                return status;
-            }
+        PathSource src{};
+        src.pixel_list = ctx->pixel_list.as<uint32_t>();
+        src.n_pixels = n_pixels;
+        src.explicit_samples = 0U;
+        src.total = total;
+        if((status = runBounces(scene, pool, params, src, ctx->samples.as<float4>(), count_visits, stats)) != PTB_OK) {
+            return status;
         }
 
         ResolveParams rp{};
