@@ -10,9 +10,9 @@
 //              (normal_a, material) (normal_b, 0) (normal_c, 0)
 //   mats   : 3 x float4 per material   (48 B): diffuse, emission, (ior, bsdf, one_way, 0)
 //   lights : 2 x float4 per point light: (pos, 0) (rgba)
-//   emis   : 3 x float4 per emissive primitive, registration order (scene.cpp:183-208): triangle (a,slot)(b,0)(c,0);
-//            sphere (origin, slot)(radius, radius^2, 0, 0)(0)   [the un-differenced vertices are needed by
-//            Triangle::sampleSurface, object.cpp:192-207]
+//   emis   : 3 x float4 per emissive primitive, registration order (scene.cpp:183-208): triangle (a,slot)(b,p)(c,0);
+//            sphere (origin, slot)(radius, radius^2, 0, p)(0); p = sampling density 1/area   [the un-differenced
+//            vertices are needed by Triangle::sampleSurface, object.cpp:192-207]
 //   cdf    : one float per emissive primitive (scene.cpp:169-180)
 //
 // One primitive per leaf, as in the reference; slot = position in left-to-right leaf order, which is also the

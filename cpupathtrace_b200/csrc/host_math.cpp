@@ -92,6 +92,19 @@ namespace ptb {
         return 0.0F;
     }
 
+    // Object::sampleSurface's density: Triangle 1 / area (object.cpp:203-204), Sphere 1 / (4 pi r^2) (:113)
+    float primSampleDensity(const ptb_prim &prim) {
+        if(prim.kind == PTB_PRIM_TRIANGLE) {
+            return 1.0F / primSurfaceArea(prim);
+        }
+        if(prim.kind == PTB_PRIM_SPHERE) {
+            constexpr float pi = static_cast<float>(M_PI);
+            const float radius2 = prim.p[3] * prim.p[3];
+            return 1.0F / (4.0F * pi * radius2);
+        }
+        return 0.0F;
+    }
+
     // Scene::registerEmissiveObjects + the prefix sum / normalisation of Scene::Scene (scene.cpp:165-208),
     // visiting primitives in leaf (slot) order.
     EmissiveTable buildEmissiveTable(const ptb_prim *prims, const ptb_material *materials, const uint32_t *slot_to_prim, uint64_t n_prims) {

@@ -12,6 +12,7 @@ namespace ptb {
                     float aperture_width, float aperture_height, uint32_t aperture_kind, float hexagon_horizontal_ratio, float focal_plane_dist);
 
     float primSurfaceArea(const ptb_prim &prim);
+    float primSampleDensity(const ptb_prim &prim);
 
     struct EmissiveTable {
         std::vector<uint32_t> slots; // leaf slots of the emissive primitives, registration order

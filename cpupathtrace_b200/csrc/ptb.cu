@@ -612,6 +612,7 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
             e2 = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
         }
         std::memcpy(&e0.w, &slot, sizeof(uint32_t));
+        e1.w = primSampleDensity(prim);
         emis[3 * i] = e0;
         emis[3 * i + 1] = e1;
         emis[3 * i + 2] = e2;
@@ -1217,14 +1218,14 @@ namespace {
             l.shade[1] = make_float4(p[12], p[13], p[14], 0.0F);
             l.shade[2] = make_float4(p[15], p[16], p[17], 0.0F);
             l.raw[0] = make_float4(p[0], p[1], p[2], 0.0F);
-            l.raw[1] = make_float4(p[3], p[4], p[5], 0.0F);
+            l.raw[1] = make_float4(p[3], p[4], p[5], primSampleDensity(prim));
             l.raw[2] = make_float4(p[6], p[7], p[8], 0.0F);
         }
         else if(prim.kind == PTB_PRIM_SPHERE) {
             l.geom[0] = make_float4(p[0], p[1], p[2], 0.0F);
             l.geom[1] = make_float4(p[3], p[3] * p[3], 0.0F, 0.0F);
             l.raw[0] = l.geom[0];
-            l.raw[1] = l.geom[1];
+            l.raw[1] = make_float4(p[3], p[3] * p[3], 0.0F, primSampleDensity(prim));
         }
         std::memcpy(&l.geom[0].w, &l.flags, sizeof(uint32_t));
         return l;

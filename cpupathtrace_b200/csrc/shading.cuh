@@ -167,21 +167,20 @@ namespace ptb {
             const float r2 = rng.uniform01();
             const float rr1 = sqrtf(r1);
             surface_pos = (a * (1.0F - rr1) + b * (rr1 * (1.0F - r2))) + c * (rr1 * r2);
-            const float area = length(cross(b - a, c - a)) / 2.0F;
-            surface_p = 1.0F / area;
+            // p = 1 / (|cross(b - a, c - a)| / 2), evaluated once on the host with the same operations (host_math.cpp)
+            surface_p = e1.w;
             surface_cull = (flags & kCullBit) != 0U;
         }
         else if((flags & kKindMask) == PTB_PRIM_SPHERE) {
             const V3 origin = mk3(e0.x, e0.y, e0.z);
             const float radius = e1.x;
-            const float radius2 = e1.y;
             const float theta = kTwoPi * rng.uniform01();
             const float phi = glibcAcosf(1.0F - 2.0F * rng.uniform01());
             const float x = glibcSinf(phi) * glibcCosf(theta);
             const float y = glibcSinf(phi) * glibcSinf(theta);
             const float z = glibcCosf(phi);
             surface_pos = origin + mk3(x, y, z) * radius;
-            surface_p = 1.0F / ((4.0F * kPi) * radius2);
+            surface_p = e1.w; // 1 / (4 pi r^2), evaluated once on the host
             surface_cull = false;
         }
         else {

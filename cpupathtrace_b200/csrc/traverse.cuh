@@ -298,7 +298,8 @@ namespace ptb {
             while(sp > 0) {
                 sp--;
                 const uint2 e = stack[sp];
-                if(__uint_as_float(e.y) < best_t) {
+                // any-hit: the bound never shrinks, so an entry that passed `entry < limit` when deferred still passes
+                if(ANY_HIT || __uint_as_float(e.y) < best_t) {
                     node = static_cast<int32_t>(e.x);
                     status = node >= 0 ? kLaneInner : kLaneLeaf;
                     return;

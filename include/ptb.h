@@ -5,9 +5,9 @@
  *
  *     processJob -> processItem -> impl::getSample -> Scene::getIntersection / Scene::sampleLights / BSDF
  *
- * The reference has no plugin/FFI layer; its boundary is the public C++ API in include/PathTrace/** (reference
+ * The reference has no plugin/FFI layer; its boundary is the public C++ API in include/PathTrace (reference
  * include/PathTrace/worker.h:69,83-84, include/PathTrace/scene/scene.h:32,41,54, include/PathTrace/camera.h:92,108,123).
- * The C++ host layer of this repository (include/PathTrace/** + cpupathtrace_b200/host/**) re-provides exactly that
+ * The C++ host layer of this repository (include/PathTrace + cpupathtrace_b200/host) re-provides exactly that
  * API and forwards the hot path through the entry points declared below.  A binding from any other language
  * (ctypes, cgo, JNI, N-API) binds these functions directly; see INTEGRATION.md.
  *
