@@ -62,6 +62,16 @@ namespace ptb {
         return static_cast<float>(fma(x6, c2, c));
     }
 
+    // Arguments outside the ranges the render path can produce go to CUDA's own routines through real calls, so that
+    // the (never taken) fallbacks are not if-converted into the hot path.
+    __device__ __noinline__ float libmFallbackSinCos(float y, int which) {
+        return which == 0 ? sinf(y) : cosf(y);
+    }
+
+    __device__ __noinline__ float libmFallbackPowHalf(float x) {
+        return powf(x, 0.5F);
+    }
+
     // which = 0: sinf(y), which = 1: cosf(y)
     PTB_DEV float glibcSinCos(float y, int which) {
         const uint32_t top = absTop12(y);
@@ -80,7 +90,7 @@ namespace ptb {
             const SinCosTable &p = kSinCosTable[(n & 2) ? 1 : 0];
             return sinCosPoly(x * s, x * x, p, which == 0 ? n : (n ^ 1));
         }
-        return which == 0 ? sinf(y) : cosf(y); // outside the path's argument range
+        return libmFallbackSinCos(y, which); // |y| >= 120: outside the path's argument range
     }
 
     PTB_DEV float glibcSinf(float y) {
@@ -104,7 +114,7 @@ namespace ptb {
         }
         if(ix - 0x00800000U >= 0x7f800000U - 0x00800000U) {
             if(ix >= 0x7f800000U) {
-                return powf(x, 0.5F); // negative, inf or NaN: outside the path's argument range
+                return libmFallbackPowHalf(x); // negative, inf or NaN: outside the path's argument range
             }
             // subnormal: normalise (e_powf.c)
             ix = __float_as_uint(x * 0x1p23F);

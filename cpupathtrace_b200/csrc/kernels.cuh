@@ -96,13 +96,19 @@ namespace ptb {
         return base + __popc(mask & ((1U << laneId()) - 1U));
     }
 
-    PTB_DEV void loadPath(const PathPool &pool, uint32_t i, PathRegs &p, uint32_t &flags) {
+    // The alpha lane of the throughput and radiance spectra is never observable: impl::getSample overwrites the
+    // output alpha with the "collected" flag (worker.cpp:141-143) and getContribution reads rgb only (worker.cpp:12-14).
+    // It is therefore not carried through the pool (constant lanes let the compiler drop the alpha arithmetic).
+    template<typename RNG>
+    PTB_DEV void loadPath(const PathPool &pool, uint32_t i, PathRegs<RNG> &p, uint32_t &flags) {
         const float4 o = pool.ray_o[i];
         const float4 d = pool.ray_d[i];
         p.ray_o = mk3(o.x, o.y, o.z);
         p.ray_d = mk3(d.x, d.y, d.z);
-        p.throughput = v4(pool.throughput[i]);
-        p.radiance = v4(pool.radiance[i]);
+        const float4 thr = pool.throughput[i];
+        const float4 rad = pool.radiance[i];
+        p.throughput = V4{thr.x, thr.y, thr.z, 1.0F};
+        p.radiance = V4{rad.x, rad.y, rad.z, 0.0F};
         p.divisor = pool.divisor[i];
         p.bounce_pd = pool.bounce_pd[i];
         p.contribution_unweighted = pool.contribution[i];
@@ -111,14 +117,14 @@ namespace ptb {
         flags = st & 0xFFU;
         p.rng.state = pool.rng[i];
         p.rng.counter = 0U;
-        p.rng.xorshift = (flags & kFlagXorshift) != 0U ? 1U : 0U;
     }
 
-    PTB_DEV void storePath(const PathPool &pool, uint32_t i, const PathRegs &p, uint32_t flags) {
+    template<typename RNG>
+    PTB_DEV void storePath(const PathPool &pool, uint32_t i, const PathRegs<RNG> &p, uint32_t flags) {
         pool.ray_o[i] = make_float4(p.ray_o.x, p.ray_o.y, p.ray_o.z, 0.0F);
         pool.ray_d[i] = make_float4(p.ray_d.x, p.ray_d.y, p.ray_d.z, 0.0F);
-        pool.throughput[i] = f4(p.throughput);
-        pool.radiance[i] = f4(p.radiance);
+        pool.throughput[i] = make_float4(p.throughput.x, p.throughput.y, p.throughput.z, 1.0F);
+        pool.radiance[i] = make_float4(p.radiance.x, p.radiance.y, p.radiance.z, 0.0F);
         pool.divisor[i] = p.divisor;
         pool.bounce_pd[i] = p.bounce_pd;
         pool.contribution[i] = p.contribution_unweighted;
@@ -142,6 +148,7 @@ namespace ptb {
     };
 
     // Camera::shootRay for work item g into pool slot i (worker.cpp:27-34, 168-170)
+    template<typename RNG>
     PTB_DEV void generatePath(const PathPool &pool, const RenderParams &params, const PathSource &src, uint32_t i, unsigned long long g) {
         int px;
         int py;
@@ -159,11 +166,10 @@ namespace ptb {
             key = counterKey(params.seed, static_cast<uint32_t>(px), static_cast<uint32_t>(py), sample);
         }
 
-        PathRegs p;
+        PathRegs<RNG> p;
         initPath(p);
-        p.rng.xorshift = params.rng_xorshift;
         p.rng.counter = 0U;
-        p.rng.state = params.rng_xorshift != 0U ? xorshiftSeed(key) : key;
+        p.rng.state = RNG::kXorshift ? xorshiftSeed(key) : key;
 
         float x_camera;
         float y_camera;
@@ -171,7 +177,7 @@ namespace ptb {
         shootRay(params.camera, x_camera, y_camera, 1.0F / static_cast<float>(params.image_width), 1.0F / static_cast<float>(params.image_height), p.rng,
                  p.ray_o, p.ray_d);
 
-        storePath(pool, i, p, params.rng_xorshift != 0U ? kFlagXorshift : 0U);
+        storePath(pool, i, p, RNG::kXorshift ? kFlagXorshift : 0U);
         pool.dest[i] = static_cast<uint32_t>(g);
         pool.shadow_count[i] = 0U;
     }
@@ -179,6 +185,7 @@ namespace ptb {
     // Fills pool slots [0, count) with work items [0, count) and queues them; later work items are started by the
     // accumulate kernel in the slots of retired paths (path regeneration), so the pool stays full until the call's
     // work runs out and only the very last bounce iterations of a call run on a thin queue.
+    template<typename RNG>
     __global__ void __launch_bounds__(kBlock) generateKernel(PathPool pool, RenderParams params, PathSource src, uint32_t count, uint32_t *__restrict__ queue,
                                                              uint32_t *__restrict__ counters, int queue_slot) {
         const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,7 +195,7 @@ namespace ptb {
         if(i >= count) {
             return;
         }
-        generatePath(pool, params, src, i, i);
+        generatePath<RNG>(pool, params, src, i, i);
         queue[i] = i;
     }
 
@@ -244,16 +251,17 @@ namespace ptb {
 
     // ------------------------------------------------------------------------------------------------ shade
 
+    template<typename RNG>
     __global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene scene, PathPool pool, RenderParams params, const uint32_t *__restrict__ queue,
                                                           uint32_t *__restrict__ counters, int queue_slot, uint32_t *__restrict__ shadow_queue) {
         const uint32_t count = counters[queue_slot];
         const uint32_t stride = gridDim.x * blockDim.x;
-        // whole warps iterate together so that the warp-aggregated appends see converged lanes
+        // whole warps iterate together so that the warp-wide scans below see all 32 lanes
         const uint32_t rounded = (count + 31U) & ~31U;
         for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < rounded; k += stride) {
             const bool active = k < count;
             uint32_t i = 0U;
-            PathRegs p;
+            PathRegs<RNG> p;
             uint32_t flags = 0U;
             bool hit_surface = false;
             float t = -1.0F;
@@ -296,23 +304,29 @@ namespace ptb {
                 pool.shadow_count[i] = n_shadow;
             }
 
-            for(uint32_t j = 0U; j < pool.shadow_stride; j++) {
-                const bool has = active && j < n_shadow;
-                if(__ballot_sync(0xFFFFFFFFU, has) == 0U) {
-                    break;
+            // queue the shadow rays: exclusive warp scan of the per-lane counts, one atomic per warp
+            uint32_t inclusive = n_shadow;
+            for(int offset = 1; offset < 32; offset <<= 1) {
+                const uint32_t below = __shfl_up_sync(0xFFFFFFFFU, inclusive, offset);
+                if(laneId() >= static_cast<uint32_t>(offset)) {
+                    inclusive += below;
                 }
-                const uint32_t at = warpAppend(&counters[kCountShadow], has);
-                if(has) {
-                    shadow_queue[at] = shadow_base + j;
+            }
+            const uint32_t warp_total = __shfl_sync(0xFFFFFFFFU, inclusive, 31);
+            if(warp_total != 0U) {
+                uint32_t base = 0U;
+                if(laneId() == 0U) {
+                    base = atomicAdd(&counters[kCountShadow], warp_total);
+                }
+                base = __shfl_sync(0xFFFFFFFFU, base, 0) + (inclusive - n_shadow);
+                for(uint32_t j = 0U; j < n_shadow; j++) {
+                    shadow_queue[base + j] = shadow_base + j;
                 }
             }
 
             // statistics: one atomic per warp
             const uint32_t hit_mask = __ballot_sync(0xFFFFFFFFU, active && hit_surface);
-            uint32_t skipped = n_skipped;
-            for(int offset = 16; offset > 0; offset >>= 1) {
-                skipped += __shfl_xor_sync(0xFFFFFFFFU, skipped, offset);
-            }
+            const uint32_t skipped = __reduce_add_sync(0xFFFFFFFFU, n_skipped);
             if(laneId() == 0U) {
                 if(hit_mask != 0U) {
                     atomicAdd(&counters[kCountVertices], static_cast<uint32_t>(__popc(hit_mask)));
@@ -326,6 +340,7 @@ namespace ptb {
 
     // ------------------------------------------------------------------------------------------------ accumulate
 
+    template<typename RNG>
     __global__ void __launch_bounds__(kBlock) accumulateKernel(PathPool pool, RenderParams params, PathSource src, const uint32_t *__restrict__ queue,
                                                                uint32_t *__restrict__ counters, int queue_slot, uint32_t *__restrict__ next_queue, int next_slot,
                                                                float4 *__restrict__ samples, unsigned long long *__restrict__ work_cursor) {
@@ -378,7 +393,7 @@ namespace ptb {
                 if(retired) {
                     const unsigned long long g = base + static_cast<unsigned long long>(__popc(retired_mask & ((1U << laneId()) - 1U)));
                     if(g < src.total) {
-                        generatePath(pool, params, src, i, g);
+                        generatePath<RNG>(pool, params, src, i, g);
                         survives = true;
                     }
                 }
@@ -620,9 +635,8 @@ namespace ptb {
         t_out[k] = hitSlot(scene, r, 0U);
     }
 
-    PTB_DEV Rng engineFromState(uint64_t state) {
-        Rng rng;
-        rng.xorshift = 1U;
+    PTB_DEV ReferenceRng engineFromState(uint64_t state) {
+        ReferenceRng rng;
         rng.counter = 0U;
         rng.state = state;
         return rng;
@@ -634,7 +648,7 @@ namespace ptb {
         if(k >= n) {
             return;
         }
-        Rng rng = engineFromState(states[k]);
+        ReferenceRng rng = engineFromState(states[k]);
         V3 o;
         V3 d;
         shootRay(camera, xy[2 * k], xy[2 * k + 1], pixel_width, pixel_height, rng, o, d);
@@ -653,7 +667,7 @@ namespace ptb {
         if(k >= n) {
             return;
         }
-        Rng rng = engineFromState(states[k]);
+        ReferenceRng rng = engineFromState(states[k]);
         float sx;
         float sy;
         sampleAperture(camera, rng, sx, sy);
@@ -668,7 +682,7 @@ namespace ptb {
         if(blockIdx.x != 0U || threadIdx.x != 0U) {
             return;
         }
-        Rng rng = engineFromState(*state);
+        ReferenceRng rng = engineFromState(*state);
         uint32_t n = 0U;
         sampleLights(scene, mk3(px, py, pz), rng, [&](const LightSample &ls) {
             if(n < max_out) {
@@ -707,7 +721,7 @@ namespace ptb {
         if(k >= n) {
             return;
         }
-        Rng rng = engineFromState(states[k]);
+        ReferenceRng rng = engineFromState(states[k]);
         V3 pos;
         float density;
         bool cull;
@@ -738,7 +752,7 @@ namespace ptb {
             return;
         }
         const float *p = in + 9 * k;
-        Rng rng = engineFromState(states[k]);
+        ReferenceRng rng = engineFromState(states[k]);
         V3 o;
         V3 d;
         float factor;

@@ -281,7 +281,14 @@ namespace {
             PTB_CUDA(cudaMemcpyAsync(work_cursor, &started, sizeof(started), cudaMemcpyHostToDevice, ctx->stream));
             PTB_CUDA(cudaStreamSynchronize(ctx->stream)); // `started` lives on this stack frame
             LaunchTimer timer(ctx, 1);
-            generateKernel<<<(first_wave + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(pool, params, src, first_wave, queues[0], counters, kCountQueueA);
+            if(params.rng_xorshift != 0U) {
+                generateKernel<ReferenceRng><<<(first_wave + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(pool, params, src, first_wave, queues[0], counters,
+                                                                                                             kCountQueueA);
+            }
+            else {
+                generateKernel<CounterRng><<<(first_wave + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(pool, params, src, first_wave, queues[0], counters,
+                                                                                                           kCountQueueA);
+            }
         }
         PTB_CUDA(cudaGetLastError());
         if(stats != nullptr) {
@@ -309,7 +316,12 @@ namespace {
             }
             {
                 LaunchTimer timer(ctx, 1);
-                shadeKernel<<<flat_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, cur, shadow_queue);
+                if(params.rng_xorshift != 0U) {
+                    shadeKernel<ReferenceRng><<<flat_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, cur, shadow_queue);
+                }
+                else {
+                    shadeKernel<CounterRng><<<flat_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, cur, shadow_queue);
+                }
             }
             {
                 LaunchTimer timer(ctx, 0);
@@ -322,7 +334,14 @@ namespace {
             }
             {
                 LaunchTimer timer(ctx, 1);
-                accumulateKernel<<<flat_grid, kBlock, 0, ctx->stream>>>(pool, params, src, queues[cur], counters, cur, queues[nxt], nxt, samples, work_cursor);
+                if(params.rng_xorshift != 0U) {
+                    accumulateKernel<ReferenceRng><<<flat_grid, kBlock, 0, ctx->stream>>>(pool, params, src, queues[cur], counters, cur, queues[nxt], nxt,
+                                                                                        samples, work_cursor);
+                }
+                else {
+                    accumulateKernel<CounterRng><<<flat_grid, kBlock, 0, ctx->stream>>>(pool, params, src, queues[cur], counters, cur, queues[nxt], nxt, samples,
+                                                                                      work_cursor);
+                }
             }
             PTB_CUDA(cudaMemcpyAsync(ctx->host_counters, counters, kCounterSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
             PTB_CUDA(cudaStreamSynchronize(ctx->stream));

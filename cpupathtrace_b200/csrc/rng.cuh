@@ -29,22 +29,27 @@ namespace ptb {
         return z ^ (z >> 31);
     }
 
-    struct Rng {
+    // XORSHIFT = true: the reference engine (validation); false: the counter-based production generator.
+    // The kind is a compile-time property of the kernels so that neither pays for the other's arithmetic.
+    template<bool XORSHIFT>
+    struct RngT {
+        static constexpr bool kXorshift = XORSHIFT;
         uint64_t state;   // xorshift state, or the (pixel, sample) key in counter mode
         uint32_t counter; // counter mode: (bounce << 8) | draw-in-bounce
-        uint32_t xorshift;
 
         PTB_DEV uint32_t draw() {
-            if(xorshift != 0U) {
+            if constexpr(XORSHIFT) {
                 const uint64_t result = state * 0xD989BCACC137DCD5ULL;
                 state ^= state >> 11;
                 state ^= state << 31;
                 state ^= state >> 18;
                 return static_cast<uint32_t>(result >> 32);
             }
-            const uint64_t z = mix64(state + 0x9E3779B97F4A7C15ULL * (static_cast<uint64_t>(counter) + 1ULL));
-            counter++;
-            return static_cast<uint32_t>(z >> 32);
+            else {
+                const uint64_t z = mix64(state + 0x9E3779B97F4A7C15ULL * (static_cast<uint64_t>(counter) + 1ULL));
+                counter++;
+                return static_cast<uint32_t>(z >> 32);
+            }
         }
 
         // generate_canonical<float, 24>
@@ -58,8 +63,9 @@ namespace ptb {
             return canonical() * (b - a) + a;
         }
 
+        // uniform_real_distribution<float>(0, 1): u * (1 - 0) + 0 == u
         PTB_DEV float uniform01() {
-            return canonical() * 1.0F + 0.0F;
+            return canonical();
         }
 
         // bernoulli_distribution(p)
@@ -73,7 +79,17 @@ namespace ptb {
             }
             return u < p * 1.0;
         }
+
+        // counter mode: the draws of path vertex `bounce` start at counter bounce << 8
+        PTB_DEV void startBounce(int bounce) {
+            if constexpr(!XORSHIFT) {
+                counter = static_cast<uint32_t>(bounce) << 8;
+            }
+        }
     };
+
+    using ReferenceRng = RngT<true>;
+    using CounterRng = RngT<false>;
 
     PTB_DEV uint64_t xorshiftSeed(uint64_t seed) {
         return seed ^ (~seed << 32);

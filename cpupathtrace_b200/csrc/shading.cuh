@@ -25,7 +25,8 @@ namespace ptb {
 
     // ------------------------------------------------------------------------------------------------ camera
 
-    PTB_DEV void sampleAperture(const ptb_camera &c, Rng &rng, float &sx, float &sy) {
+    template<typename RNG>
+    PTB_DEV void sampleAperture(const ptb_camera &c, RNG &rng, float &sx, float &sy) {
         if(c.aperture_kind == PTB_APERTURE_CIRCULAR) {
             const float r = sqrtf(rng.uniform01());
             const float theta = kTwoPi * rng.uniform01();
@@ -54,7 +55,8 @@ namespace ptb {
         sy = y;
     }
 
-    PTB_DEV void shootRay(const ptb_camera &c, float x, float y, float pixel_width, float pixel_height, Rng &rng, V3 &ray_o, V3 &ray_d) {
+    template<typename RNG>
+    PTB_DEV void shootRay(const ptb_camera &c, float x, float y, float pixel_width, float pixel_height, RNG &rng, V3 &ray_o, V3 &ray_d) {
         const float offset_x = rng.uniform(-pixel_width / 2.0F, pixel_width / 2.0F);
         const float offset_y = rng.uniform(-pixel_height / 2.0F, pixel_height / 2.0F);
         const float sensor_x = x + offset_x;
@@ -158,7 +160,8 @@ namespace ptb {
 
     // Object::sampleSurface for a primitive given as its three un-differenced lanes
     // (triangle: a, b, c; sphere: origin / (radius, radius^2)): uniformly sampled point, density, cull flag.
-    PTB_DEV void samplePrimSurface(float4 e0, float4 e1, float4 e2, uint32_t flags, Rng &rng, V3 &surface_pos, float &surface_p, bool &surface_cull) {
+    template<typename RNG>
+    PTB_DEV void samplePrimSurface(float4 e0, float4 e1, float4 e2, uint32_t flags, RNG &rng, V3 &surface_pos, float &surface_p, bool &surface_cull) {
         if((flags & kKindMask) == PTB_PRIM_TRIANGLE) {
             const V3 a = mk3(e0.x, e0.y, e0.z);
             const V3 b = mk3(e1.x, e1.y, e1.z);
@@ -200,8 +203,8 @@ namespace ptb {
     // Scene::sampleLights.  `emit(LightSample)` is called once per produced sample, in the reference's order:
     // explicit lights first, then the emissive-object samples that survive the rejection tests.  All engine draws of
     // a rejected sample are consumed before the rejection (scene.cpp:239-277).
-    template<typename Emit>
-    PTB_DEV void sampleLights(const DeviceScene &s, V3 pos, Rng &rng, Emit emit) {
+    template<typename RNG, typename Emit>
+    PTB_DEV void sampleLights(const DeviceScene &s, V3 pos, RNG &rng, Emit emit) {
         for(uint32_t i = 0; i < s.n_lights; i++) {
             LightSample ls;
             const float4 p = __ldg(s.lights + 2 * i);
@@ -319,7 +322,8 @@ namespace ptb {
     }
 
     // BSDF::propagateRay: next ray, radiance factor, probability density
-    PTB_DEV void propagateRay(const Material &m, V3 ray_d, V3 pos, V3 normal, float epsilon, Rng &rng, V3 &out_o, V3 &out_d, float &factor, float &pd) {
+    template<typename RNG>
+    PTB_DEV void propagateRay(const Material &m, V3 ray_d, V3 pos, V3 normal, float epsilon, RNG &rng, V3 &out_o, V3 &out_d, float &factor, float &pd) {
         if(m.bsdf == PTB_BSDF_LAMBERT) {
             // importanceSampleCosine(dist(re), dist(re), 1.0F): g++ evaluates the second argument first, so the first
             // draw is r2 (the cos-theta variate) and the second is r1 (the azimuth)   [SURVEY.md App. B]
@@ -404,6 +408,7 @@ namespace ptb {
 
     // ------------------------------------------------------------------------------------------------ path vertex
 
+    template<typename RNG>
     struct PathRegs {
         V3 ray_o;
         V3 ray_d;
@@ -413,10 +418,11 @@ namespace ptb {
         double bounce_pd; // sample_bounce_pd
         float contribution_unweighted;
         int path_length;
-        Rng rng;
+        RNG rng;
     };
 
-    PTB_DEV void initPath(PathRegs &p) {
+    template<typename RNG>
+    PTB_DEV void initPath(PathRegs<RNG> &p) {
         p.throughput = V4{1.0F, 1.0F, 1.0F, 1.0F};
         p.radiance = V4{0.0F, 0.0F, 0.0F, 0.0F};
         p.divisor = 1.0;
@@ -437,8 +443,8 @@ namespace ptb {
     // samples whose BSDF returns pd 0 for synthetic rays (Glass, Mirror): the reference traces their shadow ray and
     // discards the result (worker.cpp:84-92), so they carry geometry but no contribution.
     // Returns true when the path continues with the new ray in p.
-    template<typename Shadow>
-    PTB_DEV bool shadeVertex(const DeviceScene &s, float epsilon, int max_depth, PathRegs &p, float t, uint32_t slot, Shadow shadow) {
+    template<typename RNG, typename Shadow>
+    PTB_DEV bool shadeVertex(const DeviceScene &s, float epsilon, int max_depth, PathRegs<RNG> &p, float t, uint32_t slot, Shadow shadow) {
         p.path_length++;
 
         const V3 pos = p.ray_o + p.ray_d * t;
@@ -446,14 +452,16 @@ namespace ptb {
         const V3 n = surfaceNormal(s, slot, pos, material_index);
         const Material m = loadMaterial(s, material_index);
 
-        p.radiance = p.radiance + (p.throughput * m.emission) / static_cast<float>(p.divisor * p.bounce_pd);
+        // a non-emissive surface adds exactly +0 to every channel (the divisor is finite and non-zero here), so the four
+        // IEEE divisions are skipped for it
+        if(m.emission.x != 0.0F || m.emission.y != 0.0F || m.emission.z != 0.0F) {
+            p.radiance = p.radiance + (p.throughput * m.emission) / static_cast<float>(p.divisor * p.bounce_pd);
+        }
 
         const float contribution = ((p.throughput.x + p.throughput.y) + p.throughput.z) / 3.0F;
         const float bounce_probability = p.path_length <= 4 ? 1.0F : 0.1F + 0.1F * stdmin(p.contribution_unweighted * contribution, 1.0F);
 
-        if(p.rng.xorshift == 0U) {
-            p.rng.counter = static_cast<uint32_t>(p.path_length) << 8;
-        }
+        p.rng.startBounce(p.path_length);
         const bool do_bounce = p.rng.uniform01() < bounce_probability;
 
         sampleLights(s, pos, p.rng, [&](const LightSample &ls) {
