@@ -308,6 +308,12 @@ def run_b200_arm(args):
     cstats = capi.RenderStats()
     co = opts(count_spp, capi.PTB_FLAG_DEVICE_IO | capi.PTB_FLAG_COUNT_VISITS, 99)
     capi.check(lib.ptb_render(handle, C.byref(camera), C.byref(co), 0, 0, args.width, args.height, C.c_void_p(image.data_ptr()), C.byref(cstats)))
+    count_detail = {
+        "closest_inner_per_ray": (cstats.inner_visits - cstats.shadow_inner_visits) / max(cstats.closest_rays, 1),
+        "closest_leaf_per_ray": (cstats.leaf_visits - cstats.shadow_leaf_visits) / max(cstats.closest_rays, 1),
+        "shadow_inner_per_ray": cstats.shadow_inner_visits / max(cstats.shadow_rays, 1),
+        "shadow_leaf_per_ray": cstats.shadow_leaf_visits / max(cstats.shadow_rays, 1),
+    }
     count_rays = sum_over_ranks(float(cstats.closest_rays + cstats.shadow_rays))
     inner_per_ray = sum_over_ranks(float(cstats.inner_visits)) / max(count_rays, 1.0)
     leaf_per_ray = sum_over_ranks(float(cstats.leaf_visits)) / max(count_rays, 1.0)
@@ -323,7 +329,8 @@ def run_b200_arm(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     step_ms, wall_ms = [], []
-    totals = {"samples": 0, "closest": 0, "shadow": 0, "skipped": 0, "vertices": 0, "launches": 0, "trace_ms": 0.0, "shade_ms": 0.0, "iterations": 0}
+    totals = {"samples": 0, "closest": 0, "shadow": 0, "skipped": 0, "vertices": 0, "launches": 0, "trace_ms": 0.0, "shade_ms": 0.0, "iterations": 0,
+              "shadow_ms": 0.0}
     for i in range(args.steps):
         flush.zero_()
         barrier()
@@ -342,6 +349,7 @@ def run_b200_arm(args):
         totals["launches"] += stats.kernel_launches + (1 if dist is not None else 0)
         totals["trace_ms"] += stats.device_ms_trace
         totals["shade_ms"] += stats.device_ms_shade
+        totals["shadow_ms"] += stats.device_ms_trace_shadow
         totals["iterations"] += stats.bounce_iterations
     clocks = sampler.stop()
 
@@ -428,7 +436,10 @@ def run_b200_arm(args):
                      "peak_source": f"{peak_source} HBM copy bandwidth", "kernel": "traceClosestKernel + traceShadowKernel",
                      "bytes_per_ray": bytes_per_ray, "inner_fetches_per_ray": inner_per_ray, "leaf_fetches_per_ray": leaf_per_ray,
                      "trace_ms_per_step": totals["trace_ms"] / args.steps, "shade_ms_per_step": totals["shade_ms"] / args.steps,
-                     "trace_share_of_step": totals["trace_ms"] / max(sum(step_ms), 1e-9), "mrays_per_s_trace_only": rank_rays / max(trace_s, 1e-12) / 1e6},
+                     "trace_share_of_step": totals["trace_ms"] / max(sum(step_ms), 1e-9), "mrays_per_s_trace_only": rank_rays / max(trace_s, 1e-12) / 1e6,
+                     "shadow_trace_ms_per_step": totals["shadow_ms"] / args.steps,
+                     "closest_mrays_per_s": totals["closest"] / max(totals["trace_ms"] - totals["shadow_ms"], 1e-9) / 1e3,
+                     "shadow_mrays_per_s": totals["shadow"] / max(totals["shadow_ms"], 1e-9) / 1e3, **count_detail},
         "cpu_baseline": cpu_baseline,
         "scene": {"prims": int(info.n_prims), "inner_nodes": int(info.n_inner_nodes), "bvh_depth": int(info.bvh_depth),
                   "device_mb": info.device_bytes / 2**20, "build_s": info.build_seconds, "scene_ctor_s": t_build},

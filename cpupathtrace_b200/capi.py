@@ -108,6 +108,9 @@ class RenderStats(C.Structure):
         ("device_ms_total", C.c_double),
         ("device_ms_trace", C.c_double),
         ("device_ms_shade", C.c_double),
+        ("device_ms_trace_shadow", C.c_double),
+        ("shadow_inner_visits", C.c_uint64),
+        ("shadow_leaf_visits", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -46,6 +46,13 @@ namespace ptb {
     // Builds the reference topology over `prims` and flattens it.  `threads` <= 0 picks hardware concurrency.
     FlatBvh buildReferenceBvh(const ptb_prim *prims, uint64_t n_prims, int threads);
 
+    // A second hierarchy over the same primitives for ANY-HIT (shadow) queries only.  Whether a segment is occluded
+    // does not depend on the order in which primitives are tested, so this tree is free to be a better one than the
+    // reference's median split: binned surface-area heuristic (16 bins per axis, all three axes), one primitive per
+    // leaf, same 64-byte record.  Leaf references are ~slot with slot = position of the primitive in the REFERENCE
+    // tree's leaf order (`prim_to_slot`), so both trees share one geometry array.  `slot_to_prim` of the result is unused.
+    FlatBvh buildOcclusionBvh(const ptb_prim *prims, uint64_t n_prims, const uint32_t *prim_to_slot, int threads);
+
 }
 
 #endif

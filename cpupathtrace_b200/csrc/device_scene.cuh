@@ -3,6 +3,7 @@
 // HBM layout (every array 16-byte aligned, read with 128-bit loads through the read-only path):
 //
 //   nodes  : 4 x float4 per inner record (64 B), DFS preorder              <- AABB tree (scene/bounding_box.h:22-68)
+//   occ_nodes: same record format, a second (SAH) hierarchy over the same primitives used by any-hit queries only
 //   geom   : 4 x float4 per leaf slot  (64 B, last lane padding), leaf order <- Triangle / Sphere geometry (scene/object.h)
 //              triangle: (a, flags) (b - a, 0) (c - a, 0) (pad)  flags = kind | cull << 2
 //              sphere  : (origin, flags) (radius, radius^2, 0, 0) (0) (pad)
@@ -30,6 +31,7 @@ namespace ptb {
 
     struct DeviceScene {
         const float4 *nodes;
+        const float4 *occ_nodes; // occlusion hierarchy for any-hit queries (same record format, shares `geom`); may be null
         const float4 *geom;
         const float4 *shade;
         const float4 *mats;
@@ -42,6 +44,7 @@ namespace ptb {
         uint32_t n_emissive;
         uint32_t object_sample_count;
         int32_t root_ref;
+        int32_t occ_root_ref;
         float root_lo[3];
         float root_hi[3];
     };

@@ -201,6 +201,16 @@ namespace ptb {
 
     // ------------------------------------------------------------------------------------------------ trace
 
+    // Any-hit queries walk the occlusion hierarchy when the scene has one (visibility is order-independent).
+    PTB_DEV DeviceScene occlusionView(const DeviceScene &scene) {
+        DeviceScene view = scene;
+        if(scene.occ_nodes != nullptr) {
+            view.nodes = scene.occ_nodes;
+            view.root_ref = scene.occ_root_ref;
+        }
+        return view;
+    }
+
     // Persistent warps over the device-side queue; scheduling by warp votes, see warpTrace in traverse.cuh.
     template<bool COUNT>
     __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) traceClosestKernel(DeviceScene scene, VoteParams vote, PathPool pool, const uint32_t *__restrict__ queue,
@@ -233,7 +243,7 @@ namespace ptb {
         };
         if(any_hit != 0U) {
             warpTrace<true, COUNT>(
-              scene, vote, &counters[kCountFetchShadow], count, fetch,
+              occlusionView(scene), vote, &counters[kCountFetchShadow], count, fetch,
               [&](uint32_t k, const Hit &h) { pool.shadow_c[shadow_queue[k]].w = h.slot < 0 ? 1.0F : 0.0F; }, visits);
         }
         else {
@@ -604,7 +614,7 @@ namespace ptb {
     __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) occludedKernel(DeviceScene scene, VoteParams vote, const float *__restrict__ rays, uint32_t n, uint8_t *__restrict__ out,
                                                              uint32_t *__restrict__ cursor, VisitCounters *visits) {
         warpTrace<true, COUNT>(
-          scene, vote, cursor, n,
+          occlusionView(scene), vote, cursor, n,
           [&](uint32_t k, V3 &o, V3 &d, float &limit) {
               const float *p = rays + 7 * static_cast<size_t>(k);
               o = mk3(p[0], p[1], p[2]);

@@ -106,7 +106,7 @@ struct ptb_context {
     Buffer io_d;
     uint32_t *host_counters = nullptr; // pinned
 
-    // profiling events: [pair][0 = start, 1 = stop], class 0 = trace, 1 = everything else
+    // profiling events: [pair][0 = start, 1 = stop], class 0 = closest-hit trace, 2 = shadow trace, 1 = everything else
     cudaEvent_t events[kEventPairs][2];
     int event_class[kEventPairs];
     int events_used = 0;
@@ -119,6 +119,7 @@ struct ptb_scene {
     ptb_context *ctx = nullptr;
     ptb::DeviceScene dev{};
     Buffer nodes;
+    Buffer occ_nodes;
     Buffer geom;
     Buffer shade;
     Buffer mats;
@@ -168,6 +169,10 @@ namespace {
             if(cudaEventElapsedTime(&ms, ctx->events[i][0], ctx->events[i][1]) == cudaSuccess && stats != nullptr) {
                 if(ctx->event_class[i] == 0) {
                     stats->device_ms_trace += ms;
+                }
+                else if(ctx->event_class[i] == 2) {
+                    stats->device_ms_trace += ms;
+                    stats->device_ms_trace_shadow += ms;
                 }
                 else {
                     stats->device_ms_shade += ms;
@@ -240,7 +245,7 @@ namespace {
         if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK) {
             return status;
         }
-        if((status = ctx->visits.reserve(sizeof(VisitCounters))) != PTB_OK) {
+        if((status = ctx->visits.reserve(2 * sizeof(VisitCounters))) != PTB_OK) {
             return status;
         }
         if((status = ctx->work_cursor.reserve(sizeof(unsigned long long))) != PTB_OK) {
@@ -324,12 +329,12 @@ namespace {
                 }
             }
             {
-                LaunchTimer timer(ctx, 0);
+                LaunchTimer timer(ctx, 2);
                 if(count_visits) {
-                    traceShadowKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, shadow_queue, counters, params.any_hit_shadows, visits);
+                    traceShadowKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, shadow_queue, counters, params.any_hit_shadows, visits + 1);
                 }
                 else {
-                    traceShadowKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, shadow_queue, counters, params.any_hit_shadows, visits);
+                    traceShadowKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, shadow_queue, counters, params.any_hit_shadows, visits + 1);
                 }
             }
             {
@@ -393,10 +398,12 @@ namespace {
             return PTB_OK;
         }
         if(count_visits) {
-            VisitCounters v{};
-            PTB_CUDA(cudaMemcpy(&v, ctx->visits.ptr, sizeof(v), cudaMemcpyDeviceToHost));
-            stats->inner_visits = v.inner;
-            stats->leaf_visits = v.leaf;
+            VisitCounters v[2] = {};
+            PTB_CUDA(cudaMemcpy(v, ctx->visits.ptr, sizeof(v), cudaMemcpyDeviceToHost));
+            stats->inner_visits = v[0].inner + v[1].inner;
+            stats->leaf_visits = v[0].leaf + v[1].leaf;
+            stats->shadow_inner_visits = v[1].inner;
+            stats->shadow_leaf_visits = v[1].leaf;
         }
         return PTB_OK;
     }
@@ -636,6 +643,18 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
         emis[3 * i + 1] = e1;
         emis[3 * i + 2] = e2;
     }
+    // occlusion hierarchy for any-hit (shadow) queries: SAH over the same primitives, leaf refs in reference slots
+    FlatBvh occlusion;
+    if(n > 1 && envLong("PTB_OCCLUSION_BVH", 1) != 0) {
+        std::vector<uint32_t> prim_to_slot(n);
+        for(uint64_t slot = 0; slot < n; slot++) {
+            prim_to_slot[bvh.slot_to_prim[slot]] = static_cast<uint32_t>(slot);
+        }
+        occlusion = buildOcclusionBvh(desc->prims, n, prim_to_slot.data(), threads);
+        if(occlusion.depth > static_cast<uint32_t>(kStackCapacity)) {
+            occlusion = FlatBvh{}; // pathological input: keep using the reference tree
+        }
+    }
     const double t1 = nowSeconds();
 
     auto *scene = new(std::nothrow) ptb_scene();
@@ -655,6 +674,9 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
         return PTB_OK;
     };
     status = upload(scene->nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(NodeRecord));
+    if(status == PTB_OK && !occlusion.nodes.empty()) {
+        status = upload(scene->occ_nodes, occlusion.nodes.data(), occlusion.nodes.size() * sizeof(NodeRecord));
+    }
     status = status != PTB_OK ? status : upload(scene->geom, geom.data(), geom.size() * sizeof(float4));
     status = status != PTB_OK ? status : upload(scene->shade, shade.data(), shade.size() * sizeof(float4));
     status = status != PTB_OK ? status : upload(scene->mats, mats.data(), mats.size() * sizeof(float4));
@@ -670,6 +692,8 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
 
     DeviceScene &d = scene->dev;
     d.nodes = scene->nodes.as<float4>();
+    d.occ_nodes = occlusion.nodes.empty() ? nullptr : scene->occ_nodes.as<float4>();
+    d.occ_root_ref = occlusion.root_ref;
     d.geom = scene->geom.as<float4>();
     d.shade = scene->shade.as<float4>();
     d.mats = scene->mats.as<float4>();
@@ -696,7 +720,7 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
     info.n_emissive = d.n_emissive;
     info.object_sample_count = d.object_sample_count;
     info.n_lights = desc->n_lights;
-    info.device_bytes = scene->nodes.bytes + scene->geom.bytes + scene->shade.bytes + scene->mats.bytes + scene->lights.bytes + scene->emis.bytes +
+    info.device_bytes = scene->nodes.bytes + scene->occ_nodes.bytes + scene->geom.bytes + scene->shade.bytes + scene->mats.bytes + scene->lights.bytes + scene->emis.bytes +
                         scene->cdf.bytes + scene->slot_to_prim.bytes;
     info.build_seconds = t1 - t0;
     info.upload_seconds = t2 - t1;
@@ -717,7 +741,7 @@ int ptb_scene_destroy(ptb_scene *scene) {
         cudaSetDevice(scene->ctx->device);
         cudaStreamSynchronize(scene->ctx->stream);
     }
-    for(Buffer *b : {&scene->nodes, &scene->geom, &scene->shade, &scene->mats, &scene->lights, &scene->emis, &scene->cdf, &scene->slot_to_prim}) {
+    for(Buffer *b : {&scene->nodes, &scene->occ_nodes, &scene->geom, &scene->shade, &scene->mats, &scene->lights, &scene->emis, &scene->cdf, &scene->slot_to_prim}) {
         b->release();
     }
     delete scene;
@@ -762,11 +786,11 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
         d_t = ctx->io_b.as<float>();
         d_prim = ctx->io_c.as<int32_t>();
     }
-    if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK || (status = ctx->visits.reserve(sizeof(VisitCounters))) != PTB_OK) {
+    if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK || (status = ctx->visits.reserve(2 * sizeof(VisitCounters))) != PTB_OK) {
         return status;
     }
     PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
-    PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, sizeof(VisitCounters), ctx->stream));
+    PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, 2 * sizeof(VisitCounters), ctx->stream));
 
     constexpr uint64_t kChunk = 1ULL << 30;
     for(uint64_t first = 0; first < n_rays; first += kChunk) {
@@ -824,25 +848,25 @@ int ptb_occluded(ptb_scene *scene, const float *rays, uint64_t n_rays, uint8_t *
         d_rays = ctx->io_a.as<float>();
         d_out = ctx->io_b.as<uint8_t>();
     }
-    if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK || (status = ctx->visits.reserve(sizeof(VisitCounters))) != PTB_OK) {
+    if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK || (status = ctx->visits.reserve(2 * sizeof(VisitCounters))) != PTB_OK) {
         return status;
     }
     PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
-    PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, sizeof(VisitCounters), ctx->stream));
+    PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, 2 * sizeof(VisitCounters), ctx->stream));
 
     constexpr uint64_t kChunk = 1ULL << 30;
     for(uint64_t first = 0; first < n_rays; first += kChunk) {
         const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(kChunk, n_rays - first));
         const int grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 16))));
         PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(uint32_t), ctx->stream));
-        LaunchTimer timer(ctx, 0);
+        LaunchTimer timer(ctx, 2);
         if(count_visits) {
             occludedKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
-                                                                    ctx->visits.as<VisitCounters>());
+                                                                    ctx->visits.as<VisitCounters>() + 1);
         }
         else {
             occludedKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
-                                                                     ctx->visits.as<VisitCounters>());
+                                                                     ctx->visits.as<VisitCounters>() + 1);
         }
     }
     PTB_CUDA(cudaGetLastError());
@@ -901,7 +925,7 @@ int ptb_render_samples(ptb_scene *scene, const ptb_camera *camera, const ptb_ren
         d_out = ctx->io_c.as<float4>();
     }
     PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
-    PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, sizeof(VisitCounters), ctx->stream));
+    PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, 2 * sizeof(VisitCounters), ctx->stream));
 
     const RenderParams params = makeParams(*camera, *opts);
     if(n > 0xFFFFFFFFULL) {
@@ -988,10 +1012,10 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
 
     const uint64_t pool_limit = static_cast<uint64_t>(envLong("PTB_POOL_PATHS", 1L << 22));
     const RenderParams params = makeParams(*camera, *opts);
-    if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK || (status = ctx->visits.reserve(sizeof(VisitCounters))) != PTB_OK) {
+    if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK || (status = ctx->visits.reserve(2 * sizeof(VisitCounters))) != PTB_OK) {
         return status;
     }
-    PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, sizeof(VisitCounters), ctx->stream));
+    PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, 2 * sizeof(VisitCounters), ctx->stream));
     PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
 
     std::vector<uint32_t> pixel_list;

@@ -381,6 +381,8 @@ namespace ptb {
                     if(visit_left && visit_right) {
                         // nearer child first, the right one on ties (scene.cpp:122-123); the other is deferred
                         const bool left_first = lt < rt;
+                        // (an L2 prefetch of the deferred sibling was measured and rejected: -9 % on the bench scene, -10 % on
+                        // the 16 Mi-triangle soup)
                         stack[sp] = make_uint2(static_cast<uint32_t>(left_first ? right : left), __float_as_uint(left_first ? rt : lt));
                         sp++;
                         node = left_first ? left : right;

@@ -193,6 +193,9 @@ typedef struct ptb_render_stats {
     double device_ms_total;  /* CUDA-event time of the whole call on the context's stream */
     double device_ms_trace;  /* closest + shadow traversal kernels                         */
     double device_ms_shade;  /* generate + shade + accumulate + resolve                    */
+    double device_ms_trace_shadow;  /* the shadow-ray share of device_ms_trace            */
+    uint64_t shadow_inner_visits;   /* the shadow-ray share of inner_visits               */
+    uint64_t shadow_leaf_visits;    /* the shadow-ray share of leaf_visits                */
 } ptb_render_stats;
 
 /* ------------------------------------------------------------------------------------------------ entry points */
