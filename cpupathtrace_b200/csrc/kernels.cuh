@@ -25,6 +25,9 @@
 namespace ptb {
 
     constexpr int kBlock = 128;
+#ifndef PTB_SHADE_MIN_BLOCKS
+#define PTB_SHADE_MIN_BLOCKS 6 // 80 registers: +4 % shade throughput over the unconstrained 93 (8 CTAs / 64 registers spill and gain nothing)
+#endif
 #ifndef PTB_TRACE_MIN_BLOCKS
 #define PTB_TRACE_MIN_BLOCKS 12 // resident 128-thread CTAs per SM the trace kernels are compiled for (register cap 65536 / (12 * 128) = 42)
 #endif
@@ -262,7 +265,7 @@ namespace ptb {
     // ------------------------------------------------------------------------------------------------ shade
 
     template<typename RNG>
-    __global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene scene, PathPool pool, RenderParams params, const uint32_t *__restrict__ queue,
+    __global__ void __launch_bounds__(kBlock, PTB_SHADE_MIN_BLOCKS) shadeKernel(DeviceScene scene, PathPool pool, RenderParams params, const uint32_t *__restrict__ queue,
                                                           uint32_t *__restrict__ counters, int queue_slot, uint32_t *__restrict__ shadow_queue) {
         const uint32_t count = counters[queue_slot];
         const uint32_t stride = gridDim.x * blockDim.x;
