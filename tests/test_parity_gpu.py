@@ -214,3 +214,59 @@ def test_image_statistics_match_reference(ref, b200):
     assert ours <= 1.35 * noise + 1e-4
     med = [np.median(x[..., :3]) for x in (a, b, g)]
     assert abs(med[2] - med[0]) <= 3 * abs(med[1] - med[0]) + 0.01
+
+
+def test_axis_aligned_and_boundary_rays(ref, b200):
+    """Edge cases of the slab test and of Moeller-Trumbore: directions with exact zero components (the 1/d -> FLT_MAX
+    path, bounding_box.cpp:43-45), origins exactly on box planes and on triangle planes, rays along shared edges and
+    through vertices, rays starting inside spheres (near root only, object.cpp:77-83), back-face-culled hits."""
+    spec = scenes.mixed_materials(seed=5, n_tris=180)
+    builder = spec.replay(ref)
+    tris = builder.get_triangles()
+    builder.close()
+    tris = tris[~np.isnan(tris).any(axis=1)]
+    rng = np.random.Generator(np.random.PCG64(9))
+    rays = []
+    axes = np.eye(3, dtype=np.float32)
+    for _ in range(6000):
+        o = rng.uniform(-2.2, 2.2, 3).astype(np.float32)
+        d = axes[rng.integers(0, 3)] * np.float32(rng.choice([-1.0, 1.0]))
+        rays.append(np.concatenate([o, d]))
+    for _ in range(6000):  # two zero components replaced by one: directions inside a coordinate plane
+        o = rng.uniform(-2.0, 2.0, 3).astype(np.float32)
+        d = rng.normal(size=3).astype(np.float32)
+        d[rng.integers(0, 3)] = 0.0
+        d = d * (np.float32(1.0) / np.sqrt(np.float32((d * d).sum())))
+        rays.append(np.concatenate([o, d]))
+    for t in tris[rng.permutation(len(tris))[:3000]]:  # origins on a vertex / edge midpoint / centroid, towards another
+        a, b, c = t[0:3], t[3:6], t[6:9]
+        start = [a, 0.5 * (a + b), (a + b + c) / 3][rng.integers(0, 3)].astype(np.float32)
+        other = tris[rng.integers(0, len(tris))]
+        target = [other[0:3], 0.5 * (other[3:6] + other[6:9])][rng.integers(0, 2)].astype(np.float32)
+        d = target - start
+        n2 = np.float32((d * d).sum())
+        if n2 > 0:
+            rays.append(np.concatenate([start, d * (np.float32(1.0) / np.sqrt(n2))]))
+    for _ in range(3000):  # on the walls of the enclosing box (x, y or z = +-2 exactly)
+        o = rng.uniform(-2.0, 2.0, 3).astype(np.float32)
+        o[rng.integers(0, 3)] = np.float32(rng.choice([-2.0, 2.0]))
+        d = rng.normal(size=3).astype(np.float32)
+        d = d * (np.float32(1.0) / np.sqrt(np.float32((d * d).sum())))
+        rays.append(np.concatenate([o, d]))
+    for _ in range(3000):  # inside the spheres
+        centre, radius = [((-1.2, -1.2, 0.8), 0.35), ((0.9, -1.3, 0.2), 0.6), ((-0.2, 0.4, 0.9), 0.45)][rng.integers(0, 3)]
+        o = (np.array(centre) + rng.uniform(-0.5, 0.5, 3) * radius).astype(np.float32)
+        d = rng.normal(size=3).astype(np.float32)
+        d = d * (np.float32(1.0) / np.sqrt(np.float32((d * d).sum())))
+        rays.append(np.concatenate([o, d]))
+    rays = np.array(rays, np.float32)
+    sr, sg = _pair(spec, ref, b200)
+    _compare_hits(sr, sg, rays)
+
+
+def test_large_sample_batch_is_bit_exact(ref, b200):
+    """250 k samples on the demo scene (more than the wavefront's refill granularity, fewer than one pool)."""
+    cam = scenes.demo_camera(None, 160, 90)
+    bad, exact, want, got = _sample_parity(ref, b200, scenes.cornell_demo(("obj", scenes.standin_obj(90, 60))), cam, 160, 90, 250000, seed=77)
+    print(f"250k: diverged {bad:.6f}, bit-exact {exact:.6f}")
+    assert bad == 0.0 and exact == 1.0
