@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -84,6 +85,7 @@ namespace {
 }
 
 struct ptb_context {
+    std::mutex mutex; // entry points serialise on their context: its workspace and stream are shared state
     int device = 0;
     int sm_count = 0;
     ptb::VoteParams vote{12, 6};
@@ -273,6 +275,7 @@ namespace {
     int runBounces(ptb_scene *scene, const PathPool &pool, const RenderParams &params, const PathSource &src, float4 *samples, bool count_visits,
                    ptb_render_stats *stats) {
         ptb_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mutex);
         uint32_t *counters = ctx->counters.as<uint32_t>();
         uint32_t *queues[2] = {ctx->queue_a.as<uint32_t>(), ctx->queue_b.as<uint32_t>()};
         uint32_t *shadow_queue = ctx->shadow_queue.as<uint32_t>();
@@ -552,6 +555,7 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
             return fail(PTB_ERR_UNSUPPORTED, "ptb_scene_create: unknown BSDF kind");
         }
     }
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = useDevice(ctx);
     if(status != PTB_OK) {
         return status;
@@ -763,6 +767,7 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
         return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_intersect: null argument");
     }
     ptb_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = beginCall(ctx, stats);
     if(status != PTB_OK) {
         return status;
@@ -828,6 +833,7 @@ int ptb_occluded(ptb_scene *scene, const float *rays, uint64_t n_rays, uint8_t *
         return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_occluded: null argument");
     }
     ptb_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = beginCall(ctx, stats);
     if(status != PTB_OK) {
         return status;
@@ -895,6 +901,7 @@ int ptb_render_samples(ptb_scene *scene, const ptb_camera *camera, const ptb_ren
         return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render_samples: empty image");
     }
     ptb_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = beginCall(ctx, stats);
     if(status != PTB_OK) {
         return status;
@@ -961,6 +968,7 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
         return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render: empty image");
     }
     ptb_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = beginCall(ctx, stats);
     if(status != PTB_OK) {
         return status;
@@ -1096,6 +1104,7 @@ int ptb_camera_shoot(ptb_context *ctx, const ptb_camera *camera, uint64_t n, con
     if(ctx == nullptr || camera == nullptr || (n > 0 && (xy == nullptr || engine_states == nullptr || rays_out == nullptr))) {
         return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_camera_shoot: null argument");
     }
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = useDevice(ctx);
     if(status != PTB_OK || n == 0) {
         return status;
@@ -1122,6 +1131,7 @@ int ptb_aperture_sample(ptb_context *ctx, uint32_t aperture_kind, float hexagon_
     if(aperture_kind != PTB_APERTURE_CIRCULAR && aperture_kind != PTB_APERTURE_HEXAGONAL) {
         return fail(PTB_ERR_UNSUPPORTED, "ptb_aperture_sample: unknown aperture kind");
     }
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = useDevice(ctx);
     if(status != PTB_OK || n == 0) {
         return status;
@@ -1146,6 +1156,7 @@ int ptb_sample_lights(ptb_scene *scene, const float pos[3], uint64_t *engine_sta
         return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_sample_lights: null argument");
     }
     ptb_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = useDevice(ctx);
     if(status != PTB_OK) {
         return status;
@@ -1175,6 +1186,7 @@ int ptb_aabb_intersect(ptb_context *ctx, const float low[3], const float high[3]
     if(ctx == nullptr || low == nullptr || high == nullptr || (n_rays > 0 && (rays == nullptr || t_out == nullptr))) {
         return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_aabb_intersect: null argument");
     }
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = useDevice(ctx);
     if(status != PTB_OK || n_rays == 0) {
         return status;
@@ -1198,6 +1210,7 @@ int ptb_prim_intersect(ptb_context *ctx, const ptb_prim *prim, uint64_t n_rays, 
     if(prim->kind > PTB_PRIM_NULL) {
         return fail(PTB_ERR_UNSUPPORTED, "ptb_prim_intersect: unknown primitive kind");
     }
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = useDevice(ctx);
     if(status != PTB_OK || n_rays == 0) {
         return status;
@@ -1283,6 +1296,7 @@ int ptb_prim_normal(ptb_context *ctx, const ptb_prim *prim, uint64_t n, const fl
     if(prim->kind > PTB_PRIM_NULL) {
         return fail(PTB_ERR_UNSUPPORTED, "ptb_prim_normal: unknown primitive kind");
     }
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = useDevice(ctx);
     if(status != PTB_OK || n == 0) {
         return status;
@@ -1314,6 +1328,7 @@ int ptb_prim_sample(ptb_context *ctx, const ptb_prim *prim, uint64_t n, uint64_t
     if(prim->kind > PTB_PRIM_NULL) {
         return fail(PTB_ERR_UNSUPPORTED, "ptb_prim_sample: unknown primitive kind");
     }
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = useDevice(ctx);
     if(status != PTB_OK || n == 0) {
         return status;
@@ -1339,6 +1354,7 @@ int ptb_bsdf_propagate(ptb_context *ctx, const ptb_material *material, float eps
     if(material->bsdf > PTB_BSDF_MIRROR) {
         return fail(PTB_ERR_UNSUPPORTED, "ptb_bsdf_propagate: unknown BSDF kind");
     }
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = useDevice(ctx);
     if(status != PTB_OK || n == 0) {
         return status;
@@ -1365,6 +1381,7 @@ int ptb_bsdf_spectrum(ptb_context *ctx, const ptb_material *material, uint32_t s
     if(material->bsdf > PTB_BSDF_MIRROR) {
         return fail(PTB_ERR_UNSUPPORTED, "ptb_bsdf_spectrum: unknown BSDF kind");
     }
+    std::lock_guard<std::mutex> lock(ctx->mutex);
     int status = useDevice(ctx);
     if(status != PTB_OK || n == 0) {
         return status;

@@ -117,122 +117,14 @@ namespace ptb {
         int32_t slot; // -1: none
     };
 
-    // ANY_HIT = false: closest hit, limit ignored.
-    // ANY_HIT = true : returns at the first primitive with 0 <= t < limit (slot = that primitive, t = its distance).
-    template<bool ANY_HIT, bool COUNT>
-    PTB_DEV Hit traverse(const DeviceScene &s, const RayInv &r, float limit, VisitCounters *counters) {
-        Hit hit;
-        hit.t = -1.0F;
-        hit.slot = -1;
-        if(s.n_prims == 0U) {
-            return hit;
-        }
-
-        // Scene::getIntersection tests the root box first and passes its (negative) result through on a miss
-        const float root_t = slab(r, s.root_lo[0], s.root_lo[1], s.root_lo[2], s.root_hi[0], s.root_hi[1], s.root_hi[2]);
-        if(!(root_t >= 0.0F)) {
-            hit.t = root_t;
-            return hit;
-        }
-
-        float best_t = ANY_HIT ? limit : kFloatMax;
-        int32_t stack_node[kStackCapacity];
-        float stack_t[kStackCapacity];
-        int sp = 0;
-        int32_t node = s.root_ref;
-        unsigned long long n_inner = 0;
-        unsigned long long n_leaf = 0;
-
-        for(;;) {
-            while(node >= 0) {
-                const float4 *rec = s.nodes + 4 * static_cast<size_t>(node);
-                float4 n0;
-                float4 n1;
-                float4 n2;
-                float4 n3;
-                ld256(rec, n0, n1);
-                ld256(rec + 2, n2, n3);
-                if(COUNT) {
-                    n_inner++;
-                }
-                const float lt = slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-                const float rt = slab(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
-                const int32_t left = __float_as_int(n3.x);
-                const int32_t right = __float_as_int(n3.y);
-                const bool left_first = lt < rt;
-                const float ct = left_first ? lt : rt;
-                const float ft = left_first ? rt : lt;
-                const int32_t cnode = left_first ? left : right;
-                const int32_t fnode = left_first ? right : left;
-                const bool vc = ct >= 0.0F && ct < best_t;
-                const bool vf = ft >= 0.0F && ft < best_t;
-                if(vc) {
-                    if(vf) {
-                        stack_node[sp] = fnode;
-                        stack_t[sp] = ft;
-                        sp++;
-                    }
-                    node = cnode;
-                }
-                else if(vf) {
-                    node = fnode;
-                }
-                else {
-                    node = INT32_MIN; // nothing to enter: pop
-                    break;
-                }
-            }
-
-            if(node != INT32_MIN) {
-                const uint32_t slot = static_cast<uint32_t>(~node);
-                if(COUNT) {
-                    n_leaf++;
-                }
-                const float t = hitSlot(s, r, slot);
-                if(ANY_HIT) {
-                    if(t >= 0.0F && t < limit) {
-                        hit.t = t;
-                        hit.slot = static_cast<int32_t>(slot);
-                        break;
-                    }
-                }
-                else {
-                    if(t >= 0.0F && (hit.slot < 0 || t <= best_t)) {
-                        best_t = t;
-                        hit.t = t;
-                        hit.slot = static_cast<int32_t>(slot);
-                    }
-                }
-            }
-
-            // pop the next deferred far child that still beats the best distance
-            bool found = false;
-            while(sp > 0) {
-                sp--;
-                if(stack_t[sp] < best_t) {
-                    node = stack_node[sp];
-                    found = true;
-                    break;
-                }
-            }
-            if(!found) {
-                break;
-            }
-        }
-
-        if(COUNT && counters != nullptr) {
-            atomicAdd(&counters->inner, n_inner);
-            atomicAdd(&counters->leaf, n_leaf);
-        }
-        return hit;
-    }
-
-
     // ------------------------------------------------------------------------------------------------ warp scheduling
     //
-    // Persistent-warp traversal with warp-level votes.  The per-ray algorithm is exactly traverse<> above (same node
-    // order, same pruning, same tie rules: each lane runs its own ray's sequence of steps unchanged); what changes
-    // is WHEN a lane takes its next step, so that the 32 lanes of a warp execute the same kind of step together:
+    // Persistent-warp traversal with warp-level votes.  Every lane runs the per-ray algorithm described at the top of
+    // this file on its own ray (same node order, same pruning, same tie rules); what the votes decide is WHEN a lane
+    // takes its next step, so that the 32 lanes of a warp execute the same kind of step together:
+    //
+    //   ANY_HIT = false: closest hit, `limit` ignored.
+    //   ANY_HIT = true : the ray is finished at the first primitive with 0 <= t < limit.
     //
     //   * a lane that has finished its ray does not wait for the slowest ray of a 32-ray batch: finished lanes are
     //     refilled from the device-side queue cursor as soon as kRefillVote of them are idle (one atomic per refill,
