@@ -274,8 +274,7 @@ namespace {
     // the call has been retired into `samples` (retired slots are refilled by the accumulate kernel).
     int runBounces(ptb_scene *scene, const PathPool &pool, const RenderParams &params, const PathSource &src, float4 *samples, bool count_visits,
                    ptb_render_stats *stats) {
-        ptb_context *ctx = scene->ctx;
-    std::lock_guard<std::mutex> lock(ctx->mutex);
+        ptb_context *ctx = scene->ctx; // the calling entry point holds ctx->mutex
         uint32_t *counters = ctx->counters.as<uint32_t>();
         uint32_t *queues[2] = {ctx->queue_a.as<uint32_t>(), ctx->queue_b.as<uint32_t>()};
         uint32_t *shadow_queue = ctx->shadow_queue.as<uint32_t>();
