@@ -143,6 +143,7 @@ PROTOTYPES = {
     "ptb_prim_sample": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "ptb_bsdf_propagate": (C.c_int, [_P, _P, C.c_float, C.c_uint64, _P, _P, _P]),
     "ptb_bsdf_spectrum": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, _P, _P]),
+    "ptb_post_process": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_uint32, C.c_float, C.c_uint32]),
 }
 
 _lib = None
@@ -268,6 +269,16 @@ class Context:
         material = np.ascontiguousarray(material, dtype=MATERIAL_DTYPE).reshape(1)
         check(load().ptb_bsdf_propagate(self._h, _ptr(material), epsilon, len(inputs), _ptr(inputs), _ptr(states), _ptr(out)))
         return out, states
+
+    def post_process(self, image, mode=2, gamma=1.8):
+        """toneMap (0) / gammaCorrect (1) / postProcess (2) on a [h, w, 4] float image; returns the processed copy."""
+        img = np.ascontiguousarray(image, dtype=np.float32).copy()
+        h, w = img.shape[:2]
+        check(load().ptb_post_process(self._h, _ptr(img), w, h, mode, gamma, 0))
+        return img
+
+    def post_process_device(self, ptr, width, height, mode=2, gamma=1.8):
+        check(load().ptb_post_process(self._h, C.c_void_p(ptr), width, height, mode, gamma, PTB_FLAG_DEVICE_IO))
 
     def bsdf_spectrum(self, material, synthetic, inputs):
         inputs = _f32(inputs, (-1, 13))

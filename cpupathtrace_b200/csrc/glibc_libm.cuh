@@ -68,8 +68,8 @@ namespace ptb {
         return which == 0 ? sinf(y) : cosf(y);
     }
 
-    __device__ __noinline__ float libmFallbackPowHalf(float x) {
-        return powf(x, 0.5F);
+    __device__ __noinline__ float libmFallbackPow(float x, float y) {
+        return powf(x, y);
     }
 
     // which = 0: sinf(y), which = 1: cosf(y)
@@ -107,16 +107,20 @@ namespace ptb {
 #include "glibc_libm_tables.h"
 #undef PTB_TABLE
 
-    PTB_DEV float glibcPowfHalf(float x) {
+    // powf(x, y) for finite x >= 0 and finite y != 0 (e_powf.c: log2_inline, exp2_inline and the zero / subnormal /
+    // overflow / underflow branches that this argument range can reach).  Callers: propagation.cpp:14 (y = 0.5) and
+    // post_processing.cpp:170 (y = 1 / gamma - 1).
+    PTB_DEV float glibcPowfPositive(float x, float y) {
         uint32_t ix = __float_as_uint(x);
-        if(ix == 0U) {
-            return 0.0F;
-        }
         if(ix - 0x00800000U >= 0x7f800000U - 0x00800000U) {
             if(ix >= 0x7f800000U) {
-                return libmFallbackPowHalf(x); // negative, inf or NaN: outside the path's argument range
+                return libmFallbackPow(x, y); // negative, inf or NaN: outside the supported argument range
             }
-            // subnormal: normalise (e_powf.c)
+            if(ix == 0U) {
+                // x == +0: x^y = 0 for y > 0, +inf for y < 0 (1 / (x * x))
+                return (__float_as_uint(y) & 0x80000000U) != 0U ? CUDART_INF_F : 0.0F;
+            }
+            // subnormal: normalise
             ix = __float_as_uint(x * 0x1p23F);
             ix &= 0x7fffffffU;
             ix -= 23U << 23;
@@ -133,18 +137,28 @@ namespace ptb {
         const double r = fma(z, invc, -1.0);
         const double y0 = logc + static_cast<double>(k);
         const double r2 = r * r;
-        double y = fma(kPowfLog2Poly[0], r, kPowfLog2Poly[1]);
+        double lg = fma(kPowfLog2Poly[0], r, kPowfLog2Poly[1]);
         const double p = fma(kPowfLog2Poly[2], r, kPowfLog2Poly[3]);
         const double r4 = r2 * r2;
         double q = fma(kPowfLog2Poly[4], r, y0);
         q = fma(p, r2, q);
-        y = fma(y, r4, q);
-        // exp2_inline(0.5 * log2 x)
-        const double xd = 0.5 * y;
-        double kd = xd + kExp2fShiftScaled;
+        lg = fma(lg, r4, q);
+        const double ylogx = static_cast<double>(y) * lg;
+        // |y * log2(x)| >= 126: overflow / underflow (e_powf.c)
+        if(((static_cast<unsigned long long>(__double_as_longlong(ylogx)) >> 47) & 0xffffULL) >=
+           (static_cast<unsigned long long>(__double_as_longlong(126.0)) >> 47)) {
+            if(ylogx > 0x1.fffffffd1d571p+6) {
+                return CUDART_INF_F; // __math_oflowf
+            }
+            if(ylogx <= -150.0) {
+                return 0.0F; // __math_uflowf
+            }
+        }
+        // exp2_inline
+        double kd = ylogx + kExp2fShiftScaled;
         const unsigned long long ki = static_cast<unsigned long long>(__double_as_longlong(kd));
         kd -= kExp2fShiftScaled;
-        const double rr = xd - kd;
+        const double rr = ylogx - kd;
         unsigned long long t = kExp2fTab[ki % 32ULL];
         t += ki << (52 - 5);
         const double s = __longlong_as_double(static_cast<long long>(t));
@@ -154,6 +168,10 @@ namespace ptb {
         out = fma(zz, rr2, out);
         out = out * s;
         return static_cast<float>(out);
+    }
+
+    PTB_DEV float glibcPowfHalf(float x) {
+        return glibcPowfPositive(x, 0.5F);
     }
 
     // ---- acosf (fdlibm, fp32, no contraction)

@@ -5,9 +5,13 @@
 #include "bvh_build.h"
 #include "host_math.h"
 #include "kernels.cuh"
+#include "post_process.cuh"
+
+#include <cub/cub.cuh>
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1394,6 +1398,117 @@ int ptb_bsdf_spectrum(ptb_context *ctx, const ptb_material *material, uint32_t s
     PTB_CUDA(cudaGetLastError());
     PTB_CUDA(cudaMemcpyAsync(out, ctx->io_c.ptr, n * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+int ptb_post_process(ptb_context *ctx, float *rgba, int32_t width, int32_t height, uint32_t mode, float gamma, uint32_t flags) {
+    if(ctx == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_post_process: null context");
+    }
+    if(mode > PTB_POST_BOTH) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_post_process: unknown mode");
+    }
+    if(width < 0 || height < 0 || static_cast<int64_t>(width) * height > 0x7FFFFFFFLL) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_post_process: image size out of range");
+    }
+    const uint32_t n = static_cast<uint32_t>(width) * static_cast<uint32_t>(height);
+    if(n == 0U) {
+        return PTB_OK;
+    }
+    if(rgba == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_post_process: null image");
+    }
+    std::lock_guard<std::mutex> lock(ctx->mutex);
+    int status = useDevice(ctx);
+    if(status != PTB_OK) {
+        return status;
+    }
+    const bool device_io = (flags & PTB_FLAG_DEVICE_IO) != 0U;
+    const size_t image_bytes = static_cast<size_t>(n) * sizeof(float4);
+    float4 *pixels = reinterpret_cast<float4 *>(rgba);
+    if(!device_io) {
+        if((status = ctx->io_d.reserve(image_bytes)) != PTB_OK) {
+            return status;
+        }
+        pixels = ctx->io_d.as<float4>();
+        PTB_CUDA(cudaMemcpyAsync(pixels, rgba, image_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const unsigned blocks = (n + 255U) / 256U;
+
+    if(mode == PTB_POST_TONE_MAP || mode == PTB_POST_BOTH) {
+        // segment weights and the data-independent part of the ceilings recurrence (post_processing.cpp:92-128):
+        // which sorted element each segment's ceiling picks depends on the pixel count and the weights only
+        const int pixel_count = static_cast<int>(n);
+        const int segments = std::min(1024, pixel_count);
+        std::vector<float> weights(static_cast<size_t>(segments));
+        float total_weight = 0.0F;
+        for(int i = 0; i < segments; i++) {
+            float x = (static_cast<float>(i) + 0.5F) / static_cast<float>(segments);
+            x = 2.0F * (x - 0.5F);
+            constexpr float pi = static_cast<float>(M_PI);
+            const float fac = 1.0F / (std::sqrt(2 * pi));
+            const float exponent_part = (x - 0.0F) / (0.3F);
+            const float gaussian = fac * std::exp(-(exponent_part * exponent_part) / 2.0F) / 0.3F;
+            weights[i] = 0.1F + gaussian;
+            total_weight += weights[i];
+        }
+        std::vector<int32_t> pick(static_cast<size_t>(segments), -1);
+        int previous_index = 0;
+        float missed = 0.0F;
+        for(int i = 0; i < segments - 1; i++) {
+            const int item_count = static_cast<int>(std::round(weights[i] * static_cast<float>(pixel_count) / total_weight + missed));
+            if(item_count > 0) {
+                pick[i] = std::min(previous_index + item_count - 1, pixel_count - 1);
+                previous_index += item_count;
+                missed = 0.0F;
+            }
+            else {
+                missed += weights[i] * static_cast<float>(pixel_count) / total_weight;
+            }
+        }
+
+        size_t sort_bytes = 0;
+        size_t reduce_bytes = 0;
+        PTB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, static_cast<const float *>(nullptr), static_cast<float *>(nullptr), static_cast<int>(n), 0, 32,
+                                                ctx->stream));
+        PTB_CUDA(cub::DeviceReduce::Min(nullptr, reduce_bytes, static_cast<const float *>(nullptr), static_cast<float *>(nullptr), static_cast<int>(n), ctx->stream));
+        const size_t temp_bytes = std::max(sort_bytes, reduce_bytes) + 256;
+        const size_t floats = static_cast<size_t>(n);
+        // io_a: brightness | sorted ; io_b: cub temp ; io_c: range(2) + ceilings + pick
+        if((status = ctx->io_a.reserve(2 * floats * sizeof(float))) != PTB_OK || (status = ctx->io_b.reserve(temp_bytes)) != PTB_OK ||
+           (status = ctx->io_c.reserve((2 + 2 * static_cast<size_t>(segments)) * sizeof(float) + 64)) != PTB_OK) {
+            return status;
+        }
+        float *brightness = ctx->io_a.as<float>();
+        float *sorted = brightness + floats;
+        float *range = ctx->io_c.as<float>();
+        float *ceilings = range + 2;
+        int32_t *d_pick = reinterpret_cast<int32_t *>(ceilings + segments);
+        PTB_CUDA(cudaMemcpyAsync(d_pick, pick.data(), static_cast<size_t>(segments) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        PTB_CUDA(cudaStreamSynchronize(ctx->stream)); // `pick` is pageable host memory owned by this frame
+
+        brightnessKernel<<<blocks, 256, 0, ctx->stream>>>(pixels, n, brightness);
+        size_t bytes = temp_bytes;
+        PTB_CUDA(cub::DeviceReduce::Min(ctx->io_b.ptr, bytes, brightness, range, static_cast<int>(n), ctx->stream));
+        bytes = temp_bytes;
+        PTB_CUDA(cub::DeviceReduce::Max(ctx->io_b.ptr, bytes, brightness, range + 1, static_cast<int>(n), ctx->stream));
+        rangeKernel<<<1, 32, 0, ctx->stream>>>(range);
+        bytes = temp_bytes;
+        PTB_CUDA(cub::DeviceRadixSort::SortKeys(ctx->io_b.ptr, bytes, brightness, sorted, static_cast<int>(n), 0, 32, ctx->stream));
+        ceilingsKernel<<<1, 32, 0, ctx->stream>>>(sorted, d_pick, segments, range, ceilings);
+        toneMapKernel<<<blocks, 256, 0, ctx->stream>>>(pixels, n, ceilings, segments, range);
+        PTB_CUDA(cudaGetLastError());
+    }
+    if(mode == PTB_POST_GAMMA || mode == PTB_POST_BOTH) {
+        const float exponent = 1.0F / gamma - 1.0F;
+        gammaKernel<<<blocks, 256, 0, ctx->stream>>>(pixels, n, exponent);
+        PTB_CUDA(cudaGetLastError());
+    }
+    if(!device_io) {
+        PTB_CUDA(cudaMemcpyAsync(rgba, pixels, image_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    PTB_CUDA(cudaGetLastError());
     return PTB_OK;
 }
 

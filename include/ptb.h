@@ -277,6 +277,19 @@ int ptb_bsdf_propagate(ptb_context *ctx, const ptb_material *material, float eps
  * in: 13 floats (from-camera direction, to-light direction, normal, light rgba); out: 6 floats (rgba, shade, density) */
 int ptb_bsdf_spectrum(ptb_context *ctx, const ptb_material *material, uint32_t synthetic, uint64_t n, const float *in, float *out);
 
+/* ------------------------------------------------------------------------------------------------ post-processing
+ *
+ * toneMap / gammaCorrect / postProcess (reference src/post_processing.cpp:32-163, 165-177, 179-182) in place on a
+ * width x height RGBA float image (host pointer, or a device pointer with PTB_FLAG_DEVICE_IO so that a frame rendered
+ * into HBM by ptb_render can be post-processed without leaving the device).  Alpha is left untouched. */
+typedef enum ptb_post_mode {
+    PTB_POST_TONE_MAP = 0,
+    PTB_POST_GAMMA = 1,
+    PTB_POST_BOTH = 2 /* tone map, then gamma */
+} ptb_post_mode;
+
+int ptb_post_process(ptb_context *ctx, float *rgba, int32_t width, int32_t height, uint32_t mode, float gamma, uint32_t flags);
+
 #ifdef __cplusplus
 }
 #endif

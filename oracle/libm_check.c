@@ -88,9 +88,14 @@ static float restated_sincos(float y, int which) {
     return sincos_poly(x * s, x * x, p, which == 0 ? n : (n ^ 1));
 }
 
-static float restated_powf_half(float x) {
+static float restated_powf(float x, float y_exp) {
     uint32_t ix = asuint(x);
-    if(ix == 0) return 0.0f;
+    if(ix == 0) return (asuint(y_exp) & 0x80000000u) ? INFINITY : 0.0f;
+    if(ix < 0x00800000) {
+        ix = asuint(x * 0x1p23f);
+        ix &= 0x7fffffff;
+        ix -= 23u << 23;
+    }
     uint32_t tmp = ix - 0x3f330000;
     int i = (tmp >> (23 - 4)) % 16;
     uint32_t top = tmp & 0xff800000;
@@ -107,7 +112,11 @@ static float restated_powf_half(float x) {
     double q = FMA(kPowfLog2Poly[4], r, y0);
     q = FMA(p, r2, q);
     y = FMA(y, r4, q);
-    double xd = 0.5 * y;
+    double xd = (double)y_exp * y;
+    if(((asuint64(xd) >> 47) & 0xffff) >= (asuint64(126.0) >> 47)) {
+        if(xd > 0x1.fffffffd1d571p+6) return INFINITY;
+        if(xd <= -150.0) return 0.0f;
+    }
     double kd = xd + kExp2fShiftScaled;
     uint64_t ki = asuint64(kd);
     kd -= kExp2fShiftScaled;
@@ -174,7 +183,13 @@ void pto_libm_check(uint64_t n, uint64_t seed, uint64_t mismatches[4]) {
         volatile float arg = 1.0f - 2.0f * vu;
         if(sinf(angle) != restated_sincos(angle, 0)) mismatches[0]++;
         if(cosf(angle) != restated_sincos(angle, 1)) mismatches[1]++;
-        if(powf(vu, 0.5f) != restated_powf_half(vu)) mismatches[2]++;
+        if(powf(vu, 0.5f) != restated_powf(vu, 0.5f)) mismatches[2]++;
+        /* post_processing.cpp:170: pow(brightness, 1 / gamma - 1) over a wide range of brightness and gamma */
+        {
+            volatile float bx = ldexpf(vu + 1e-9f, (int)((s >> 8) % 61) - 40);
+            volatile float by = ((s >> 20) & 1) ? (1.0f / 1.8f - 1.0f) : (float)(int)((s >> 24) % 4001 - 2000) / 500.0f;
+            if(by != 0.0f && powf(bx, by) != restated_powf(bx, by)) mismatches[2]++;
+        }
         float a = acosf(arg), b = restated_acosf(arg);
         if(a != b) mismatches[3]++;
         /* the sphere sampler also takes sin/cos of phi = acos(.) in [0, pi] */

@@ -68,24 +68,6 @@ def test_obj_parser_edge_cases_match_reference(ref, b200):
                 assert ta.shape == tb.shape and np.array_equal(ta, tb, equal_nan=True), (text, smooth, tr)
 
 
-def test_post_processing_matches_reference(ref, b200):
-    """toneMap / gammaCorrect / postProcess are host-side in both implementations (reference
-    test/post_processing_test.cpp checks dimensions and gamma 1.0 identity; here the values themselves)."""
-    rng = np.random.Generator(np.random.PCG64(1234))
-    image = rng.gamma(0.6, 0.4, size=(37, 53, 4)).astype(np.float32)
-    image[..., 3] = (rng.uniform(size=(37, 53)) > 0.1).astype(np.float32)
-    image[5:9, 7:20] = 0.0
-    for mode in (0, 1, 2):
-        a = ref.post_process(mode, image, 1.8)
-        b = b200.post_process(mode, image, 1.8)
-        assert a.shape == image.shape
-        assert np.allclose(a, b, rtol=2e-6, atol=1e-7, equal_nan=True), mode  # black pixels: 0 ** negative = inf, inf * 0 = NaN on both sides
-    assert np.array_equal(b200.post_process(1, image, 1.0)[..., 3], image[..., 3])
-    assert np.allclose(b200.post_process(1, image, 1.0), image, rtol=1e-6)
-    tiny = np.full((1, 1, 4), 0.25, np.float32)
-    assert np.allclose(ref.post_process(2, tiny), b200.post_process(2, tiny), rtol=2e-6)
-
-
 def test_png_round_trip(b200):
     """reference test/image/image_io_test.cpp:12-40: encode/decode within 0.004 per channel (seeded random 256x128)."""
     rng = np.random.Generator(np.random.PCG64(1234))

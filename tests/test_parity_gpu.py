@@ -270,3 +270,30 @@ def test_large_sample_batch_is_bit_exact(ref, b200):
     bad, exact, want, got = _sample_parity(ref, b200, scenes.cornell_demo(("obj", scenes.standin_obj(90, 60))), cam, 160, 90, 250000, seed=77)
     print(f"250k: diverged {bad:.6f}, bit-exact {exact:.6f}")
     assert bad == 0.0 and exact == 1.0
+
+
+def test_post_processing_is_bit_exact(ref, b200, ctx):
+    """toneMap / gammaCorrect / postProcess run on the device behind the reference's API (row f3) and must reproduce the
+    reference's values bit for bit (reference test/post_processing_test.cpp only checks dimensions and gamma 1.0)."""
+    from cpupathtrace_b200 import capi
+
+    rng = np.random.Generator(np.random.PCG64(1234))
+    for (h, w) in [(37, 53), (1, 1), (3, 300), (270, 480)]:
+        image = rng.gamma(0.6, 0.4, size=(h, w, 4)).astype(np.float32)
+        image[..., 3] = (rng.uniform(size=(h, w)) > 0.1).astype(np.float32)
+        if h > 8:
+            image[5:9, 7:20] = 0.0  # black pixels: gamma gives 0 ** negative = inf, inf * 0 = NaN on both sides
+        for mode, gamma in ((0, 1.8), (1, 1.8), (1, 2.2), (1, 1.0), (2, 1.8)):
+            want = ref.post_process(mode, image, gamma)
+            got = b200.post_process(mode, image, gamma)
+            assert np.array_equal(want, got, equal_nan=True), (h, w, mode, gamma)
+            assert np.array_equal(got[..., 3], image[..., 3])
+            assert np.array_equal(ctx.post_process(image, mode, gamma), want, equal_nan=True)
+    # a rendered frame, processed where it lives
+    import torch
+
+    frame = torch.from_numpy(rng.gamma(0.5, 0.2, size=(64, 96, 4)).astype(np.float32)).cuda()
+    host = frame.cpu().numpy()
+    ctx.post_process_device(frame.data_ptr(), 96, 64, 2, 1.8)
+    torch.cuda.synchronize()
+    assert np.array_equal(frame.cpu().numpy(), ref.post_process(2, host), equal_nan=True)
