@@ -49,6 +49,8 @@ def parse_args():
     p.add_argument("--spp", type=int, default=256)
     p.add_argument("--mesh", default="1000x500", help="stand-in mesh grid nu x nv (2 triangles per cell); 'none' = Cornell only")
     p.add_argument("--max-depth", type=int, default=0, help="0 = unlimited, as the reference")
+    p.add_argument("--reference-closest", action="store_true",
+                   help="closest-hit queries walk the reference-topology tree only (default: certified SAH walk + re-trace of uncertified rays)")
     p.add_argument("--reference-shadows", action="store_true",
                    help="trace shadow rays exactly like the reference (closest-hit queries, also for glass/mirror vertices whose result is discarded)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -254,6 +256,9 @@ def run_b200_arm(args):
     capi.check(lib.ptb_scene_get_info(handle, C.byref(info)))
 
     flags = 0 if args.reference_shadows else (capi.PTB_FLAG_ANY_HIT_SHADOWS | capi.PTB_FLAG_SKIP_NULL_SHADOWS)
+    if not args.reference_closest:
+        flags |= capi.PTB_FLAG_CERTIFIED_CLOSEST
+    os.environ["PTB_CERTIFIED_CLOSEST"] = "0" if args.reference_closest else "1"
     os.environ["PTB_MAX_DEPTH"] = str(args.max_depth)
     os.environ["PTB_ANY_HIT_SHADOWS"] = "0" if args.reference_shadows else "1"
     os.environ["PTB_SKIP_NULL_SHADOWS"] = "0" if args.reference_shadows else "1"
@@ -329,7 +334,7 @@ def run_b200_arm(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     step_ms, wall_ms = [], []
-    totals = {"samples": 0, "closest": 0, "shadow": 0, "skipped": 0, "vertices": 0, "launches": 0, "trace_ms": 0.0, "shade_ms": 0.0, "iterations": 0,
+    totals = {"samples": 0, "closest": 0, "shadow": 0, "skipped": 0, "vertices": 0, "launches": 0, "retraced": 0, "trace_ms": 0.0, "shade_ms": 0.0, "iterations": 0,
               "shadow_ms": 0.0}
     for i in range(args.steps):
         flush.zero_()
@@ -345,6 +350,7 @@ def run_b200_arm(args):
         totals["closest"] += stats.closest_rays
         totals["shadow"] += stats.shadow_rays
         totals["skipped"] += stats.shadow_rays_skipped
+        totals["retraced"] += stats.closest_rays_retraced
         totals["vertices"] += stats.path_vertices
         totals["launches"] += stats.kernel_launches + (1 if dist is not None else 0)
         totals["trace_ms"] += stats.device_ms_trace
@@ -444,6 +450,8 @@ def run_b200_arm(args):
         "scene": {"prims": int(info.n_prims), "inner_nodes": int(info.n_inner_nodes), "bvh_depth": int(info.bvh_depth),
                   "device_mb": info.device_bytes / 2**20, "build_s": info.build_seconds, "scene_ctor_s": t_build},
         "bounce_iterations_per_step": totals["iterations"] / args.steps,
+        "closest_hit": ("reference-topology tree" if args.reference_closest else
+                        f"certified SAH walk; {totals['retraced']} of {totals['closest']} closest-hit rays had no certificate and were re-traced on the reference tree"),
     }
     print(json.dumps(line))
     if dist is not None:

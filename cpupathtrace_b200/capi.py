@@ -24,6 +24,7 @@ PTB_FLAG_DEVICE_IO = 0x1
 PTB_FLAG_ANY_HIT_SHADOWS = 0x2
 PTB_FLAG_SKIP_NULL_SHADOWS = 0x4
 PTB_FLAG_COUNT_VISITS = 0x8
+PTB_FLAG_CERTIFIED_CLOSEST = 0x10
 
 # numpy dtypes of the POD records (layout-identical to the C structs)
 PRIM_DTYPE = np.dtype([("kind", "<u4"), ("material", "<u4"), ("cull_backface", "<u4"), ("reserved", "<u4"), ("p", "<f4", (18,))])
@@ -111,6 +112,7 @@ class RenderStats(C.Structure):
         ("device_ms_trace_shadow", C.c_double),
         ("shadow_inner_visits", C.c_uint64),
         ("shadow_leaf_visits", C.c_uint64),
+        ("closest_rays_retraced", C.c_uint64),
     ]
 
     def as_dict(self):

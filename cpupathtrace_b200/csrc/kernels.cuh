@@ -40,8 +40,11 @@ namespace ptb {
         kCountFetchShadow = 4,
         kCountSkippedShadows = 5,
         kCountVertices = 6,
-        kCounterSlots = 8
+        kCountRedo = 7,      // rays the certified closest-hit walk handed back
+        kCountFetchRedo = 8, // fetch cursor of their re-trace on the reference tree
+        kCounterSlots = 12
     };
+    constexpr int kPerIterationCounters = kCountFetchRedo - kCountShadow + 1; // slots zeroed before every bounce iteration
 
     constexpr uint32_t kFlagTerminated = 1U;
     constexpr uint32_t kFlagXorshift = 2U;
@@ -215,12 +218,16 @@ namespace ptb {
     }
 
     // Persistent warps over the device-side queue; scheduling by warp votes, see warpTrace in traverse.cuh.
-    template<bool COUNT>
+    // MODE = kTraceClosest walks the reference tree; MODE = kTraceCertified walks the SAH hierarchy and appends the
+    // paths whose result carries no certificate to `redo_queue` (length counters[kCountRedo]), which a second launch
+    // of the kTraceClosest instantiation then serves (queue = redo_queue, queue_slot = kCountRedo).
+    template<int MODE, bool COUNT>
     __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) traceClosestKernel(DeviceScene scene, VoteParams vote, PathPool pool, const uint32_t *__restrict__ queue,
-                                                                 uint32_t *__restrict__ counters, int queue_slot, VisitCounters *visits) {
+                                                                 uint32_t *__restrict__ counters, int queue_slot, int cursor_slot, uint32_t *__restrict__ redo_queue,
+                                                                 VisitCounters *visits) {
         const uint32_t count = counters[queue_slot];
-        warpTrace<false, COUNT>(
-          scene, vote, &counters[kCountFetchClosest], count,
+        warpTrace<MODE, COUNT>(
+          MODE == kTraceCertified ? occlusionView(scene) : scene, vote, &counters[cursor_slot], count,
           [&](uint32_t k, V3 &o, V3 &d, float &limit) {
               const uint32_t i = queue[k];
               const float4 ro = pool.ray_o[i];
@@ -229,7 +236,16 @@ namespace ptb {
               d = mk3(rd.x, rd.y, rd.z);
               limit = 0.0F;
           },
-          [&](uint32_t k, const Hit &h) { pool.hit[queue[k]] = make_float2(h.t, __int_as_float(h.slot)); }, visits);
+          [&](uint32_t k, const Hit &h, bool certain) {
+              const uint32_t i = queue[k];
+              if(MODE == kTraceCertified && !certain) {
+                  redo_queue[atomicAdd(&counters[kCountRedo], 1U)] = i;
+              }
+              else {
+                  pool.hit[i] = make_float2(h.t, __int_as_float(h.slot));
+              }
+          },
+          visits);
     }
 
     template<bool COUNT>
@@ -245,15 +261,15 @@ namespace ptb {
             limit = so.w;
         };
         if(any_hit != 0U) {
-            warpTrace<true, COUNT>(
+            warpTrace<kTraceAnyHit, COUNT>(
               occlusionView(scene), vote, &counters[kCountFetchShadow], count, fetch,
-              [&](uint32_t k, const Hit &h) { pool.shadow_c[shadow_queue[k]].w = h.slot < 0 ? 1.0F : 0.0F; }, visits);
+              [&](uint32_t k, const Hit &h, bool) { pool.shadow_c[shadow_queue[k]].w = h.slot < 0 ? 1.0F : 0.0F; }, visits);
         }
         else {
             // the reference's full closest-hit query (worker.cpp:84-86): unoccluded iff t < 0 or t >= |to_light| - epsilon
-            warpTrace<false, COUNT>(
+            warpTrace<kTraceClosest, COUNT>(
               scene, vote, &counters[kCountFetchShadow], count, fetch,
-              [&](uint32_t k, const Hit &h) {
+              [&](uint32_t k, const Hit &h, bool) {
                   const uint32_t slot = shadow_queue[k];
                   const float limit = pool.shadow_o[slot].w;
                   pool.shadow_c[slot].w = (h.t < 0.0F || h.t >= limit) ? 1.0F : 0.0F;
@@ -595,20 +611,33 @@ namespace ptb {
 
     // ------------------------------------------------------------------------------------------------ unit kernels
 
-    template<bool COUNT>
-    __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) intersectKernel(DeviceScene scene, VoteParams vote, const float *__restrict__ rays, uint32_t n, float *__restrict__ t_out,
-                                                              int32_t *__restrict__ prim_out, uint32_t *__restrict__ cursor, VisitCounters *visits) {
-        warpTrace<false, COUNT>(
-          scene, vote, cursor, n,
+    // Batch closest-hit query.  `index` (may be null) selects the rays of a re-trace pass: work item k is ray index[k].
+    // MODE = kTraceCertified appends the rays without a certificate to `redo` (length *redo_count) instead of
+    // writing their result.
+    template<int MODE, bool COUNT>
+    __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) intersectKernel(DeviceScene scene, VoteParams vote, const float *__restrict__ rays, const uint32_t *__restrict__ index,
+                                                              const uint32_t *__restrict__ index_count, uint32_t n, float *__restrict__ t_out, int32_t *__restrict__ prim_out,
+                                                              uint32_t *__restrict__ cursor, uint32_t *__restrict__ redo, uint32_t *__restrict__ redo_count,
+                                                              VisitCounters *visits) {
+        const uint32_t count = index != nullptr ? *index_count : n;
+        warpTrace<MODE, COUNT>(
+          MODE == kTraceCertified ? occlusionView(scene) : scene, vote, cursor, count,
           [&](uint32_t k, V3 &o, V3 &d, float &limit) {
-              const float *p = rays + 6 * static_cast<size_t>(k);
+              const uint32_t ray = index != nullptr ? index[k] : k;
+              const float *p = rays + 6 * static_cast<size_t>(ray);
               o = mk3(p[0], p[1], p[2]);
               d = mk3(p[3], p[4], p[5]);
               limit = 0.0F;
           },
-          [&](uint32_t k, const Hit &h) {
-              t_out[k] = h.t;
-              prim_out[k] = (h.slot >= 0 && h.t >= 0.0F) ? static_cast<int32_t>(scene.slot_to_prim[h.slot]) : -1;
+          [&](uint32_t k, const Hit &h, bool certain) {
+              const uint32_t ray = index != nullptr ? index[k] : k;
+              if(MODE == kTraceCertified && !certain) {
+                  redo[atomicAdd(redo_count, 1U)] = ray;
+              }
+              else {
+                  t_out[ray] = h.t;
+                  prim_out[ray] = (h.slot >= 0 && h.t >= 0.0F) ? static_cast<int32_t>(scene.slot_to_prim[h.slot]) : -1;
+              }
           },
           visits);
     }
@@ -616,7 +645,7 @@ namespace ptb {
     template<bool COUNT>
     __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) occludedKernel(DeviceScene scene, VoteParams vote, const float *__restrict__ rays, uint32_t n, uint8_t *__restrict__ out,
                                                              uint32_t *__restrict__ cursor, VisitCounters *visits) {
-        warpTrace<true, COUNT>(
+        warpTrace<kTraceAnyHit, COUNT>(
           occlusionView(scene), vote, cursor, n,
           [&](uint32_t k, V3 &o, V3 &d, float &limit) {
               const float *p = rays + 7 * static_cast<size_t>(k);
@@ -624,7 +653,7 @@ namespace ptb {
               d = mk3(p[3], p[4], p[5]);
               limit = p[6];
           },
-          [&](uint32_t k, const Hit &h) { out[k] = h.slot >= 0 ? 1 : 0; }, visits);
+          [&](uint32_t k, const Hit &h, bool) { out[k] = h.slot >= 0 ? 1 : 0; }, visits);
     }
 
     __global__ void aabbKernel(float lox, float loy, float loz, float hix, float hiy, float hiz, const float *__restrict__ rays, uint64_t n,

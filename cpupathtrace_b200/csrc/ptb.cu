@@ -92,8 +92,9 @@ struct ptb_context {
     std::mutex mutex; // entry points serialise on their context: its workspace and stream are shared state
     int device = 0;
     int sm_count = 0;
-    ptb::VoteParams vote{12, 6};
+    ptb::VoteParams vote{12, 6, 0xFFFFFFFFU};
     int trace_blocks_per_sm = 16;
+    bool log_iterations = false; // PTB_LOG_ITERATIONS=1: one stderr line per bounce iteration
     cudaStream_t stream = nullptr;
 
     // wavefront workspace
@@ -101,6 +102,7 @@ struct ptb_context {
     Buffer queue_a;
     Buffer queue_b;
     Buffer shadow_queue;
+    Buffer redo_queue; // paths / rays the certified closest-hit walk handed back for a re-trace on the reference tree
     Buffer counters;
     Buffer visits;
     Buffer work_cursor;
@@ -248,6 +250,9 @@ namespace {
         if((status = ctx->shadow_queue.reserve(ns * sizeof(uint32_t))) != PTB_OK) {
             return status;
         }
+        if((status = ctx->redo_queue.reserve(n * sizeof(uint32_t))) != PTB_OK) {
+            return status;
+        }
         if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK) {
             return status;
         }
@@ -277,12 +282,14 @@ namespace {
     // Starts the first `first_wave` work items of `src` in the pool and runs bounce iterations until every work item of
     // the call has been retired into `samples` (retired slots are refilled by the accumulate kernel).
     int runBounces(ptb_scene *scene, const PathPool &pool, const RenderParams &params, const PathSource &src, float4 *samples, bool count_visits,
-                   ptb_render_stats *stats) {
+                   bool certified_closest, ptb_render_stats *stats) {
         ptb_context *ctx = scene->ctx; // the calling entry point holds ctx->mutex
         uint32_t *counters = ctx->counters.as<uint32_t>();
         uint32_t *queues[2] = {ctx->queue_a.as<uint32_t>(), ctx->queue_b.as<uint32_t>()};
         uint32_t *shadow_queue = ctx->shadow_queue.as<uint32_t>();
+        uint32_t *redo_queue = ctx->redo_queue.as<uint32_t>();
         VisitCounters *visits = ctx->visits.as<VisitCounters>();
+        const bool certified = certified_closest && scene->dev.occ_nodes != nullptr;
 
         const int trace_grid = gridFor(ctx, ctx->trace_blocks_per_sm);
         const uint32_t first_wave = static_cast<uint32_t>(std::min<unsigned long long>(pool.capacity, src.total));
@@ -313,16 +320,33 @@ namespace {
             const int nxt = cur ^ 1;
             // zero: next queue length; shadow queue length, both fetch cursors and the per-iteration statistics (slots 2..6)
             PTB_CUDA(cudaMemsetAsync(counters + nxt, 0, sizeof(uint32_t), ctx->stream));
-            PTB_CUDA(cudaMemsetAsync(counters + kCountShadow, 0, 5 * sizeof(uint32_t), ctx->stream));
+            PTB_CUDA(cudaMemsetAsync(counters + kCountShadow, 0, kPerIterationCounters * sizeof(uint32_t), ctx->stream));
 
             const int flat_grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_cur) + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 32))));
             {
                 LaunchTimer timer(ctx, 0);
-                if(count_visits) {
-                    traceClosestKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur, visits);
+                if(certified) {
+                    // SAH walk with certificate, then the handed-back rays on the reference tree (usually a handful)
+                    if(count_visits) {
+                        traceClosestKernel<kTraceCertified, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur,
+                                                                                                         kCountFetchClosest, redo_queue, visits);
+                        traceClosestKernel<kTraceClosest, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, redo_queue, counters, kCountRedo,
+                                                                                                          kCountFetchRedo, redo_queue, visits);
+                    }
+                    else {
+                        traceClosestKernel<kTraceCertified, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur,
+                                                                                                          kCountFetchClosest, redo_queue, visits);
+                        traceClosestKernel<kTraceClosest, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, redo_queue, counters, kCountRedo,
+                                                                                                           kCountFetchRedo, redo_queue, visits);
+                    }
+                }
+                else if(count_visits) {
+                    traceClosestKernel<kTraceClosest, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur, kCountFetchClosest,
+                                                                                                   redo_queue, visits);
                 }
                 else {
-                    traceClosestKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur, visits);
+                    traceClosestKernel<kTraceClosest, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur, kCountFetchClosest,
+                                                                                                    redo_queue, visits);
                 }
             }
             {
@@ -362,11 +386,16 @@ namespace {
                 stats->closest_rays += n_cur;
                 stats->shadow_rays += ctx->host_counters[kCountShadow];
                 stats->shadow_rays_skipped += ctx->host_counters[kCountSkippedShadows];
+                stats->closest_rays_retraced += ctx->host_counters[kCountRedo];
                 stats->path_vertices += ctx->host_counters[kCountVertices];
                 stats->bounce_iterations += 1;
-                stats->kernel_launches += 4;
+                stats->kernel_launches += certified ? 5 : 4;
             }
             collectTimers(ctx, stats);
+            if(ctx->log_iterations) {
+                std::fprintf(stderr, "[ptb] bounce iteration: %u paths, %u shadow rays, %u retraced, %u continue\n", n_cur, ctx->host_counters[kCountShadow],
+                             ctx->host_counters[kCountRedo], ctx->host_counters[nxt]);
+            }
             n_cur = ctx->host_counters[nxt];
             cur = nxt;
         }
@@ -480,6 +509,7 @@ int ptb_context_create(int device, ptb_context **out) {
     ctx->vote.refill = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_REFILL_VOTE", 12))));
     ctx->vote.leaf = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_LEAF_VOTE", 6))));
     ctx->trace_blocks_per_sm = static_cast<int>(std::max(1L, envLong("PTB_TRACE_BLOCKS_PER_SM", 16)));
+    ctx->log_iterations = envLong("PTB_LOG_ITERATIONS", 0) != 0;
     *out = ctx;
     return PTB_OK;
 }
@@ -490,7 +520,7 @@ int ptb_context_destroy(ptb_context *ctx) {
     }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->counters, &ctx->visits, &ctx->work_cursor, &ctx->samples, &ctx->pixel_list,
+    for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->redo_queue, &ctx->counters, &ctx->visits, &ctx->work_cursor, &ctx->samples, &ctx->pixel_list,
                      &ctx->io_a, &ctx->io_b, &ctx->io_c, &ctx->io_d}) {
         b->release();
     }
@@ -800,19 +830,47 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
     PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
     PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, 2 * sizeof(VisitCounters), ctx->stream));
 
-    constexpr uint64_t kChunk = 1ULL << 30;
+    const bool certified = (flags & PTB_FLAG_CERTIFIED_CLOSEST) != 0U && scene->dev.occ_nodes != nullptr;
+    constexpr uint64_t kChunk = 1ULL << 28;
+    if(certified && (status = ctx->redo_queue.reserve(std::min<uint64_t>(kChunk, n_rays) * sizeof(uint32_t))) != PTB_OK) {
+        return status;
+    }
+    uint32_t *counters = ctx->counters.as<uint32_t>();
+    uint32_t *redo = ctx->redo_queue.as<uint32_t>();
+    VisitCounters *visits = ctx->visits.as<VisitCounters>();
+    uint64_t retraced = 0;
     for(uint64_t first = 0; first < n_rays; first += kChunk) {
         const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(kChunk, n_rays - first));
         const int grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 16))));
-        PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(uint32_t), ctx->stream));
+        PTB_CUDA(cudaMemsetAsync(counters, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
+        const float *chunk_rays = d_rays + 6 * first;
         LaunchTimer timer(ctx, 0);
-        if(count_visits) {
-            intersectKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, d_rays + 6 * first, n, d_t + first, d_prim + first, ctx->counters.as<uint32_t>(),
-                                                                     ctx->visits.as<VisitCounters>());
+        if(certified) {
+            if(count_visits) {
+                intersectKernel<kTraceCertified, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, nullptr, nullptr, n, d_t + first, d_prim + first,
+                                                                                        counters + kCountFetchClosest, redo, counters + kCountRedo, visits);
+                intersectKernel<kTraceClosest, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, redo, counters + kCountRedo, n, d_t + first, d_prim + first,
+                                                                                      counters + kCountFetchRedo, nullptr, nullptr, visits);
+            }
+            else {
+                intersectKernel<kTraceCertified, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, nullptr, nullptr, n, d_t + first, d_prim + first,
+                                                                                         counters + kCountFetchClosest, redo, counters + kCountRedo, visits);
+                intersectKernel<kTraceClosest, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, redo, counters + kCountRedo, n, d_t + first, d_prim + first,
+                                                                                       counters + kCountFetchRedo, nullptr, nullptr, visits);
+            }
+            if(stats != nullptr) {
+                PTB_CUDA(cudaMemcpyAsync(ctx->host_counters, counters, kCounterSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+                retraced += ctx->host_counters[kCountRedo];
+            }
+        }
+        else if(count_visits) {
+            intersectKernel<kTraceClosest, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, nullptr, nullptr, n, d_t + first, d_prim + first,
+                                                                                  counters + kCountFetchClosest, nullptr, nullptr, visits);
         }
         else {
-            intersectKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, d_rays + 6 * first, n, d_t + first, d_prim + first, ctx->counters.as<uint32_t>(),
-                                                                      ctx->visits.as<VisitCounters>());
+            intersectKernel<kTraceClosest, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, nullptr, nullptr, n, d_t + first, d_prim + first,
+                                                                                   counters + kCountFetchClosest, nullptr, nullptr, visits);
         }
     }
     PTB_CUDA(cudaGetLastError());
@@ -826,7 +884,8 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
     }
     if(stats != nullptr) {
         stats->closest_rays = n_rays;
-        stats->kernel_launches = 1;
+        stats->closest_rays_retraced = retraced;
+        stats->kernel_launches = (certified ? 2 : 1) * ((n_rays + kChunk - 1) / kChunk);
     }
     return finishStats(ctx, count_visits, stats);
 }
@@ -946,7 +1005,7 @@ int ptb_render_samples(ptb_scene *scene, const ptb_camera *camera, const ptb_ren
     src.seeds = d_seeds;
     src.explicit_samples = 1U;
     src.total = n;
-    if((status = runBounces(scene, pool, params, src, d_out, count_visits, stats)) != PTB_OK) {
+    if((status = runBounces(scene, pool, params, src, d_out, count_visits, (opts->flags & PTB_FLAG_CERTIFIED_CLOSEST) != 0U, stats)) != PTB_OK) {
         return status;
     }
     if(!device_io) {
@@ -1069,7 +1128,7 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
         src.n_pixels = n_pixels;
         src.explicit_samples = 0U;
         src.total = total;
-        if((status = runBounces(scene, pool, params, src, ctx->samples.as<float4>(), count_visits, stats)) != PTB_OK) {
+        if((status = runBounces(scene, pool, params, src, ctx->samples.as<float4>(), count_visits, (opts->flags & PTB_FLAG_CERTIFIED_CLOSEST) != 0U, stats)) != PTB_OK) {
             return status;
         }
 

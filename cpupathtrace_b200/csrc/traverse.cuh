@@ -123,8 +123,11 @@ namespace ptb {
     // this file on its own ray (same node order, same pruning, same tie rules); what the votes decide is WHEN a lane
     // takes its next step, so that the 32 lanes of a warp execute the same kind of step together:
     //
-    //   ANY_HIT = false: closest hit, `limit` ignored.
-    //   ANY_HIT = true : the ray is finished at the first primitive with 0 <= t < limit.
+    //   MODE = kTraceClosest  : closest hit on the reference-topology tree, `limit` ignored.
+    //   MODE = kTraceAnyHit   : the ray is finished at the first primitive with 0 <= t < limit.
+    //   MODE = kTraceCertified: closest hit on the SAH hierarchy plus a certificate that the reference walk returns the
+    //                           same primitive (see "certified closest hit" below); commit() receives certain = false
+    //                           for the rays that must be re-traced on the reference tree.
     //
     //   * a lane that has finished its ray does not wait for the slowest ray of a 32-ray batch: finished lanes are
     //     refilled from the device-side queue cursor as soon as kRefillVote of them are idle (one atomic per refill,
@@ -136,11 +139,33 @@ namespace ptb {
     // active threads per issued instruction with issue slots 75 % busy, i.e. the kernels were bound by SIMT divergence,
     // not by memory.
     struct VoteParams {
-        int refill; // idle lanes that trigger a refill
-        int leaf;   // parked lanes that trigger the primitive tests
+        int refill;     // idle lanes that trigger a refill
+        int leaf;       // parked lanes that trigger the primitive tests
+        uint32_t lanes; // member mask of the warp collectives: always 0xFFFFFFFF, passed at run time (see warpTrace)
     };
 
     enum LaneStatus : uint32_t { kLaneIdle = 0U, kLaneInner = 1U, kLaneLeaf = 2U };
+
+    enum TraceMode : int { kTraceClosest = 0, kTraceAnyHit = 1, kTraceCertified = 2 };
+
+    // ---- certified closest hit
+    //
+    // The reference's result depends on its tree only through ORDER: a primitive P (leaf-box entry e_P, own distance
+    // t_P) is tested iff e_P < best_t at the moment its leaf is reached (its ancestors' entries are <= e_P and were
+    // compared with an earlier, larger best_t), and replaces the best iff 0 <= t_P <= best_t.  Hence, with
+    // Q = argmin t_P over the primitives whose leaf box is hit and t_P >= 0:
+    //     if every other such primitive R has  t_R > t_Q  and  t_R > e_Q,
+    // then in ANY visiting order Q is tested (best_t is a minimum of some t_R, or FLT_MAX) and wins strictly, so the
+    // reference returns (t_Q, Q) whatever its tree looks like.  The SAH walk finds Q visiting every subtree whose entry
+    // is <= t_Q (1 + 2^-7) and checks the condition on everything it tested; primitives it never reached have
+    // e_R > t_Q (1 + 2^-7), and the certificate additionally asks e_Q <= t_Q (1 + 2^-9), so such an R could only matter if
+    // its own test returned t_R < e_R (1 - 2^-8), i.e. if Moeller-Trumbore put the hit more than 0.4 % in front of the
+    // triangle's own bounding box (only possible for |det| within rounding of the 1e-6 rejection threshold on very
+    // large triangles; the parity tests compare both modes ray for ray).  Rays without a certificate -- exact ties on
+    // shared edges and vertices, near-ties within an ulp or two of a box face -- are handed back (certain = false)
+    // and re-traced on the reference tree, so ties keep the reference's later-visited-wins outcome.
+    constexpr float kCertifiedPruneSlack = 1.0078125F;   // 1 + 2^-7
+    constexpr float kCertifiedEntrySlack = 1.001953125F; // 1 + 2^-9
 
     // Hit test of one box in "visit" form: hit <=> the reference's slab result is >= 0, entry = that result.
     // (bounding_box.cpp:61-72: -1 iff t_max < 0 or t_min > t_max; otherwise max(t_min, 0).)
@@ -158,10 +183,21 @@ namespace ptb {
         return t_max >= 0.0F && t_min <= t_max && entry < best_t;
     }
 
-    // fetch(k, o, d, limit) loads ray k; commit(k, hit) stores its result.  `cursor` is a zero-initialised device
+    // fetch(k, o, d, limit) loads ray k; commit(k, hit, certain) stores its result.  `cursor` is a zero-initialised device
     // counter shared by all warps of the launch; `count` the number of rays.
-    template<bool ANY_HIT, bool COUNT, typename Fetch, typename Commit>
+    //
+    // Every warp collective takes its member mask from a kernel parameter (vote.lanes = 0xFFFFFFFF) instead of the
+    // literal.  With the literal, ptxas (CUDA 12.9, sm_100a) drops the warp barrier in front of a vote wherever its
+    // convergence analysis says the lanes already met at a BSYNC.RECONVERGENT -- and on B200 they demonstrably do not
+    // always: a variant of this loop was caught executing its refill vote with part of the warp (64 times in one
+    // 60-launch render; the halves then disagreed on `exhausted` and the warp never terminated).  A mask the compiler
+    // cannot see through forces a real WARPSYNC / BRA.DIV in front of every collective (checked on the SASS by
+    // tests/test_abi.py).
+    template<int MODE, bool COUNT, typename Fetch, typename Commit>
     PTB_DEV void warpTrace(const DeviceScene &s, VoteParams vote, uint32_t *cursor, uint32_t count, Fetch fetch, Commit commit, VisitCounters *counters) {
+        constexpr bool ANY_HIT = MODE == kTraceAnyHit;
+        constexpr bool CERTIFIED = MODE == kTraceCertified;
+        const uint32_t lanes = vote.lanes;
         const int kRefillVote = vote.refill;
         const int kLeafVote = vote.leaf;
         const uint32_t lane = threadIdx.x & 31U;
@@ -175,6 +211,10 @@ namespace ptb {
         r.inv = r.d;
         float limit = 0.0F;
         float best_t = 0.0F;
+        float prune_t = 0.0F;    // certified mode: what subtree entries are compared with (best_t, widened)
+        float leaf_entry = 0.0F; // certified mode: entry distance of the leaf box the lane is parked at
+        float rival_t = 0.0F;    // certified mode: max(t, leaf entry) of the best; another hit at or below it voids the certificate
+        bool certain = true;
         Hit hit;
         hit.t = -1.0F;
         hit.slot = -1;
@@ -191,19 +231,22 @@ namespace ptb {
                 sp--;
                 const uint2 e = stack[sp];
                 // any-hit: the bound never shrinks, so an entry that passed `entry < limit` when deferred still passes
-                if(ANY_HIT || __uint_as_float(e.y) < best_t) {
+                if(ANY_HIT || __uint_as_float(e.y) < (CERTIFIED ? prune_t : best_t)) {
                     node = static_cast<int32_t>(e.x);
+                    if(CERTIFIED) {
+                        leaf_entry = __uint_as_float(e.y);
+                    }
                     status = node >= 0 ? kLaneInner : kLaneLeaf;
                     return;
                 }
             }
-            commit(k, hit);
+            commit(k, hit, certain);
             status = kLaneIdle;
         };
 
         for(;;) {
             // ---- (A) refill idle lanes once enough of them wait
-            const uint32_t idle_mask = __ballot_sync(0xFFFFFFFFU, status == kLaneIdle);
+            const uint32_t idle_mask = __ballot_sync(lanes, status == kLaneIdle);
             if(idle_mask == 0xFFFFFFFFU && exhausted) {
                 break;
             }
@@ -213,7 +256,7 @@ namespace ptb {
                 if(lane == 0U) {
                     base = atomicAdd(cursor, wanted);
                 }
-                base = __shfl_sync(0xFFFFFFFFU, base, 0);
+                base = __shfl_sync(lanes, base, 0);
                 if(base + wanted >= count) {
                     exhausted = true;
                 }
@@ -229,17 +272,21 @@ namespace ptb {
                         hit.slot = -1;
                         sp = 0;
                         best_t = ANY_HIT ? limit : kFloatMax;
+                        prune_t = best_t;
+                        certain = true;
+                        rival_t = 0.0F;
                         if(s.n_prims == 0U) {
-                            commit(k, hit);
+                            commit(k, hit, true);
                         }
                         else {
                             const float root_t = slab(r, s.root_lo[0], s.root_lo[1], s.root_lo[2], s.root_hi[0], s.root_hi[1], s.root_hi[2]);
                             if(!(root_t >= 0.0F)) {
                                 hit.t = root_t;
-                                commit(k, hit);
+                                commit(k, hit, true);
                             }
                             else {
                                 node = s.root_ref;
+                                leaf_entry = root_t;
                                 status = node >= 0 ? kLaneInner : kLaneLeaf;
                             }
                         }
@@ -249,7 +296,7 @@ namespace ptb {
 
             // ---- (B) descend: inner-node steps until enough lanes are parked at a leaf or waiting for a refill
             for(;;) {
-                const uint32_t inner_mask = __ballot_sync(0xFFFFFFFFU, status == kLaneInner);
+                const uint32_t inner_mask = __ballot_sync(lanes, status == kLaneInner);
                 if(inner_mask == 0U) {
                     break;
                 }
@@ -266,8 +313,9 @@ namespace ptb {
                     }
                     float lt;
                     float rt;
-                    const bool visit_left = slabVisit(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, best_t, lt);
-                    const bool visit_right = slabVisit(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, best_t, rt);
+                    const float bound = CERTIFIED ? prune_t : best_t;
+                    const bool visit_left = slabVisit(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, bound, lt);
+                    const bool visit_right = slabVisit(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, bound, rt);
                     const int32_t left = __float_as_int(n3.x);
                     const int32_t right = __float_as_int(n3.y);
                     if(visit_left && visit_right) {
@@ -278,22 +326,28 @@ namespace ptb {
                         stack[sp] = make_uint2(static_cast<uint32_t>(left_first ? right : left), __float_as_uint(left_first ? rt : lt));
                         sp++;
                         node = left_first ? left : right;
+                        if(CERTIFIED) {
+                            leaf_entry = left_first ? lt : rt;
+                        }
                         status = node >= 0 ? kLaneInner : kLaneLeaf;
                     }
                     else if(visit_left || visit_right) {
                         node = visit_left ? left : right;
+                        if(CERTIFIED) {
+                            leaf_entry = visit_left ? lt : rt;
+                        }
                         status = node >= 0 ? kLaneInner : kLaneLeaf;
                     }
                     else {
                         advance();
                     }
                 }
-                const uint32_t parked = __ballot_sync(0xFFFFFFFFU, status == kLaneLeaf);
+                const uint32_t parked = __ballot_sync(lanes, status == kLaneLeaf);
                 if(__popc(parked) >= kLeafVote) {
                     break;
                 }
                 if(!exhausted) {
-                    const uint32_t waiting = __ballot_sync(0xFFFFFFFFU, status == kLaneIdle);
+                    const uint32_t waiting = __ballot_sync(lanes, status == kLaneIdle);
                     if(__popc(waiting) >= kRefillVote) {
                         break;
                     }
@@ -311,12 +365,30 @@ namespace ptb {
                     if(t >= 0.0F && t < limit) {
                         hit.t = t;
                         hit.slot = static_cast<int32_t>(slot);
-                        commit(k, hit);
+                        commit(k, hit, true);
                         status = kLaneIdle;
                     }
                     else {
                         advance();
                     }
+                }
+                else if(CERTIFIED) {
+                    if(t >= 0.0F) {
+                        if(t < best_t) {
+                            // every primitive tested so far has t >= the old best; they clear the new rival bound iff it does
+                            const float rival = fmaxf(t, leaf_entry);
+                            certain = best_t > rival && leaf_entry <= t * kCertifiedEntrySlack && t > 0.0F;
+                            rival_t = rival;
+                            best_t = t;
+                            prune_t = t * kCertifiedPruneSlack;
+                            hit.t = t;
+                            hit.slot = static_cast<int32_t>(slot);
+                        }
+                        else if(t <= rival_t) {
+                            certain = false;
+                        }
+                    }
+                    advance();
                 }
                 else {
                     if(t >= 0.0F && (hit.slot < 0 || t <= best_t)) {

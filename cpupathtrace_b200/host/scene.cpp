@@ -11,6 +11,7 @@
 #include "device.h"
 
 #include <PathTrace/scene/scene.h>
+#include <PathTrace/worker.h>
 
 #include <cstdio>
 #include <stdexcept>
@@ -103,7 +104,8 @@ void Scene::getIntersections(const Ray *rays, std::size_t count, float *t_out, c
     }
     static_assert(sizeof(Ray) == 6 * sizeof(float), "Ray must be six packed floats");
     std::vector<int32_t> prim(count);
-    const int status = ptb_intersect(device_scene, reinterpret_cast<const float *>(rays), count, t_out, prim.data(), 0U, nullptr);
+    const int status = ptb_intersect(device_scene, reinterpret_cast<const float *>(rays), count, t_out, prim.data(),
+                                     ptb::renderControl().certified_closest ? PTB_FLAG_CERTIFIED_CLOSEST : 0U, nullptr);
     if(!ptb::host::ok(status, "Scene::getIntersections")) {
         for(std::size_t i = 0; i < count; i++) {
             t_out[i] = -1.0F;

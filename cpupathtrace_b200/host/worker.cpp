@@ -34,7 +34,8 @@ namespace {
         opts.epsilon = options.epsilon;
         opts.max_depth = control.max_depth;
         opts.rng_mode = rng_mode;
-        opts.flags = (control.any_hit_shadows ? PTB_FLAG_ANY_HIT_SHADOWS : 0U) | (control.skip_null_shadows ? PTB_FLAG_SKIP_NULL_SHADOWS : 0U);
+        opts.flags = (control.any_hit_shadows ? PTB_FLAG_ANY_HIT_SHADOWS : 0U) | (control.skip_null_shadows ? PTB_FLAG_SKIP_NULL_SHADOWS : 0U) |
+                     (control.certified_closest ? PTB_FLAG_CERTIFIED_CLOSEST : 0U);
         opts.seed = seed;
         opts.shard_count = 1;
         return opts;
@@ -71,6 +72,7 @@ namespace ptb {
             c.max_depth = static_cast<int>(envLong("PTB_MAX_DEPTH", 0));
             c.any_hit_shadows = envLong("PTB_ANY_HIT_SHADOWS", 0) != 0;
             c.skip_null_shadows = envLong("PTB_SKIP_NULL_SHADOWS", 0) != 0;
+            c.certified_closest = envLong("PTB_CERTIFIED_CLOSEST", 0) != 0;
             c.fixed_seed = static_cast<uint64_t>(envLong("PTB_SEED", 0));
             return c;
         }();

@@ -68,10 +68,11 @@ namespace ptb {
         int max_depth = 0;            //!< 0 = unlimited, paths end by Russian roulette only
         bool any_hit_shadows = false; //!< stop shadow rays at the first occluder
         bool skip_null_shadows = false; //!< do not trace shadow rays whose contribution is always zero (glass, mirror)
+        bool certified_closest = false; //!< closest hits on the SAH hierarchy where a certificate proves the reference's result, else re-traced
         uint64_t fixed_seed = 0;      //!< processJob: non-zero replaces std::random_device
     };
 
-    //! process-wide control block; initialised from PTB_MAX_DEPTH, PTB_ANY_HIT_SHADOWS, PTB_SKIP_NULL_SHADOWS, PTB_SEED
+    //! process-wide control block; initialised from PTB_MAX_DEPTH, PTB_ANY_HIT_SHADOWS, PTB_SKIP_NULL_SHADOWS, PTB_CERTIFIED_CLOSEST, PTB_SEED
     RenderControl &renderControl();
 
     /**

@@ -159,6 +159,11 @@ typedef enum ptb_rng_mode {
 #define PTB_FLAG_SKIP_NULL_SHADOWS 0x4u /* do not trace shadow rays whose BSDF returns pd 0 for synthetic rays (Glass,   */
                                         /* Mirror: worker.cpp:84-92 traces them and discards the result)                  */
 #define PTB_FLAG_COUNT_VISITS 0x8u   /* count BVH node / primitive fetches (slower; feeds the bytes-per-ray figure)      */
+#define PTB_FLAG_CERTIFIED_CLOSEST 0x10u /* closest-hit queries walk the SAH hierarchy and keep the result only when it    */
+                                     /* carries a certificate that Scene::getIntersection returns the same primitive in  */
+                                     /* any visiting order (strictly nearest, no rival within its leaf-box entry); the    */
+                                     /* remaining rays (ties on shared edges/vertices, near-ties) are re-traced on the    */
+                                     /* reference-topology tree.  See csrc/traverse.cuh "certified closest hit".          */
 
 /* RenderOptions (reference include/PathTrace/worker.h:14-31) + the knobs that exist only on this side */
 typedef struct ptb_render_opts {
@@ -196,6 +201,7 @@ typedef struct ptb_render_stats {
     double device_ms_trace_shadow;  /* the shadow-ray share of device_ms_trace            */
     uint64_t shadow_inner_visits;   /* the shadow-ray share of inner_visits               */
     uint64_t shadow_leaf_visits;    /* the shadow-ray share of leaf_visits                */
+    uint64_t closest_rays_retraced; /* PTB_FLAG_CERTIFIED_CLOSEST: queries without a certificate, re-traced on the reference tree */
 } ptb_render_stats;
 
 /* ------------------------------------------------------------------------------------------------ entry points */

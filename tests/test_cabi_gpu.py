@@ -19,15 +19,24 @@ def _scene(ctx, g):
 
 
 @pytest.mark.parametrize("name", GOLDEN_SCENES)
-def test_golden_hits(ctx, name):
+@pytest.mark.parametrize("flags", [0, capi.PTB_FLAG_CERTIFIED_CLOSEST], ids=["reference_tree", "certified_sah"])
+def test_golden_hits(ctx, name, flags):
+    """Golden closest hits of the unmodified reference (a third of the rays aimed at shared vertices / edges), through
+    the reference-topology walk and through the certified SAH walk + re-trace of the rays without a certificate."""
     g = load_golden("hits", name)
     scene = _scene(ctx, g)
-    t, prim, stats = scene.intersect(g["rays"])
+    t, prim, stats = scene.intersect(g["rays"], flags=flags)
     hit = g["t"] >= 0
     assert np.array_equal(prim, g["prim"])
     assert np.array_equal(t[hit], g["t"][hit])
     assert (t[~hit] < 0).all()
     assert stats.closest_rays == len(g["rays"]) and stats.kernel_launches >= 1
+    if flags:
+        # the tie cases must have been handed back, and only a minority of all rays
+        assert stats.closest_rays_retraced < len(g["rays"]) // 2
+        assert stats.closest_rays_retraced > 0 or name == "advanced"  # (three primitives without a shared edge)
+    else:
+        assert stats.closest_rays_retraced == 0
     scene.close()
 
 
@@ -105,6 +114,19 @@ def test_fresh_inputs_against_oracle(ctx):
     got_fast, stats_fast = scene.render_samples(camera, fast, pixels, seeds)
     assert np.array_equal(got_fast, want)
     assert stats_fast.shadow_rays + stats_fast.shadow_rays_skipped == stats.shadow_rays and stats_fast.shadow_rays_skipped > 0
+
+    # certified closest hits (SAH walk + re-trace without certificate): same hits, same samples, same ray counts
+    t_c, prim_c, stats_c = scene.intersect(rays, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST)
+    assert np.array_equal(prim_c, prim_o) and np.array_equal(t_c[hit], t_o[hit]) and (t_c[~hit] < 0).all()
+    assert stats_c.closest_rays_retraced < len(rays) // 100
+    cert = capi.render_opts(160, 100, 1, 1, 1e-3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST)
+    got_cert, stats_cert = scene.render_samples(camera, cert, pixels, seeds)
+    assert np.array_equal(got_cert, want)
+    assert stats_cert.closest_rays == stats.closest_rays and stats_cert.shadow_rays == stats.shadow_rays
+    all_fast = capi.render_opts(160, 100, 1, 1, 1e-3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT,
+                                flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_ANY_HIT_SHADOWS | capi.PTB_FLAG_SKIP_NULL_SHADOWS)
+    got_all, _ = scene.render_samples(camera, all_fast, pixels, seeds)
+    assert np.array_equal(got_all, want)
 
     # a depth cap only truncates: samples whose path is shorter than the cap are unchanged
     capped = capi.render_opts(160, 100, 1, 1, 1e-3, max_depth=3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT)
@@ -264,6 +286,12 @@ def test_full_size_scene_properties(ctx, ref):
     sub = slice(0, 50_000)
     t_ref, id_ref = spec.build(ref).intersect(rays[sub])
     assert np.array_equal(id_ref, prim[sub]) and np.array_equal(t_ref[t_ref >= 0], t[sub][t_ref >= 0])
+
+    # certified SAH walk: all 4 M results identical to the reference-topology walk, at a fraction of the node fetches
+    t_c, prim_c, stats_c = scene.intersect(rays, flags=capi.PTB_FLAG_COUNT_VISITS | capi.PTB_FLAG_CERTIFIED_CLOSEST)
+    assert np.array_equal(prim_c, prim) and np.array_equal(t_c[hit], t[hit]) and (t_c[~hit] < 0).all()
+    assert stats_c.inner_visits < stats.inner_visits // 2
+    assert stats_c.closest_rays_retraced < len(rays) // 1000
 
     # the reported primitive, intersected alone, gives the same distance (spot check on 200 rays)
     idx = np.nonzero(hit)[0][:: max(1, hit.sum() // 200)][:200]
