@@ -193,6 +193,41 @@ namespace {
     // When the event pool runs dry mid-call the remaining launches go untimed; callers that need complete
     // per-kernel sums (bench.py) keep calls short enough (see PTB_POOL_PATHS) or read device_ms_total.
 
+    // HBM this context may plan with: what is free now plus what its own workspace already holds from earlier calls
+    uint64_t plannableBytes(const ptb_context *ctx) {
+        size_t free_bytes = 0;
+        size_t total_bytes = 0;
+        if(cudaMemGetInfo(&free_bytes, &total_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        return static_cast<uint64_t>(free_bytes) + ctx->pool_mem.bytes + ctx->queue_a.bytes + ctx->queue_b.bytes + ctx->shadow_queue.bytes + ctx->redo_queue.bytes +
+               ctx->samples.bytes;
+    }
+
+    // Paths kept in flight.  The trace kernels are persistent and end every launch with a drain phase in which each warp
+    // finishes its last rays at low lane occupancy; its length does not depend on the queue length, so the pool is made
+    // as large as memory comfortably allows (measured on the bench scene at 256 spp: 4 Mi paths 321, 32 Mi 438,
+    // 128 Mi 469 Msamples/s).  Default: 128 Mi paths (~30 GB with two shadow slots), at most a fifth of the HBM at hand.
+    uint64_t poolLimit(const ptb_context *ctx, uint32_t shadow_stride) {
+        const long forced = envLong("PTB_POOL_PATHS", 0);
+        if(forced > 0) {
+            return static_cast<uint64_t>(forced);
+        }
+        const uint64_t bytes_per_path = 112ULL + 48ULL * shadow_stride + 4ULL * (3ULL + shadow_stride);
+        const uint64_t by_memory = plannableBytes(ctx) / 5ULL / bytes_per_path;
+        return std::max<uint64_t>(1ULL << 16, std::min<uint64_t>(1ULL << 27, by_memory));
+    }
+
+    // Per-sample buffer budget of ptb_render (16 B per pixel-sample): PTB_SAMPLE_BUFFER_MB, else 40 % of the HBM at hand.
+    uint64_t sampleBufferBudget(const ptb_context *ctx) {
+        const long forced = envLong("PTB_SAMPLE_BUFFER_MB", 0);
+        if(forced > 0) {
+            return static_cast<uint64_t>(forced) << 20;
+        }
+        return std::max<uint64_t>(64ULL << 20, plannableBytes(ctx) * 2ULL / 5ULL);
+    }
+
     int carvePool(ptb_context *ctx, uint32_t capacity, uint32_t shadow_stride, PathPool &pool) {
         const size_t n = capacity;
         const size_t ns = n * shadow_stride;
@@ -275,6 +310,7 @@ namespace {
         p.rng_xorshift = opts.rng_mode == PTB_RNG_REFERENCE_XORSHIFT ? 1U : 0U;
         p.any_hit_shadows = (opts.flags & PTB_FLAG_ANY_HIT_SHADOWS) != 0U ? 1U : 0U;
         p.skip_null_shadows = (opts.flags & PTB_FLAG_SKIP_NULL_SHADOWS) != 0U ? 1U : 0U;
+        p.lanes = 0xFFFFFFFFU;
         p.seed = opts.seed;
         return p;
     }
@@ -973,7 +1009,7 @@ int ptb_render_samples(ptb_scene *scene, const ptb_camera *camera, const ptb_ren
     }
     const bool device_io = (opts->flags & PTB_FLAG_DEVICE_IO) != 0U;
     const bool count_visits = (opts->flags & PTB_FLAG_COUNT_VISITS) != 0U;
-    const uint32_t capacity = static_cast<uint32_t>(std::min<uint64_t>(n, static_cast<uint64_t>(envLong("PTB_POOL_PATHS", 1L << 22))));
+    const uint32_t capacity = static_cast<uint32_t>(std::min<uint64_t>(n, poolLimit(ctx, scene->shadow_stride)));
 
     PathPool pool{};
     if((status = carvePool(ctx, capacity, scene->shadow_stride, pool)) != PTB_OK) {
@@ -1074,13 +1110,13 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
     PTB_CUDA(cudaMemsetAsync(d_out, 0, out_bytes, ctx->stream));
 
     // pixel groups: as many whole tiles as fit the per-sample buffer budget
-    const uint64_t budget_bytes = static_cast<uint64_t>(envLong("PTB_SAMPLE_BUFFER_MB", 16384)) << 20;
+    const uint64_t pool_limit = poolLimit(ctx, scene->shadow_stride);
+    const uint64_t budget_bytes = sampleBufferBudget(ctx);
     const uint64_t per_tile_bytes = static_cast<uint64_t>(tile) * tile * std::max(spp, 1) * sizeof(float4);
     uint64_t tiles_per_group = std::max<uint64_t>(1, budget_bytes / per_tile_bytes);
     // destinations are 32-bit
     tiles_per_group = std::min<uint64_t>(tiles_per_group, std::max<uint64_t>(1, (0xFFFFFFFFULL / std::max(spp, 1)) / (static_cast<uint64_t>(tile) * tile)));
 
-    const uint64_t pool_limit = static_cast<uint64_t>(envLong("PTB_POOL_PATHS", 1L << 22));
     const RenderParams params = makeParams(*camera, *opts);
     if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK || (status = ctx->visits.reserve(2 * sizeof(VisitCounters))) != PTB_OK) {
         return status;
