@@ -92,7 +92,8 @@ struct ptb_context {
     std::mutex mutex; // entry points serialise on their context: its workspace and stream are shared state
     int device = 0;
     int sm_count = 0;
-    ptb::VoteParams vote{12, 6, 0xFFFFFFFFU};
+    ptb::VoteParams vote{12, 16, 2, 0xFFFFFFFFU};        // closest-hit kernels
+    ptb::VoteParams vote_shadow{16, 16, 2, 0xFFFFFFFFU}; // any-hit / shadow kernels (shorter rays: refill in larger batches)
     int trace_blocks_per_sm = 16;
     bool log_iterations = false; // PTB_LOG_ITERATIONS=1: one stderr line per bounce iteration
     cudaStream_t stream = nullptr;
@@ -397,10 +398,10 @@ namespace {
             {
                 LaunchTimer timer(ctx, 2);
                 if(count_visits) {
-                    traceShadowKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, shadow_queue, counters, params.any_hit_shadows, visits + 1);
+                    traceShadowKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, pool, shadow_queue, counters, params.any_hit_shadows, visits + 1);
                 }
                 else {
-                    traceShadowKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, shadow_queue, counters, params.any_hit_shadows, visits + 1);
+                    traceShadowKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, pool, shadow_queue, counters, params.any_hit_shadows, visits + 1);
                 }
             }
             {
@@ -542,8 +543,13 @@ int ptb_context_create(int device, ptb_context **out) {
     PTB_CUDA(cudaEventCreate(&ctx->call_start));
     PTB_CUDA(cudaEventCreate(&ctx->call_stop));
     ctx->events_ready = envLong("PTB_PROFILE", 1) != 0;
+    // tuned on the bench scene with the 128 Mi-path pool (with the earlier 4 Mi pool the drain phases dominated and smaller votes won)
     ctx->vote.refill = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_REFILL_VOTE", 12))));
-    ctx->vote.leaf = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_LEAF_VOTE", 6))));
+    ctx->vote.leaf = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_LEAF_VOTE", 16))));
+    ctx->vote.leaf_burst = static_cast<int>(std::min(8L, std::max(1L, envLong("PTB_LEAF_BURST", 2))));
+    ctx->vote_shadow = ctx->vote;
+    ctx->vote_shadow.refill = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_SHADOW_REFILL_VOTE", envLong("PTB_REFILL_VOTE", 16)))));
+    ctx->vote_shadow.leaf = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_SHADOW_LEAF_VOTE", envLong("PTB_LEAF_VOTE", 16)))));
     ctx->trace_blocks_per_sm = static_cast<int>(std::max(1L, envLong("PTB_TRACE_BLOCKS_PER_SM", 16)));
     ctx->log_iterations = envLong("PTB_LOG_ITERATIONS", 0) != 0;
     *out = ctx;
@@ -965,11 +971,11 @@ int ptb_occluded(ptb_scene *scene, const float *rays, uint64_t n_rays, uint8_t *
         PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(uint32_t), ctx->stream));
         LaunchTimer timer(ctx, 2);
         if(count_visits) {
-            occludedKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
+            occludedKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
                                                                     ctx->visits.as<VisitCounters>() + 1);
         }
         else {
-            occludedKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
+            occludedKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
                                                                      ctx->visits.as<VisitCounters>() + 1);
         }
     }

@@ -132,7 +132,7 @@ namespace ptb {
     //   * a lane that has finished its ray does not wait for the slowest ray of a 32-ray batch: finished lanes are
     //     refilled from the device-side queue cursor as soon as kRefillVote of them are idle (one atomic per refill,
     //     claimed by ballot/popc/shfl);
-    //   * a lane that has arrived at a leaf parks until vote.leaf (default 6) lanes are parked (or no lane has inner work left),
+    //   * a lane that has arrived at a leaf parks until vote.leaf (default 16) lanes are parked (or no lane has inner work left),
     //     then the parked lanes run the primitive test together; inner-node steps run for all unparked lanes.
     //
     // Measured with ncu before this change (profiles/r01_ncu_trace_baseline.md): 6.3 (closest) and 3.4 (shadow)
@@ -141,6 +141,7 @@ namespace ptb {
     struct VoteParams {
         int refill;     // idle lanes that trigger a refill
         int leaf;       // parked lanes that trigger the primitive tests
+        int leaf_burst; // consecutive leaves one lane may test per primitive-test phase
         uint32_t lanes; // member mask of the warp collectives: always 0xFFFFFFFF, passed at run time (see warpTrace)
     };
 
@@ -354,8 +355,9 @@ namespace ptb {
                 }
             }
 
-            // ---- (C) primitive tests for every parked lane
-            if(status == kLaneLeaf) {
+            // ---- (C) primitive tests for every parked lane; a lane whose next deferred sibling is a leaf as well (the
+            // common case at the bottom of a one-primitive-per-leaf tree) tests it in the same phase instead of parking again
+            for(int burst = 0; burst < vote.leaf_burst && status == kLaneLeaf; burst++) {
                 const uint32_t slot = static_cast<uint32_t>(~node);
                 if(COUNT) {
                     n_leaf++;

@@ -95,11 +95,17 @@ def main():
         eps = 1e-3
         shadow = torch.cat([pos + ldir * eps, ldir, (dist - eps)[:, None]], dim=1)[hit].contiguous()
 
-        for name, rays, any_hit in (("coherent", coherent, False), ("incoherent", incoherent, False), ("shadow", shadow, True)):
+        cases = []
+        for name, rays in (("coherent", coherent), ("incoherent", incoherent)):
+            cases.append((name, rays, False, 0, "reference-topology tree"))
+            cases.append((name, rays, False, capi.PTB_FLAG_CERTIFIED_CLOSEST, "certified SAH walk + re-trace"))
+        cases.append(("shadow", shadow, True, 0, "any-hit on the SAH hierarchy"))
+        reference_result = {}
+        for name, rays, any_hit, mode_flags, mode in cases:
             def run(flags=0):
                 if any_hit:
                     return scene.occluded_device(rays.data_ptr(), len(rays), occ_out.data_ptr(), flags)
-                return run_closest(rays, flags)
+                return run_closest(rays, flags | mode_flags)
 
             counted = run(capi.PTB_FLAG_COUNT_VISITS)
             inner = counted.inner_visits / len(rays)
@@ -115,8 +121,18 @@ def main():
             bytes_per_ray = 64 * inner + 48 * leaf + (28 + 1 if any_hit else 24 + 8)
             achieved = bytes_per_ray * len(rays) / (ms / 1e3) / 1e9
             result = (t_out >= 0).float().mean().item() if not any_hit else occ_out[: len(rays)].float().mean().item()
+            identical = None
+            if not any_hit:
+                # size-independent parity property: both closest-hit modes return the same primitive and distance for every ray
+                if mode_flags == 0:
+                    reference_result[name] = (t_out.clone(), prim_out.clone())
+                else:
+                    t_ref, prim_ref = reference_result[name]
+                    hit_mask = t_ref >= 0
+                    identical = bool(torch.equal(prim_ref, prim_out) and torch.equal(t_ref[hit_mask], t_out[hit_mask]) and bool((t_out[~hit_mask] < 0).all()))
             print(json.dumps({
-                "config": f"soup-{mi}Mi", "rays": name, "n_rays": len(rays), "mrays_per_s": len(rays) / ms / 1e3, "ms": ms,
+                "config": f"soup-{mi}Mi", "rays": name, "closest_hit": mode, "identical_to_reference_tree": identical,
+                "retraced": int(counted.closest_rays_retraced), "n_rays": len(rays), "mrays_per_s": len(rays) / ms / 1e3, "ms": ms,
                 "inner_fetches_per_ray": inner, "leaf_fetches_per_ray": leaf, "bytes_per_ray": bytes_per_ray,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak},
                 "hit_or_occluded_fraction": result, "bvh_depth": info.bvh_depth, "scene_mb": info.device_bytes / 2**20,
