@@ -463,7 +463,8 @@ def run_b200_arm(args):
                      "shadow_mrays_per_s": totals["shadow"] / max(totals["shadow_ms"], 1e-9) / 1e3, **count_detail},
         "cpu_baseline": cpu_baseline,
         "scene": {"prims": int(info.n_prims), "inner_nodes": int(info.n_inner_nodes), "bvh_depth": int(info.bvh_depth),
-                  "device_mb": info.device_bytes / 2**20, "build_s": info.build_seconds, "scene_ctor_s": t_build},
+                  "device_mb": info.device_bytes / 2**20, "build_s": info.build_seconds, "scene_ctor_s": t_build,
+                  "query_tree": "device LBVH" if info.query_tree_on_device else "host binned SAH", "query_tree_device_ms": info.query_tree_device_ms},
         "bounce_iterations_per_step": totals["iterations"] / args.steps,
         "closest_hit": ("reference-topology tree" if args.reference_closest else
                         f"certified SAH walk; {totals['retraced']} of {totals['closest']} closest-hit rays had no certificate and were re-traced on the reference tree"),

@@ -20,6 +20,9 @@ PTB_PRIM_TRIANGLE, PTB_PRIM_SPHERE, PTB_PRIM_NULL = 0, 1, 2
 PTB_BSDF_LAMBERT, PTB_BSDF_GLASS, PTB_BSDF_MIRROR = 0, 1, 2
 PTB_APERTURE_NONE, PTB_APERTURE_CIRCULAR, PTB_APERTURE_HEXAGONAL = 0, 1, 2
 PTB_RNG_COUNTER, PTB_RNG_REFERENCE_XORSHIFT = 0, 1
+PTB_BVH_REFERENCE = 0
+PTB_BVH_REFERENCE_GPU_QUERY_TREE = 1
+
 PTB_FLAG_DEVICE_IO = 0x1
 PTB_FLAG_ANY_HIT_SHADOWS = 0x2
 PTB_FLAG_SKIP_NULL_SHADOWS = 0x4
@@ -60,6 +63,9 @@ class SceneInfo(C.Structure):
         ("upload_seconds", C.c_double),
         ("root_low", C.c_float * 3),
         ("root_high", C.c_float * 3),
+        ("query_tree_on_device", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("query_tree_device_ms", C.c_double),
     ]
 
 
@@ -293,7 +299,7 @@ class Context:
 class Scene:
     """Device-resident scene (ptb_scene) built from POD arrays."""
 
-    def __init__(self, ctx, prims, materials, lights=None):
+    def __init__(self, ctx, prims, materials, lights=None, bvh_mode=0):
         self.ctx = ctx
         self.prims = np.ascontiguousarray(prims, dtype=PRIM_DTYPE)
         self.materials = np.ascontiguousarray(materials, dtype=MATERIAL_DTYPE)
@@ -305,7 +311,7 @@ class Scene:
         desc.n_materials = len(self.materials)
         desc.lights = self.lights.ctypes.data if len(self.lights) else None
         desc.n_lights = len(self.lights)
-        desc.bvh_mode = 0
+        desc.bvh_mode = bvh_mode
         self._h = C.c_void_p()
         check(load().ptb_scene_create(ctx.handle, C.byref(desc), C.byref(self._h)))
 

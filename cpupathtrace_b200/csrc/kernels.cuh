@@ -79,7 +79,6 @@ namespace ptb {
         uint32_t rng_xorshift;
         uint32_t any_hit_shadows;
         uint32_t skip_null_shadows;
-        uint32_t lanes; // member mask of the warp collectives: always 0xFFFFFFFF, passed at run time (see warpTrace in traverse.cuh)
         uint64_t seed;
     };
 
@@ -87,10 +86,10 @@ namespace ptb {
         return threadIdx.x & 31U;
     }
 
-    // Appends one element per participating lane with a single atomic per warp.
-    // Must be reached by all 32 lanes of the warp; `lanes` is the run-time full mask (RenderParams::lanes).
-    PTB_DEV uint32_t warpAppend(uint32_t lanes, uint32_t *counter, bool participate) {
-        const uint32_t mask = __ballot_sync(lanes, participate);
+    // Appends one element per participating lane with a single atomic per group of lanes that arrive together
+    // (normally the whole warp; see "Warp collectives and convergence" in traverse.cuh for why that is not assumed).
+    PTB_DEV uint32_t warpAppend(uint32_t *counter, bool participate) {
+        const uint32_t mask = __ballot_sync(__activemask(), participate);
         if(!participate) {
             return 0U;
         }
@@ -334,30 +333,34 @@ namespace ptb {
                 pool.shadow_count[i] = n_shadow;
             }
 
-            // queue the shadow rays: exclusive warp scan of the per-lane counts, one atomic per warp
-            uint32_t inclusive = n_shadow;
-            for(int offset = 1; offset < 32; offset <<= 1) {
-                const uint32_t below = __shfl_up_sync(params.lanes, inclusive, offset);
-                if(laneId() >= static_cast<uint32_t>(offset)) {
-                    inclusive += below;
-                }
+            // queue the shadow rays: exclusive scan of the per-lane counts over the lanes that arrive together (normally
+            // the whole warp), one atomic per group.  The scan is built from one ballot per bit of the count, which is
+            // cheaper than a shuffle ladder for counts this small and stays correct for any group of lanes.
+            const uint32_t present = __activemask();
+            const uint32_t below_me = (1U << laneId()) - 1U;
+            uint32_t exclusive = 0U;
+            uint32_t group_total = 0U;
+            for(uint32_t bit = 0U; (pool.shadow_stride >> bit) != 0U; bit++) {
+                const uint32_t votes = __ballot_sync(present, ((n_shadow >> bit) & 1U) != 0U);
+                exclusive += static_cast<uint32_t>(__popc(votes & below_me)) << bit;
+                group_total += static_cast<uint32_t>(__popc(votes)) << bit;
             }
-            const uint32_t warp_total = __shfl_sync(params.lanes, inclusive, 31);
-            if(warp_total != 0U) {
+            if(group_total != 0U) {
+                const uint32_t leader = static_cast<uint32_t>(__ffs(static_cast<int>(present))) - 1U;
                 uint32_t base = 0U;
-                if(laneId() == 0U) {
-                    base = atomicAdd(&counters[kCountShadow], warp_total);
+                if(laneId() == leader) {
+                    base = atomicAdd(&counters[kCountShadow], group_total);
                 }
-                base = __shfl_sync(params.lanes, base, 0) + (inclusive - n_shadow);
+                base = __shfl_sync(present, base, static_cast<int>(leader)) + exclusive;
                 for(uint32_t j = 0U; j < n_shadow; j++) {
                     shadow_queue[base + j] = shadow_base + j;
                 }
             }
 
             // statistics: one atomic per warp
-            const uint32_t hit_mask = __ballot_sync(params.lanes, active && hit_surface);
-            const uint32_t skipped = __reduce_add_sync(params.lanes, n_skipped);
-            if(laneId() == 0U) {
+            const uint32_t hit_mask = __ballot_sync(present, active && hit_surface);
+            const uint32_t skipped = __reduce_add_sync(present, n_skipped);
+            if(laneId() == static_cast<uint32_t>(__ffs(static_cast<int>(present))) - 1U) {
                 if(hit_mask != 0U) {
                     atomicAdd(&counters[kCountVertices], static_cast<uint32_t>(__popc(hit_mask)));
                 }
@@ -412,14 +415,15 @@ namespace ptb {
             }
 
             // path regeneration: a retired path's slot takes the next unstarted work item of the call
-            const uint32_t retired_mask = __ballot_sync(params.lanes, retired);
+            const uint32_t present = __activemask();
+            const uint32_t retired_mask = __ballot_sync(present, retired);
             if(retired_mask != 0U) {
                 const uint32_t leader = __ffs(retired_mask) - 1U;
                 unsigned long long base = 0ULL;
                 if(laneId() == leader) {
                     base = atomicAdd(work_cursor, static_cast<unsigned long long>(__popc(retired_mask)));
                 }
-                base = __shfl_sync(params.lanes, base, leader);
+                base = __shfl_sync(present, base, leader);
                 if(retired) {
                     const unsigned long long g = base + static_cast<unsigned long long>(__popc(retired_mask & ((1U << laneId()) - 1U)));
                     if(g < src.total) {
@@ -429,7 +433,7 @@ namespace ptb {
                 }
             }
 
-            const uint32_t at = warpAppend(params.lanes, &counters[next_slot], survives);
+            const uint32_t at = warpAppend(&counters[next_slot], survives);
             if(survives) {
                 next_queue[at] = i;
             }

@@ -5,6 +5,7 @@
 #include "bvh_build.h"
 #include "host_math.h"
 #include "kernels.cuh"
+#include "lbvh.cuh"
 #include "post_process.cuh"
 
 #include <cub/cub.cuh>
@@ -92,8 +93,8 @@ struct ptb_context {
     std::mutex mutex; // entry points serialise on their context: its workspace and stream are shared state
     int device = 0;
     int sm_count = 0;
-    ptb::VoteParams vote{12, 16, 2, 0xFFFFFFFFU};        // closest-hit kernels
-    ptb::VoteParams vote_shadow{16, 16, 2, 0xFFFFFFFFU}; // any-hit / shadow kernels (shorter rays: refill in larger batches)
+    ptb::VoteParams vote{12, 16, 2};        // closest-hit kernels
+    ptb::VoteParams vote_shadow{16, 16, 2}; // any-hit / shadow kernels (shorter rays: refill in larger batches)
     int trace_blocks_per_sm = 16;
     bool log_iterations = false; // PTB_LOG_ITERATIONS=1: one stderr line per bounce iteration
     cudaStream_t stream = nullptr;
@@ -229,6 +230,14 @@ namespace {
         return std::max<uint64_t>(64ULL << 20, plannableBytes(ctx) * 2ULL / 5ULL);
     }
 
+    // Pool capacity for a call of `total` work items: never more than half of them (above 2 Mi) so that path regeneration
+    // keeps the queues full for the first half of the call instead of starting everything in one wave that then thins
+    // out over dozens of iterations (8 GPUs x 66 M samples each: one wave 3.40, half 3.64 Gsamples/s).
+    uint32_t poolCapacity(uint64_t total, uint64_t limit) {
+        const uint64_t wanted = total <= (2ULL << 20) ? total : std::max<uint64_t>(2ULL << 20, (total + 1) / 2);
+        return static_cast<uint32_t>(std::min<uint64_t>(wanted, limit));
+    }
+
     int carvePool(ptb_context *ctx, uint32_t capacity, uint32_t shadow_stride, PathPool &pool) {
         const size_t n = capacity;
         const size_t ns = n * shadow_stride;
@@ -311,7 +320,6 @@ namespace {
         p.rng_xorshift = opts.rng_mode == PTB_RNG_REFERENCE_XORSHIFT ? 1U : 0U;
         p.any_hit_shadows = (opts.flags & PTB_FLAG_ANY_HIT_SHADOWS) != 0U ? 1U : 0U;
         p.skip_null_shadows = (opts.flags & PTB_FLAG_SKIP_NULL_SHADOWS) != 0U ? 1U : 0U;
-        p.lanes = 0xFFFFFFFFU;
         p.seed = opts.seed;
         return p;
     }
@@ -465,6 +473,112 @@ namespace {
         return PTB_OK;
     }
 
+    // Builds the query hierarchy on the device (lbvh.cuh).  `boxes` holds 6 floats per slot in the reference tree's leaf
+    // order.  On success `records` holds n - 1 inner records, the root is record 0 and `height` the number of inner
+    // levels (what the traversal stack must hold).
+    int buildQueryBvhOnDevice(ptb_context *ctx, const std::vector<float> &boxes, uint32_t n, const float root_lo[3], const float root_hi[3], Buffer &records,
+                              uint32_t &height, double &device_ms) {
+        height = 0;
+        device_ms = 0.0;
+        if(n < 2) {
+            return PTB_OK;
+        }
+        Buffer d_boxes, keys_a, keys_b, slots_a, slots_b, leaf_parent, node_parent, children, arrivals, node_box, node_height, node_count, sort_temp, d_height;
+        auto release_all = [&]() {
+            for(Buffer *b : {&d_boxes, &keys_a, &keys_b, &slots_a, &slots_b, &leaf_parent, &node_parent, &children, &arrivals, &node_box, &node_height, &node_count, &sort_temp,
+                             &d_height}) {
+                b->release();
+            }
+        };
+        const size_t inner = static_cast<size_t>(n) - 1;
+        int status = PTB_OK;
+        auto reserve = [&](Buffer &b, size_t bytes) {
+            if(status == PTB_OK) {
+                status = b.reserve(std::max<size_t>(bytes, 16));
+            }
+        };
+        reserve(d_boxes, boxes.size() * sizeof(float));
+        reserve(keys_a, n * sizeof(uint64_t));
+        reserve(keys_b, n * sizeof(uint64_t));
+        reserve(slots_a, n * sizeof(uint32_t));
+        reserve(slots_b, n * sizeof(uint32_t));
+        reserve(leaf_parent, n * sizeof(int32_t));
+        reserve(node_parent, inner * sizeof(int32_t));
+        reserve(children, inner * sizeof(int2));
+        reserve(arrivals, inner * sizeof(uint32_t));
+        reserve(node_box, inner * 6 * sizeof(float));
+        reserve(node_height, inner * sizeof(uint32_t));
+        reserve(node_count, inner * sizeof(uint32_t));
+        reserve(d_height, sizeof(uint32_t));
+        reserve(records, inner * sizeof(NodeRecord));
+        size_t temp_bytes = 0;
+        if(status == PTB_OK &&
+           cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), slots_a.as<uint32_t>(), slots_b.as<uint32_t>(), static_cast<int>(n), 0,
+                                           63, ctx->stream) != cudaSuccess) {
+            cudaGetLastError();
+            status = fail(PTB_ERR_CUDA, "buildQueryBvhOnDevice: radix sort sizing failed");
+        }
+        reserve(sort_temp, temp_bytes);
+        if(status != PTB_OK) {
+            release_all();
+            return status;
+        }
+
+        cudaEvent_t start = nullptr;
+        cudaEvent_t stop = nullptr;
+        cudaEventCreate(&start);
+        cudaEventCreate(&stop);
+        auto finish = [&](int st) {
+            cudaEventDestroy(start);
+            cudaEventDestroy(stop);
+            release_all();
+            return st;
+        };
+        if(cudaMemcpyAsync(d_boxes.ptr, boxes.data(), boxes.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            cudaGetLastError();
+            return finish(fail(PTB_ERR_CUDA, "buildQueryBvhOnDevice: box upload failed"));
+        }
+        cudaEventRecord(start, ctx->stream);
+
+        LbvhWorkspace w{};
+        w.boxes = d_boxes.as<float>();
+        w.keys = keys_b.as<uint64_t>();
+        w.slots = slots_b.as<uint32_t>();
+        w.leaf_parent = leaf_parent.as<int32_t>();
+        w.node_parent = node_parent.as<int32_t>();
+        w.children = children.as<int2>();
+        w.arrivals = arrivals.as<uint32_t>();
+        w.node_box = node_box.as<float>();
+        w.node_height = node_height.as<uint32_t>();
+        w.node_count = node_count.as<uint32_t>();
+        w.records = records.as<float4>();
+        w.n = n;
+        for(int c = 0; c < 3; c++) {
+            w.root_lo[c] = root_lo[c];
+            w.root_hi[c] = root_hi[c];
+        }
+        const unsigned leaf_grid = (n + 255U) / 256U;
+        mortonKernel<<<leaf_grid, 256, 0, ctx->stream>>>(w, keys_a.as<uint64_t>(), slots_a.as<uint32_t>());
+        cub::DeviceRadixSort::SortPairs(sort_temp.ptr, temp_bytes, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), slots_a.as<uint32_t>(), slots_b.as<uint32_t>(), static_cast<int>(n), 0, 63,
+                                        ctx->stream);
+        cudaMemsetAsync(arrivals.ptr, 0, inner * sizeof(uint32_t), ctx->stream);
+        cudaMemsetAsync(d_height.ptr, 0, sizeof(uint32_t), ctx->stream);
+        hierarchyKernel<<<(n - 1U + 255U) / 256U, 256, 0, ctx->stream>>>(w);
+        fitKernel<<<leaf_grid, 256, 0, ctx->stream>>>(w, d_height.as<uint32_t>());
+        cudaEventRecord(stop, ctx->stream);
+        uint32_t h = 0;
+        if(cudaMemcpyAsync(&h, d_height.ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+           cudaGetLastError() != cudaSuccess) {
+            cudaGetLastError();
+            return finish(fail(PTB_ERR_CUDA, "buildQueryBvhOnDevice: build kernels failed"));
+        }
+        float ms = 0.0F;
+        cudaEventElapsedTime(&ms, start, stop);
+        device_ms = ms;
+        height = h;
+        return finish(PTB_OK);
+    }
+
     int finishStats(ptb_context *ctx, bool count_visits, ptb_render_stats *stats) {
         if(stats == nullptr) {
             return PTB_OK;
@@ -613,7 +727,7 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
     if(desc->n_prims >= (1ULL << 31) - 1) {
         return fail(PTB_ERR_UNSUPPORTED, "ptb_scene_create: more than 2^31 - 2 primitives");
     }
-    if(desc->bvh_mode != PTB_BVH_REFERENCE) {
+    if(desc->bvh_mode != PTB_BVH_REFERENCE && desc->bvh_mode != PTB_BVH_REFERENCE_GPU_QUERY_TREE) {
         return fail(PTB_ERR_UNSUPPORTED, "ptb_scene_create: unknown bvh_mode");
     }
     for(uint64_t i = 0; i < desc->n_prims; i++) {
@@ -722,9 +836,36 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
         emis[3 * i + 1] = e1;
         emis[3 * i + 2] = e2;
     }
-    // occlusion hierarchy for any-hit (shadow) queries: SAH over the same primitives, leaf refs in reference slots
+    // query hierarchy for any-hit and certified closest-hit queries over the same primitives, leaf refs in reference
+    // slots: linear BVH built on the device, or (default) binned SAH built on the host
+    const bool want_query_tree = n > 1 && envLong("PTB_OCCLUSION_BVH", 1) != 0;
+    const bool gpu_query_tree = want_query_tree && (desc->bvh_mode == PTB_BVH_REFERENCE_GPU_QUERY_TREE || envLong("PTB_GPU_BVH", 0) != 0);
+    auto *scene = new(std::nothrow) ptb_scene();
+    if(scene == nullptr) {
+        return fail(PTB_ERR_OUT_OF_MEMORY, "ptb_scene_create: host allocation failed");
+    }
+    scene->ctx = ctx;
+    bool query_tree_on_device = false;
+    double query_tree_device_ms = 0.0;
+    if(gpu_query_tree) {
+        std::vector<float> boxes(6 * n);
+        for(uint64_t slot = 0; slot < n; slot++) {
+            primBounds(desc->prims[bvh.slot_to_prim[slot]], &boxes[6 * slot], &boxes[6 * slot + 3]);
+        }
+        uint32_t height = 0;
+        status = buildQueryBvhOnDevice(ctx, boxes, static_cast<uint32_t>(n), bvh.root_low, bvh.root_high, scene->occ_nodes, height, query_tree_device_ms);
+        if(status != PTB_OK) {
+            ptb_scene_destroy(scene);
+            return status;
+        }
+        // Morton ties can chain into a very deep tree (many coincident centres): then the host builder takes over
+        query_tree_on_device = height >= 1 && height <= static_cast<uint32_t>(kStackCapacity);
+        if(!query_tree_on_device) {
+            scene->occ_nodes.release();
+        }
+    }
     FlatBvh occlusion;
-    if(n > 1 && envLong("PTB_OCCLUSION_BVH", 1) != 0) {
+    if(want_query_tree && !query_tree_on_device) {
         std::vector<uint32_t> prim_to_slot(n);
         for(uint64_t slot = 0; slot < n; slot++) {
             prim_to_slot[bvh.slot_to_prim[slot]] = static_cast<uint32_t>(slot);
@@ -735,12 +876,6 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
         }
     }
     const double t1 = nowSeconds();
-
-    auto *scene = new(std::nothrow) ptb_scene();
-    if(scene == nullptr) {
-        return fail(PTB_ERR_OUT_OF_MEMORY, "ptb_scene_create: host allocation failed");
-    }
-    scene->ctx = ctx;
 
     auto upload = [&](Buffer &buffer, const void *src, size_t bytes) -> int {
         int st = buffer.reserve(std::max<size_t>(bytes, 16));
@@ -771,8 +906,8 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
 
     DeviceScene &d = scene->dev;
     d.nodes = scene->nodes.as<float4>();
-    d.occ_nodes = occlusion.nodes.empty() ? nullptr : scene->occ_nodes.as<float4>();
-    d.occ_root_ref = occlusion.root_ref;
+    d.occ_nodes = (query_tree_on_device || !occlusion.nodes.empty()) ? scene->occ_nodes.as<float4>() : nullptr;
+    d.occ_root_ref = query_tree_on_device ? 0 : occlusion.root_ref;
     d.geom = scene->geom.as<float4>();
     d.shade = scene->shade.as<float4>();
     d.mats = scene->mats.as<float4>();
@@ -802,6 +937,8 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
     info.device_bytes = scene->nodes.bytes + scene->occ_nodes.bytes + scene->geom.bytes + scene->shade.bytes + scene->mats.bytes + scene->lights.bytes + scene->emis.bytes +
                         scene->cdf.bytes + scene->slot_to_prim.bytes;
     info.build_seconds = t1 - t0;
+    info.query_tree_on_device = query_tree_on_device ? 1U : 0U;
+    info.query_tree_device_ms = query_tree_device_ms;
     info.upload_seconds = t2 - t1;
     for(int c = 0; c < 3; c++) {
         info.root_low[c] = bvh.root_low[c];
@@ -1015,7 +1152,7 @@ int ptb_render_samples(ptb_scene *scene, const ptb_camera *camera, const ptb_ren
     }
     const bool device_io = (opts->flags & PTB_FLAG_DEVICE_IO) != 0U;
     const bool count_visits = (opts->flags & PTB_FLAG_COUNT_VISITS) != 0U;
-    const uint32_t capacity = static_cast<uint32_t>(std::min<uint64_t>(n, poolLimit(ctx, scene->shadow_stride)));
+    const uint32_t capacity = poolCapacity(n, poolLimit(ctx, scene->shadow_stride));
 
     PathPool pool{};
     if((status = carvePool(ctx, capacity, scene->shadow_stride, pool)) != PTB_OK) {
@@ -1159,7 +1296,7 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
         PTB_CUDA(cudaMemcpyAsync(ctx->pixel_list.ptr, pixel_list.data(), n_pixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         PTB_CUDA(cudaStreamSynchronize(ctx->stream));
 
-        const uint32_t capacity = static_cast<uint32_t>(std::min<uint64_t>(total, pool_limit));
+        const uint32_t capacity = poolCapacity(total, pool_limit);
         PathPool pool{};
         if((status = carvePool(ctx, capacity, scene->shadow_stride, pool)) != PTB_OK) {
             return status;

@@ -142,7 +142,6 @@ namespace ptb {
         int refill;     // idle lanes that trigger a refill
         int leaf;       // parked lanes that trigger the primitive tests
         int leaf_burst; // consecutive leaves one lane may test per primitive-test phase
-        uint32_t lanes; // member mask of the warp collectives: always 0xFFFFFFFF, passed at run time (see warpTrace)
     };
 
     enum LaneStatus : uint32_t { kLaneIdle = 0U, kLaneInner = 1U, kLaneLeaf = 2U };
@@ -187,18 +186,21 @@ namespace ptb {
     // fetch(k, o, d, limit) loads ray k; commit(k, hit, certain) stores its result.  `cursor` is a zero-initialised device
     // counter shared by all warps of the launch; `count` the number of rays.
     //
-    // Every warp collective takes its member mask from a kernel parameter (vote.lanes = 0xFFFFFFFF) instead of the
-    // literal.  With the literal, ptxas (CUDA 12.9, sm_100a) drops the warp barrier in front of a vote wherever its
-    // convergence analysis says the lanes already met at a BSYNC.RECONVERGENT -- and on B200 they demonstrably do not
-    // always: a variant of this loop was caught executing its refill vote with part of the warp (64 times in one
-    // 60-launch render; the halves then disagreed on `exhausted` and the warp never terminated).  A mask the compiler
-    // cannot see through forces a real WARPSYNC / BRA.DIV in front of every collective (checked on the SASS by
-    // tests/test_abi.py).
+    // Warp collectives and convergence.  `__ballot_sync(0xFFFFFFFF, ...)` is only as good as the barrier in front of the
+    // VOTE instruction, and ptxas (CUDA 12.9, sm_100a) emits that barrier only where its convergence analysis thinks
+    // the warp may be split; elsewhere it trusts BSYNC.RECONVERGENT, drops an explicit __syncwarp() as redundant, and
+    // does the same for a member mask passed at run time.  On B200 the lanes demonstrably do not always arrive
+    // together: a variant of this loop was caught executing its refill vote with part of the warp (64 times in one
+    // 60-launch render); the halves then disagreed on `exhausted`, one half left and the other waited for an all-idle
+    // ballot that could no longer come.  The loop therefore does not ASSUME full-warp convergence anywhere: every
+    // group of collectives runs over `present = __activemask()`, the lanes that really are executing together, and
+    // every decision taken from a vote is a decision of that group -- it refills, parks, tests and terminates as a
+    // sub-warp of its own.  `exhausted` is re-agreed at every refill vote (groups can merge again), and a full-mask
+    // __syncwarp() at the top of the outer loop invites split groups to merge where the compiler keeps it.
     template<int MODE, bool COUNT, typename Fetch, typename Commit>
     PTB_DEV void warpTrace(const DeviceScene &s, VoteParams vote, uint32_t *cursor, uint32_t count, Fetch fetch, Commit commit, VisitCounters *counters) {
         constexpr bool ANY_HIT = MODE == kTraceAnyHit;
         constexpr bool CERTIFIED = MODE == kTraceCertified;
-        const uint32_t lanes = vote.lanes;
         const int kRefillVote = vote.refill;
         const int kLeafVote = vote.leaf;
         const uint32_t lane = threadIdx.x & 31U;
@@ -247,17 +249,21 @@ namespace ptb {
 
         for(;;) {
             // ---- (A) refill idle lanes once enough of them wait
-            const uint32_t idle_mask = __ballot_sync(lanes, status == kLaneIdle);
-            if(idle_mask == 0xFFFFFFFFU && exhausted) {
+            __syncwarp();
+            uint32_t present = __activemask();
+            exhausted = __any_sync(present, exhausted);
+            const uint32_t idle_mask = __ballot_sync(present, status == kLaneIdle);
+            if(idle_mask == present && exhausted) {
                 break;
             }
-            if(!exhausted && (__popc(idle_mask) >= kRefillVote || idle_mask == 0xFFFFFFFFU)) {
+            if(!exhausted && (__popc(idle_mask) >= kRefillVote || idle_mask == present)) {
                 const uint32_t wanted = static_cast<uint32_t>(__popc(idle_mask));
+                const uint32_t leader = static_cast<uint32_t>(__ffs(static_cast<int>(present))) - 1U;
                 uint32_t base = 0U;
-                if(lane == 0U) {
+                if(lane == leader) {
                     base = atomicAdd(cursor, wanted);
                 }
-                base = __shfl_sync(lanes, base, 0);
+                base = __shfl_sync(present, base, static_cast<int>(leader));
                 if(base + wanted >= count) {
                     exhausted = true;
                 }
@@ -297,7 +303,8 @@ namespace ptb {
 
             // ---- (B) descend: inner-node steps until enough lanes are parked at a leaf or waiting for a refill
             for(;;) {
-                const uint32_t inner_mask = __ballot_sync(lanes, status == kLaneInner);
+                present = __activemask();
+                const uint32_t inner_mask = __ballot_sync(present, status == kLaneInner);
                 if(inner_mask == 0U) {
                     break;
                 }
@@ -343,12 +350,13 @@ namespace ptb {
                         advance();
                     }
                 }
-                const uint32_t parked = __ballot_sync(lanes, status == kLaneLeaf);
+                present = __activemask();
+                const uint32_t parked = __ballot_sync(present, status == kLaneLeaf);
                 if(__popc(parked) >= kLeafVote) {
                     break;
                 }
                 if(!exhausted) {
-                    const uint32_t waiting = __ballot_sync(lanes, status == kLaneIdle);
+                    const uint32_t waiting = __ballot_sync(present, status == kLaneIdle);
                     if(__popc(waiting) >= kRefillVote) {
                         break;
                     }

@@ -88,7 +88,12 @@ typedef struct ptb_point_light {
 
 typedef enum ptb_bvh_mode {
     /* topology identical to impl::constructBVH (src/scene/scene.cpp:12-102): needed for bit-exact closest-hit parity */
-    PTB_BVH_REFERENCE = 0
+    PTB_BVH_REFERENCE = 0,
+    /* the same reference tree (it defines the answers), but the second hierarchy that any-hit and certified closest-hit
+     * queries walk is built on the GPU as a linear BVH (Morton sort + Karras hierarchy, csrc/lbvh.cuh) instead of the
+     * host's binned-SAH builder: milliseconds instead of tenths of a second, results unchanged (they do not depend on
+     * that tree's shape), somewhat more node fetches per ray.  $PTB_GPU_BVH=1 selects it for PTB_BVH_REFERENCE scenes. */
+    PTB_BVH_REFERENCE_GPU_QUERY_TREE = 1
 } ptb_bvh_mode;
 
 typedef struct ptb_scene_desc {
@@ -114,6 +119,9 @@ typedef struct ptb_scene_info {
     double upload_seconds;
     float root_low[3];
     float root_high[3];
+    uint32_t query_tree_on_device; /* 1: the any-hit / certified-closest hierarchy was built by the GPU builder */
+    uint32_t reserved;
+    double query_tree_device_ms;   /* CUDA-event time of that build (Morton codes, sort, hierarchy, box fit) */
 } ptb_scene_info;
 
 /* ------------------------------------------------------------------------------------------------ camera POD */

@@ -235,6 +235,53 @@ def test_unit_entries_match_oracle(ctx):
     scene.close()
 
 
+def test_device_built_query_tree_changes_nothing(ctx):
+    """with PTB_BVH_REFERENCE_GPU_QUERY_TREE the hierarchy walked by any-hit and certified closest-hit
+    queries is built on the GPU (Morton sort + Karras hierarchy, csrc/lbvh.cuh).  Results cannot depend on that tree's
+    shape: closest hits (a third aimed at shared vertices / edges), visibility and validation-mode samples must be
+    bit-identical to the scene with the host-built tree and to the golden vectors of the unmodified reference."""
+    for name in ("cornell_mesh", "mixed"):
+        g = load_golden("hits", name)
+        host = _scene(ctx, g)
+        dev = capi.Scene(ctx, g["prims"], g["materials"], g["lights"], bvh_mode=capi.PTB_BVH_REFERENCE_GPU_QUERY_TREE)
+        assert dev.info().query_tree_on_device == 1 and host.info().query_tree_on_device == 0
+        assert dev.info().query_tree_device_ms > 0
+        hit = g["t"] >= 0
+        for flags in (0, capi.PTB_FLAG_CERTIFIED_CLOSEST):
+            t, prim, _ = dev.intersect(g["rays"], flags=flags)
+            assert np.array_equal(prim, g["prim"]) and np.array_equal(t[hit], g["t"][hit]) and (t[~hit] < 0).all()
+        rays = random_rays(200000, seed=77, box=0.95)
+        t, prim, _ = host.intersect(rays)
+        t_d, prim_d, stats_d = dev.intersect(rays, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_COUNT_VISITS)
+        assert np.array_equal(prim_d, prim) and np.array_equal(t_d[t >= 0], t[t >= 0]) and stats_d.inner_visits > 0
+        rng = np.random.Generator(np.random.PCG64(78))
+        limit = np.where(t >= 0, t * rng.choice([0.5, 0.999, 1.0, 1.001, 2.0], size=len(t)).astype(np.float32), np.float32(5.0)).astype(np.float32)
+        shadow = np.concatenate([rays, limit[:, None]], axis=1)
+        assert np.array_equal(dev.occluded(shadow)[0], host.occluded(shadow)[0])
+        host.close()
+        dev.close()
+
+    g = load_golden("samples", "cornell_mesh")
+    w, h = (int(v) for v in g["size"])
+    dev = capi.Scene(ctx, g["prims"], g["materials"], g["lights"], bvh_mode=capi.PTB_BVH_REFERENCE_GPU_QUERY_TREE)
+    opts = capi.render_opts(w, h, 1, 1, float(g["epsilon"]), rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT,
+                            flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_ANY_HIT_SHADOWS | capi.PTB_FLAG_SKIP_NULL_SHADOWS)
+    rgba, _ = dev.render_samples(pod_camera(camera_kwargs(g["camera"])), opts, g["pixels"], g["seeds"])
+    assert np.array_equal(rgba, g["rgba"])
+    dev.close()
+
+    # degenerate input: every primitive at the same place (all Morton codes equal) still gives a usable tree
+    prims = np.repeat(g["prims"][:1], 300)
+    dev = capi.Scene(ctx, prims, g["materials"], g["lights"], bvh_mode=capi.PTB_BVH_REFERENCE_GPU_QUERY_TREE)
+    host = capi.Scene(ctx, prims, g["materials"], g["lights"])
+    rays = random_rays(5000, seed=79, box=1.0)
+    t, prim, _ = host.intersect(rays)
+    t_d, prim_d, _ = dev.intersect(rays, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST)
+    assert np.array_equal(prim_d, prim) and np.array_equal(t_d[t >= 0], t[t >= 0])
+    host.close()
+    dev.close()
+
+
 def test_sharded_renders_sum_to_the_full_frame(ctx):
     """Multi-GPU data path on one device: rendering the interleaved tile shards separately and adding the images gives
     exactly the unsharded frame (the counter-based generator is keyed per pixel and sample, not per launch)."""
