@@ -345,6 +345,30 @@ def test_full_size_scene_properties(ctx, ref):
     for i in idx:
         assert ctx.prim_intersect(prims[prim[i]], rays[i:i + 1])[0] == t[i]
 
+    # whole paths at full scene size: 1 M validation-mode samples traced with every result-neutral option switched on
+    # (certified SAH closest hits, any-hit shadows, zero-weight shadow rays skipped) equal the reference-order run bit for
+    # bit, and so do 300 k of them on a scene whose query tree was built by the GPU
+    kw = camera_kwargs(load_golden("samples", "cornell_mesh")["camera"])
+    kw["aspect_ratio"] = -16 / 9
+    camera = pod_camera(kw)
+    rng = np.random.Generator(np.random.PCG64(62))
+    n_samples = 1_000_000
+    pixels = np.stack([rng.integers(0, 1920, n_samples), rng.integers(0, 1080, n_samples)], axis=1).astype(np.int32)
+    seeds = rng.integers(1, 2**63 - 1, n_samples, dtype=np.int64).astype(np.uint64)
+    plain = capi.render_opts(1920, 1080, 1, 1, 1e-3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT)
+    fast = capi.render_opts(1920, 1080, 1, 1, 1e-3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT,
+                            flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_ANY_HIT_SHADOWS | capi.PTB_FLAG_SKIP_NULL_SHADOWS)
+    want, stats_plain = scene.render_samples(camera, plain, pixels, seeds)
+    got, stats_fast = scene.render_samples(camera, fast, pixels, seeds)
+    assert np.array_equal(got, want) and (want[:, 3] == 1).mean() > 0.99
+    assert stats_fast.closest_rays == stats_plain.closest_rays and stats_fast.path_vertices == stats_plain.path_vertices
+    assert stats_fast.shadow_rays + stats_fast.shadow_rays_skipped == stats_plain.shadow_rays
+    lbvh = capi.Scene(ctx, prims, mats, lights, bvh_mode=capi.PTB_BVH_REFERENCE_GPU_QUERY_TREE)
+    assert lbvh.info().query_tree_on_device == 1
+    got_lbvh, _ = lbvh.render_samples(camera, fast, pixels[:300_000], seeds[:300_000])
+    assert np.array_equal(got_lbvh, want[:300_000])
+    lbvh.close()
+
     # any-hit visibility just beyond / just before the closest hit
     n = 1_000_000
     beyond = np.concatenate([rays[:n], (t[:n] * np.float32(1.001) + np.float32(1e-4))[:, None]], axis=1)
