@@ -45,6 +45,7 @@ _PROTOTYPES = {
 _OPTIONAL = {
     "pth_scene_device_handle": (_P, [_P]),
     "pth_png_roundtrip": (C.c_long, [C.c_int, C.c_int, _P, _P]),
+    "pth_set_fast_queries": (None, [C.c_int, C.c_int, C.c_int]),
 }
 
 REF_PARITY = os.path.join(REPO_ROOT, "oracle", "_ref", "libpth_ref.so")
@@ -74,6 +75,10 @@ class Pth:
                 fn = getattr(self.lib, name)
                 fn.restype, fn.argtypes = restype, argtypes
         self.name = self.lib.pth_impl_name().decode()
+
+    def set_fast_queries(self, certified_closest, any_hit_shadows, skip_null_shadows):
+        """b200 build only: ptb::RenderControl's result-neutral query options for every later call of this process."""
+        self.lib.pth_set_fast_queries(int(certified_closest), int(any_hit_shadows), int(skip_null_shadows))
 
     # ---- camera
     def camera(self, origin, look_at, up, focal_length, height, aspect_ratio, aperture_width=0.0, aperture_height=0.0, sampler=0, hex_ratio=0.0,

@@ -479,6 +479,17 @@ extern "C" void *pth_scene_device_handle(void *scene) {
 #endif
 
 #ifdef PATHTRACE_B200
+// b200 build only: switches the result-neutral query options of ptb::RenderControl (certified closest hits on the SAH
+// hierarchy, any-hit shadow rays, zero-weight shadow rays skipped) for every later call of this process.
+extern "C" void pth_set_fast_queries(int certified_closest, int any_hit_shadows, int skip_null_shadows) {
+    ptb::RenderControl &control = ptb::renderControl();
+    control.certified_closest = certified_closest != 0;
+    control.any_hit_shadows = any_hit_shadows != 0;
+    control.skip_null_shadows = skip_null_shadows != 0;
+}
+#endif
+
+#ifdef PATHTRACE_B200
 #include <PathTrace/image/image_io.h>
 // b200 build only (the reference's image_io.cpp needs libpng, absent here): PNG encode -> decode round trip of an RGBA
 // float image through io::writeRGBImage / io::readRGBImage.  Returns the encoded size in bytes, or -1 on failure.

@@ -167,6 +167,34 @@ def test_sample_radiance_parity_point_light_pinhole(ref, b200):
     assert exact >= MIN_BIT_EXACT_FRACTION
 
 
+def test_fast_queries_through_the_cpp_api_change_nothing(ref, b200):
+    """The options bench.py switches on (ptb::RenderControl: certified closest hits on the SAH hierarchy, any-hit
+    shadow rays, zero-weight shadow rays skipped) must leave Scene::getIntersection results and every validation-mode
+    sample bit-identical to the unmodified reference, through the reference's own C++ API."""
+    b200.set_fast_queries(True, True, True)
+    try:
+        spec = scenes.cornell_demo(("obj", scenes.standin_obj(120, 80)))
+        builder = spec.replay(ref)
+        tris = builder.get_triangles()
+        builder.close()
+        tris = tris[~np.isnan(tris).any(axis=1)]
+        aim = np.concatenate([tris[:, :9].reshape(-1, 3), 0.5 * (tris[:, 0:3] + tris[:, 3:6])])
+        rng = np.random.Generator(np.random.PCG64(4))
+        rays = random_rays(60000, seed=12, box=1.1, aim=aim[rng.permutation(len(aim))][:20000])
+        sr, sg = _pair(spec, ref, b200)
+        assert _compare_hits(sr, sg, rays) > 0.3
+
+        cam = scenes.demo_camera(None, 64, 64)
+        bad, exact, want, got = _sample_parity(ref, b200, scenes.cornell_demo(("obj", scenes.standin_obj(60, 40))), cam, 64, 64, 20000, seed=24)
+        assert bad == 0 and exact == 1.0
+        cam = dict(origin=(0.0, 0.0, -1.9), look_at=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), focal_length=0.7, height=1.0, aspect_ratio=-1.5,
+                   aperture_width=0.04, aperture_height=0.03, sampler=2, hex_ratio=0.5, focal_plane_dist=2.0)
+        bad, exact, want, got = _sample_parity(ref, b200, scenes.mixed_materials(), cam, 96, 64, 20000, seed=25)
+        assert bad == 0 and exact == 1.0
+    finally:
+        b200.set_fast_queries(False, False, False)
+
+
 def test_render_kats(ref, b200):
     """reference test/render_test.cpp: empty scene -> (0,0,0,0); lit sphere: corner exactly 0, centre alpha > 0."""
     cam = dict(origin=(0.0, 0.0, 0.0), look_at=(0.0, 0.0, 1.0), up=(0.0, 1.0, 0.0), focal_length=1.0, height=1.0, aspect_ratio=1.0)
