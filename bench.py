@@ -324,15 +324,18 @@ def run_b200_arm(args):
     leaf_per_ray = sum_over_ranks(float(cstats.leaf_visits)) / max(count_rays, 1.0)
     bytes_per_ray = INNER_BYTES * inner_per_ray + LEAF_BYTES * leaf_per_ray + RAY_RECORD_BYTES
 
-    # ---- warm-up
+    # ---- warm-up.  The clock sampler (one nvidia-smi process polling every 200 ms) is started here rather than at the
+    # first timed step: its NVML start-up takes driver locks for a few hundred milliseconds, which showed up as idle gaps
+    # between launches of the first timed step; the samples it reports cover the warm-up and the timed steps, all under
+    # the same load.
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         flush.zero_()
         barrier()
         device_step(1000 + i)
 
     # ---- timed steps, device-resident
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     step_ms, wall_ms = [], []
     totals = {"samples": 0, "closest": 0, "shadow": 0, "skipped": 0, "vertices": 0, "launches": 0, "retraced": 0, "trace_ms": 0.0, "shade_ms": 0.0, "iterations": 0,
               "shadow_ms": 0.0}

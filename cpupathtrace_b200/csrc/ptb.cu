@@ -86,6 +86,7 @@ namespace {
     };
 
     constexpr int kEventPairs = 2048;
+    constexpr int kMaxIterationsPerSync = 16;
 
 }
 
@@ -93,10 +94,11 @@ struct ptb_context {
     std::mutex mutex; // entry points serialise on their context: its workspace and stream are shared state
     int device = 0;
     int sm_count = 0;
-    ptb::VoteParams vote{12, 16, 2};        // closest-hit kernels
-    ptb::VoteParams vote_shadow{16, 16, 2}; // any-hit / shadow kernels (shorter rays: refill in larger batches)
+    ptb::VoteParams vote{12, 12, 2, 4};        // closest-hit kernels
+    ptb::VoteParams vote_shadow{16, 12, 2, 4}; // any-hit / shadow kernels (shorter rays: refill in larger batches)
     int trace_blocks_per_sm = 16;
     bool log_iterations = false; // PTB_LOG_ITERATIONS=1: one stderr line per bounce iteration
+    int iterations_per_sync = 4; // bounce iterations launched between two host synchronisations (PTB_ITERATIONS_PER_SYNC)
     cudaStream_t stream = nullptr;
 
     // wavefront workspace
@@ -110,6 +112,7 @@ struct ptb_context {
     Buffer work_cursor;
     Buffer samples;
     Buffer pixel_list;
+    long long pixel_list_key[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1}; // what the device-side pixel list currently holds
     Buffer io_a; // staging for host<->device bulk arrays
     Buffer io_b;
     Buffer io_c;
@@ -361,88 +364,107 @@ namespace {
         int cur = 0;
         uint32_t n_cur = first_wave;
 
+        // Bounce iterations are launched in batches without a host round trip in between: queue lengths live in device
+        // memory, the ping-pong order is known in advance, and an iteration on an empty queue is five launches that return
+        // at once.  The host reads the counters of every iteration of the batch afterwards (statistics, termination); a
+        // descheduled host thread then delays one batch boundary instead of every iteration.  Queues never grow, so the
+        // length known at the start of a batch bounds the grids of all its iterations.
+        const int batch = ctx->iterations_per_sync;
         while(n_cur > 0U) {
-            const int nxt = cur ^ 1;
-            // zero: next queue length; shadow queue length, both fetch cursors and the per-iteration statistics (slots 2..6)
-            PTB_CUDA(cudaMemsetAsync(counters + nxt, 0, sizeof(uint32_t), ctx->stream));
-            PTB_CUDA(cudaMemsetAsync(counters + kCountShadow, 0, kPerIterationCounters * sizeof(uint32_t), ctx->stream));
+            int launched = 0;
+            for(; launched < batch; launched++) {
+                const int nxt = cur ^ 1;
+                // zero: next queue length; shadow queue length, both fetch cursors and the per-iteration statistics (slots 2..6)
+                PTB_CUDA(cudaMemsetAsync(counters + nxt, 0, sizeof(uint32_t), ctx->stream));
+                PTB_CUDA(cudaMemsetAsync(counters + kCountShadow, 0, kPerIterationCounters * sizeof(uint32_t), ctx->stream));
 
-            const int flat_grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_cur) + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 32))));
-            {
-                LaunchTimer timer(ctx, 0);
-                if(certified) {
-                    // SAH walk with certificate, then the handed-back rays on the reference tree (usually a handful)
-                    if(count_visits) {
-                        traceClosestKernel<kTraceCertified, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur,
-                                                                                                         kCountFetchClosest, redo_queue, visits);
-                        traceClosestKernel<kTraceClosest, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, redo_queue, counters, kCountRedo,
-                                                                                                          kCountFetchRedo, redo_queue, visits);
+                const int flat_grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_cur) + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 32))));
+                {
+                    LaunchTimer timer(ctx, 0);
+                    if(certified) {
+                        // SAH walk with certificate, then the handed-back rays on the reference tree (usually a handful)
+                        if(count_visits) {
+                            traceClosestKernel<kTraceCertified, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur,
+                                                                                                             kCountFetchClosest, redo_queue, visits);
+                            traceClosestKernel<kTraceClosest, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, redo_queue, counters, kCountRedo,
+                                                                                                              kCountFetchRedo, redo_queue, visits);
+                        }
+                        else {
+                            traceClosestKernel<kTraceCertified, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur,
+                                                                                                              kCountFetchClosest, redo_queue, visits);
+                            traceClosestKernel<kTraceClosest, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, redo_queue, counters, kCountRedo,
+                                                                                                               kCountFetchRedo, redo_queue, visits);
+                        }
+                    }
+                    else if(count_visits) {
+                        traceClosestKernel<kTraceClosest, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur, kCountFetchClosest,
+                                                                                                       redo_queue, visits);
                     }
                     else {
-                        traceClosestKernel<kTraceCertified, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur,
-                                                                                                          kCountFetchClosest, redo_queue, visits);
-                        traceClosestKernel<kTraceClosest, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, redo_queue, counters, kCountRedo,
-                                                                                                           kCountFetchRedo, redo_queue, visits);
+                        traceClosestKernel<kTraceClosest, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur, kCountFetchClosest,
+                                                                                                        redo_queue, visits);
                     }
                 }
-                else if(count_visits) {
-                    traceClosestKernel<kTraceClosest, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur, kCountFetchClosest,
-                                                                                                   redo_queue, visits);
+                {
+                    LaunchTimer timer(ctx, 1);
+                    if(params.rng_xorshift != 0U) {
+                        shadeKernel<ReferenceRng><<<flat_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, cur, shadow_queue);
+                    }
+                    else {
+                        shadeKernel<CounterRng><<<flat_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, cur, shadow_queue);
+                    }
                 }
-                else {
-                    traceClosestKernel<kTraceClosest, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur, kCountFetchClosest,
-                                                                                                    redo_queue, visits);
+                {
+                    LaunchTimer timer(ctx, 2);
+                    if(count_visits) {
+                        traceShadowKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, pool, shadow_queue, counters, params.any_hit_shadows, visits + 1);
+                    }
+                    else {
+                        traceShadowKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, pool, shadow_queue, counters, params.any_hit_shadows, visits + 1);
+                    }
                 }
+                {
+                    LaunchTimer timer(ctx, 1);
+                    if(params.rng_xorshift != 0U) {
+                        accumulateKernel<ReferenceRng><<<flat_grid, kBlock, 0, ctx->stream>>>(pool, params, src, queues[cur], counters, cur, queues[nxt], nxt,
+                                                                                            samples, work_cursor);
+                    }
+                    else {
+                        accumulateKernel<CounterRng><<<flat_grid, kBlock, 0, ctx->stream>>>(pool, params, src, queues[cur], counters, cur, queues[nxt], nxt, samples,
+                                                                                          work_cursor);
+                    }
+                }
+                PTB_CUDA(cudaMemcpyAsync(ctx->host_counters + launched * kCounterSlots, counters, kCounterSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                cur = nxt;
             }
-            {
-                LaunchTimer timer(ctx, 1);
-                if(params.rng_xorshift != 0U) {
-                    shadeKernel<ReferenceRng><<<flat_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, cur, shadow_queue);
-                }
-                else {
-                    shadeKernel<CounterRng><<<flat_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, cur, shadow_queue);
-                }
-            }
-            {
-                LaunchTimer timer(ctx, 2);
-                if(count_visits) {
-                    traceShadowKernel<true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, pool, shadow_queue, counters, params.any_hit_shadows, visits + 1);
-                }
-                else {
-                    traceShadowKernel<false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, pool, shadow_queue, counters, params.any_hit_shadows, visits + 1);
-                }
-            }
-            {
-                LaunchTimer timer(ctx, 1);
-                if(params.rng_xorshift != 0U) {
-                    accumulateKernel<ReferenceRng><<<flat_grid, kBlock, 0, ctx->stream>>>(pool, params, src, queues[cur], counters, cur, queues[nxt], nxt,
-                                                                                        samples, work_cursor);
-                }
-                else {
-                    accumulateKernel<CounterRng><<<flat_grid, kBlock, 0, ctx->stream>>>(pool, params, src, queues[cur], counters, cur, queues[nxt], nxt, samples,
-                                                                                      work_cursor);
-                }
-            }
-            PTB_CUDA(cudaMemcpyAsync(ctx->host_counters, counters, kCounterSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
             PTB_CUDA(cudaStreamSynchronize(ctx->stream));
             PTB_CUDA(cudaGetLastError());
 
-            if(stats != nullptr) {
-                stats->closest_rays += n_cur;
-                stats->shadow_rays += ctx->host_counters[kCountShadow];
-                stats->shadow_rays_skipped += ctx->host_counters[kCountSkippedShadows];
-                stats->closest_rays_retraced += ctx->host_counters[kCountRedo];
-                stats->path_vertices += ctx->host_counters[kCountVertices];
-                stats->bounce_iterations += 1;
-                stats->kernel_launches += certified ? 5 : 4;
+            // `cur` is now the queue the last launched iteration wrote; walk the batch in launch order
+            int slot_in = (launched % 2 == 0) ? cur : (cur ^ 1);
+            uint32_t n_in = n_cur;
+            for(int j = 0; j < launched; j++) {
+                const uint32_t *hc = ctx->host_counters + j * kCounterSlots;
+                const int slot_out = slot_in ^ 1;
+                if(n_in > 0U) {
+                    if(stats != nullptr) {
+                        stats->closest_rays += n_in;
+                        stats->shadow_rays += hc[kCountShadow];
+                        stats->shadow_rays_skipped += hc[kCountSkippedShadows];
+                        stats->closest_rays_retraced += hc[kCountRedo];
+                        stats->path_vertices += hc[kCountVertices];
+                        stats->bounce_iterations += 1;
+                        stats->kernel_launches += certified ? 5 : 4;
+                    }
+                    if(ctx->log_iterations) {
+                        std::fprintf(stderr, "[ptb] bounce iteration: %u paths, %u shadow rays, %u retraced, %u continue\n", n_in, hc[kCountShadow], hc[kCountRedo], hc[slot_out]);
+                    }
+                }
+                n_in = hc[slot_out];
+                slot_in = slot_out;
             }
             collectTimers(ctx, stats);
-            if(ctx->log_iterations) {
-                std::fprintf(stderr, "[ptb] bounce iteration: %u paths, %u shadow rays, %u retraced, %u continue\n", n_cur, ctx->host_counters[kCountShadow],
-                             ctx->host_counters[kCountRedo], ctx->host_counters[nxt]);
-            }
-            n_cur = ctx->host_counters[nxt];
-            cur = nxt;
+            n_cur = n_in;
         }
         return PTB_OK;
     }
@@ -649,7 +671,7 @@ int ptb_context_create(int device, ptb_context **out) {
         return fail(PTB_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100-class; the kernels are built for sm_100a only");
     }
     PTB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    PTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->host_counters), kCounterSlots * sizeof(uint32_t)));
+    PTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->host_counters), kMaxIterationsPerSync * kCounterSlots * sizeof(uint32_t)));
     for(auto &pair : ctx->events) {
         PTB_CUDA(cudaEventCreate(&pair[0]));
         PTB_CUDA(cudaEventCreate(&pair[1]));
@@ -659,13 +681,15 @@ int ptb_context_create(int device, ptb_context **out) {
     ctx->events_ready = envLong("PTB_PROFILE", 1) != 0;
     // tuned on the bench scene with the 128 Mi-path pool (with the earlier 4 Mi pool the drain phases dominated and smaller votes won)
     ctx->vote.refill = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_REFILL_VOTE", 12))));
-    ctx->vote.leaf = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_LEAF_VOTE", 16))));
+    ctx->vote.leaf = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_LEAF_VOTE", 12))));
     ctx->vote.leaf_burst = static_cast<int>(std::min(8L, std::max(1L, envLong("PTB_LEAF_BURST", 2))));
+    ctx->vote.inner_burst = static_cast<int>(std::min(8L, std::max(1L, envLong("PTB_INNER_BURST", 4))));
     ctx->vote_shadow = ctx->vote;
     ctx->vote_shadow.refill = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_SHADOW_REFILL_VOTE", envLong("PTB_REFILL_VOTE", 16)))));
-    ctx->vote_shadow.leaf = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_SHADOW_LEAF_VOTE", envLong("PTB_LEAF_VOTE", 16)))));
+    ctx->vote_shadow.leaf = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_SHADOW_LEAF_VOTE", envLong("PTB_LEAF_VOTE", 12)))));
     ctx->trace_blocks_per_sm = static_cast<int>(std::max(1L, envLong("PTB_TRACE_BLOCKS_PER_SM", 16)));
     ctx->log_iterations = envLong("PTB_LOG_ITERATIONS", 0) != 0;
+    ctx->iterations_per_sync = static_cast<int>(std::min<long>(kMaxIterationsPerSync, std::max(1L, envLong("PTB_ITERATIONS_PER_SYNC", 4))));
     *out = ctx;
     return PTB_OK;
 }
@@ -1270,31 +1294,45 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
     std::vector<uint32_t> pixel_list;
     for(size_t group_begin = 0; group_begin < owned.size() && spp > 0; group_begin += tiles_per_group) {
         const size_t group_end = std::min<size_t>(owned.size(), group_begin + tiles_per_group);
-        pixel_list.clear();
+        // pixels of the group's tiles in tile order; frames rendered repeatedly reuse the list already on the device
+        const long long key[9] = {x0, y0, w, h, tile, shard_index, shard_count, static_cast<long long>(group_begin), static_cast<long long>(group_end)};
+        const bool list_cached = std::equal(key, key + 9, ctx->pixel_list_key);
+        uint64_t n_group_pixels = 0;
         for(size_t k = group_begin; k < group_end; k++) {
             const int t = owned[k];
             const int tx0 = (t % tiles_x) * tile;
             const int ty0 = (t / tiles_x) * tile;
-            const int tx1 = std::min(tx0 + tile, w);
-            const int ty1 = std::min(ty0 + tile, h);
-            for(int y = ty0; y < ty1; y++) {
-                for(int x = tx0; x < tx1; x++) {
-                    pixel_list.push_back(static_cast<uint32_t>(x0 + x) | (static_cast<uint32_t>(y0 + y) << 16));
-                }
-            }
+            n_group_pixels += static_cast<uint64_t>(std::min(tx0 + tile, w) - tx0) * static_cast<uint64_t>(std::min(ty0 + tile, h) - ty0);
         }
-        const uint32_t n_pixels = static_cast<uint32_t>(pixel_list.size());
+        const uint32_t n_pixels = static_cast<uint32_t>(n_group_pixels);
         if(n_pixels == 0U) {
             continue;
         }
         const uint64_t total = static_cast<uint64_t>(n_pixels) * spp;
-
         if((status = ctx->pixel_list.reserve(n_pixels * sizeof(uint32_t))) != PTB_OK || (status = ctx->samples.reserve(total * sizeof(float4))) != PTB_OK) {
             return status;
         }
-        // the list is consumed by kernels of this group only; a pageable copy on the stream is ordered before them
-        PTB_CUDA(cudaMemcpyAsync(ctx->pixel_list.ptr, pixel_list.data(), n_pixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-        PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if(!list_cached) {
+            pixel_list.clear();
+            pixel_list.reserve(n_pixels);
+            for(size_t k = group_begin; k < group_end; k++) {
+                const int t = owned[k];
+                const int tx0 = (t % tiles_x) * tile;
+                const int ty0 = (t / tiles_x) * tile;
+                const int tx1 = std::min(tx0 + tile, w);
+                const int ty1 = std::min(ty0 + tile, h);
+                for(int y = ty0; y < ty1; y++) {
+                    for(int x = tx0; x < tx1; x++) {
+                        pixel_list.push_back(static_cast<uint32_t>(x0 + x) | (static_cast<uint32_t>(y0 + y) << 16));
+                    }
+                }
+            }
+            std::fill(ctx->pixel_list_key, ctx->pixel_list_key + 9, -1LL);
+            // the list is consumed by kernels of this group only; a pageable copy on the stream is ordered before them
+            PTB_CUDA(cudaMemcpyAsync(ctx->pixel_list.ptr, pixel_list.data(), n_pixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+            PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+            std::copy(key, key + 9, ctx->pixel_list_key);
+        }
 
         const uint32_t capacity = poolCapacity(total, pool_limit);
         PathPool pool{};

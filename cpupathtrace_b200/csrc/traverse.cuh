@@ -132,7 +132,7 @@ namespace ptb {
     //   * a lane that has finished its ray does not wait for the slowest ray of a 32-ray batch: finished lanes are
     //     refilled from the device-side queue cursor as soon as kRefillVote of them are idle (one atomic per refill,
     //     claimed by ballot/popc/shfl);
-    //   * a lane that has arrived at a leaf parks until vote.leaf (default 16) lanes are parked (or no lane has inner work left),
+    //   * a lane that has arrived at a leaf parks until vote.leaf (default 12) lanes are parked (or no lane has inner work left),
     //     then the parked lanes run the primitive test together; inner-node steps run for all unparked lanes.
     //
     // Measured with ncu before this change (profiles/r01_ncu_trace_baseline.md): 6.3 (closest) and 3.4 (shadow)
@@ -142,6 +142,7 @@ namespace ptb {
         int refill;     // idle lanes that trigger a refill
         int leaf;       // parked lanes that trigger the primitive tests
         int leaf_burst; // consecutive leaves one lane may test per primitive-test phase
+        int inner_burst; // inner-node steps between two votes of the descend loop
     };
 
     enum LaneStatus : uint32_t { kLaneIdle = 0U, kLaneInner = 1U, kLaneLeaf = 2U };
@@ -247,6 +248,50 @@ namespace ptb {
             status = kLaneIdle;
         };
 
+        // one inner-node step of a lane whose `node` is an inner record
+        auto innerStep = [&]() {
+            const float4 *rec = s.nodes + 4 * static_cast<size_t>(node);
+            float4 n0;
+            float4 n1;
+            float4 n2;
+            float4 n3;
+            ld256(rec, n0, n1);
+            ld256(rec + 2, n2, n3);
+            if(COUNT) {
+                n_inner++;
+            }
+            float lt;
+            float rt;
+            const float bound = CERTIFIED ? prune_t : best_t;
+            const bool visit_left = slabVisit(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, bound, lt);
+            const bool visit_right = slabVisit(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, bound, rt);
+            const int32_t left = __float_as_int(n3.x);
+            const int32_t right = __float_as_int(n3.y);
+            if(visit_left && visit_right) {
+                // nearer child first, the right one on ties (scene.cpp:122-123); the other is deferred
+                const bool left_first = lt < rt;
+                // (an L2 prefetch of the deferred sibling was measured and rejected: -9 % on the bench scene, -10 % on
+                // the 16 Mi-triangle soup)
+                stack[sp] = make_uint2(static_cast<uint32_t>(left_first ? right : left), __float_as_uint(left_first ? rt : lt));
+                sp++;
+                node = left_first ? left : right;
+                if(CERTIFIED) {
+                    leaf_entry = left_first ? lt : rt;
+                }
+                status = node >= 0 ? kLaneInner : kLaneLeaf;
+            }
+            else if(visit_left || visit_right) {
+                node = visit_left ? left : right;
+                if(CERTIFIED) {
+                    leaf_entry = visit_left ? lt : rt;
+                }
+                status = node >= 0 ? kLaneInner : kLaneLeaf;
+            }
+            else {
+                advance();
+            }
+        };
+
         for(;;) {
             // ---- (A) refill idle lanes once enough of them wait
             __syncwarp();
@@ -308,46 +353,11 @@ namespace ptb {
                 if(inner_mask == 0U) {
                     break;
                 }
-                if(status == kLaneInner) {
-                    const float4 *rec = s.nodes + 4 * static_cast<size_t>(node);
-                    float4 n0;
-                    float4 n1;
-                    float4 n2;
-                    float4 n3;
-                    ld256(rec, n0, n1);
-                    ld256(rec + 2, n2, n3);
-                    if(COUNT) {
-                        n_inner++;
-                    }
-                    float lt;
-                    float rt;
-                    const float bound = CERTIFIED ? prune_t : best_t;
-                    const bool visit_left = slabVisit(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, bound, lt);
-                    const bool visit_right = slabVisit(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, bound, rt);
-                    const int32_t left = __float_as_int(n3.x);
-                    const int32_t right = __float_as_int(n3.y);
-                    if(visit_left && visit_right) {
-                        // nearer child first, the right one on ties (scene.cpp:122-123); the other is deferred
-                        const bool left_first = lt < rt;
-                        // (an L2 prefetch of the deferred sibling was measured and rejected: -9 % on the bench scene, -10 % on
-                        // the 16 Mi-triangle soup)
-                        stack[sp] = make_uint2(static_cast<uint32_t>(left_first ? right : left), __float_as_uint(left_first ? rt : lt));
-                        sp++;
-                        node = left_first ? left : right;
-                        if(CERTIFIED) {
-                            leaf_entry = left_first ? lt : rt;
-                        }
-                        status = node >= 0 ? kLaneInner : kLaneLeaf;
-                    }
-                    else if(visit_left || visit_right) {
-                        node = visit_left ? left : right;
-                        if(CERTIFIED) {
-                            leaf_entry = visit_left ? lt : rt;
-                        }
-                        status = node >= 0 ? kLaneInner : kLaneLeaf;
-                    }
-                    else {
-                        advance();
+                // up to vote.inner_burst steps between two votes: a lane that leaves the Inner state early sits the rest of the
+                // burst out, which costs less than voting after every step
+                for(int step = 0; step < vote.inner_burst; step++) {
+                    if(status == kLaneInner) {
+                        innerStep();
                     }
                 }
                 present = __activemask();
