@@ -440,8 +440,11 @@ namespace ptb {
 
     // One iteration of the getSample loop for a path whose ray hit `slot` at distance t (worker.cpp:50-138).
     // `shadow(candidate, is_null)` is invoked per next-event-estimation sample, in light order; is_null marks the
-    // samples whose BSDF returns pd 0 for synthetic rays (Glass, Mirror): the reference traces their shadow ray and
-    // discards the result (worker.cpp:84-92), so they carry geometry but no contribution.
+    // samples that cannot change the radiance whatever their visibility: those whose BSDF returns pd 0 for synthetic
+    // rays (Glass, Mirror: the reference traces their shadow ray and discards the result, worker.cpp:84-92), and those
+    // whose contribution is +-0 in all three channels (a Lambertian surface facing away from the light has shading
+    // factor max(n.l, 0) = 0, propagation.cpp:104-108; adding +-0 to the non-negative radiance sum leaves every bit of
+    // it unchanged).  They carry geometry but no weight.
     // Returns true when the path continues with the new ray in p.
     template<typename RNG, typename Shadow>
     PTB_DEV bool shadeVertex(const DeviceScene &s, float epsilon, int max_depth, PathRegs<RNG> &p, float t, uint32_t slot, Shadow shadow) {
@@ -478,7 +481,7 @@ namespace ptb {
             if(shadow_ray_pd > 0.0F) {
                 const V4 combined = (base * shading_factor) * p.throughput;
                 c.contribution = combined / static_cast<float>(p.divisor * p.bounce_pd * ls.pd * shadow_ray_pd);
-                shadow(c, false);
+                shadow(c, c.contribution.x == 0.0F && c.contribution.y == 0.0F && c.contribution.z == 0.0F);
             }
             else {
                 c.contribution = V4{0.0F, 0.0F, 0.0F, 0.0F};

@@ -164,8 +164,9 @@ typedef enum ptb_rng_mode {
 #define PTB_FLAG_DEVICE_IO 0x1u      /* bulk in/out arrays are device pointers                                          */
 #define PTB_FLAG_ANY_HIT_SHADOWS 0x2u /* shadow rays stop at the first occluder (result-identical up to ulp-level box/   */
                                       /* primitive disagreement) instead of the reference's full closest-hit query       */
-#define PTB_FLAG_SKIP_NULL_SHADOWS 0x4u /* do not trace shadow rays whose BSDF returns pd 0 for synthetic rays (Glass,   */
-                                        /* Mirror: worker.cpp:84-92 traces them and discards the result)                  */
+#define PTB_FLAG_SKIP_NULL_SHADOWS 0x4u /* do not trace shadow rays that cannot change the radiance: BSDF pd 0 for       */
+                                        /* synthetic rays (Glass, Mirror: worker.cpp:84-92 traces them and discards the   */
+                                        /* result) or a contribution of +-0 in all channels (surface facing away)         */
 #define PTB_FLAG_COUNT_VISITS 0x8u   /* count BVH node / primitive fetches (slower; feeds the bytes-per-ray figure)      */
 #define PTB_FLAG_CERTIFIED_CLOSEST 0x10u /* closest-hit queries walk the SAH hierarchy and keep the result only when it    */
                                      /* carries a certificate that Scene::getIntersection returns the same primitive in  */
