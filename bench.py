@@ -287,11 +287,16 @@ def run_b200_arm(args):
         stop.synchronize()
         return start.elapsed_time(stop)
 
+    rank_detail = {"render_ms": [], "reduce_ms": []}
+
     def device_step(seed):
         stats = capi.RenderStats()
         o = opts(args.spp, capi.PTB_FLAG_DEVICE_IO, seed)
         capi.check(lib.ptb_render(handle, C.byref(camera), C.byref(o), 0, 0, args.width, args.height, C.c_void_p(image.data_ptr()), C.byref(stats)))
-        ms = stats.device_ms_total + reduce_image()
+        reduce_ms = reduce_image()
+        rank_detail["render_ms"].append(stats.device_ms_total)
+        rank_detail["reduce_ms"].append(reduce_ms)
+        ms = stats.device_ms_total + reduce_ms
         return ms, stats
 
     def max_over_ranks(value):
@@ -337,6 +342,8 @@ def run_b200_arm(args):
 
     # ---- timed steps, device-resident
     step_ms, wall_ms = [], []
+    rank_detail["render_ms"].clear()
+    rank_detail["reduce_ms"].clear()
     totals = {"samples": 0, "closest": 0, "shadow": 0, "skipped": 0, "vertices": 0, "launches": 0, "retraced": 0, "trace_ms": 0.0, "shade_ms": 0.0, "iterations": 0,
               "shadow_ms": 0.0}
     for i in range(args.steps):
@@ -361,6 +368,14 @@ def run_b200_arm(args):
         totals["shadow_ms"] += stats.device_ms_trace_shadow
         totals["iterations"] += stats.bounce_iterations
     clocks = sampler.stop()
+    # this rank's own render time (its tiles) and the time it spent in the image reduce, which includes waiting for the
+    # slowest rank; gathered so that imbalance between ranks is visible in the report
+    per_rank = None
+    if dist is not None:
+        mine = torch.tensor([float(np.mean(rank_detail["render_ms"])), float(np.mean(rank_detail["reduce_ms"]))], dtype=torch.float64, device="cuda")
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        per_rank = {"render_ms": [round(float(g[0]), 2) for g in gathered], "reduce_ms_incl_wait": [round(float(g[1]), 2) for g in gathered]}
 
     job_samples = sum_over_ranks(float(totals["samples"]))
     job_rays = sum_over_ranks(float(totals["closest"] + totals["shadow"]))
@@ -469,6 +484,7 @@ def run_b200_arm(args):
                   "device_mb": info.device_bytes / 2**20, "build_s": info.build_seconds, "scene_ctor_s": t_build,
                   "query_tree": "device LBVH" if info.query_tree_on_device else "host binned SAH", "query_tree_device_ms": info.query_tree_device_ms},
         "bounce_iterations_per_step": totals["iterations"] / args.steps,
+        "per_rank": per_rank,
         "closest_hit": ("reference-topology tree" if args.reference_closest else
                         f"certified SAH walk; {totals['retraced']} of {totals['closest']} closest-hit rays had no certificate and were re-traced on the reference tree"),
     }
