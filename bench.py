@@ -313,22 +313,6 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---- counting pass (untimed): inner / leaf fetches per ray of the same traversal at reduced spp
-    count_spp = max(1, min(args.spp, 2))
-    cstats = capi.RenderStats()
-    co = opts(count_spp, capi.PTB_FLAG_DEVICE_IO | capi.PTB_FLAG_COUNT_VISITS, 99)
-    capi.check(lib.ptb_render(handle, C.byref(camera), C.byref(co), 0, 0, args.width, args.height, C.c_void_p(image.data_ptr()), C.byref(cstats)))
-    count_detail = {
-        "closest_inner_per_ray": (cstats.inner_visits - cstats.shadow_inner_visits) / max(cstats.closest_rays, 1),
-        "closest_leaf_per_ray": (cstats.leaf_visits - cstats.shadow_leaf_visits) / max(cstats.closest_rays, 1),
-        "shadow_inner_per_ray": cstats.shadow_inner_visits / max(cstats.shadow_rays, 1),
-        "shadow_leaf_per_ray": cstats.shadow_leaf_visits / max(cstats.shadow_rays, 1),
-    }
-    count_rays = sum_over_ranks(float(cstats.closest_rays + cstats.shadow_rays))
-    inner_per_ray = sum_over_ranks(float(cstats.inner_visits)) / max(count_rays, 1.0)
-    leaf_per_ray = sum_over_ranks(float(cstats.leaf_visits)) / max(count_rays, 1.0)
-    bytes_per_ray = INNER_BYTES * inner_per_ray + LEAF_BYTES * leaf_per_ray + RAY_RECORD_BYTES
-
     # ---- warm-up.  The clock sampler (one nvidia-smi process polling every 200 ms) is started here rather than at the
     # first timed step: its NVML start-up takes driver locks for a few hundred milliseconds, which showed up as idle gaps
     # between launches of the first timed step; the samples it reports cover the warm-up and the timed steps, all under
@@ -376,6 +360,23 @@ def run_b200_arm(args):
         gathered = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
         per_rank = {"render_ms": [round(float(g[0]), 2) for g in gathered], "reduce_ms_incl_wait": [round(float(g[1]), 2) for g in gathered]}
+
+    # ---- counting pass (untimed, after the timed steps so that a profiler attached to this command meets steady-state
+    # launches first): inner / leaf fetches per ray of the same traversal at reduced spp
+    count_spp = max(1, min(args.spp, 2))
+    cstats = capi.RenderStats()
+    co = opts(count_spp, capi.PTB_FLAG_DEVICE_IO | capi.PTB_FLAG_COUNT_VISITS, 99)
+    capi.check(lib.ptb_render(handle, C.byref(camera), C.byref(co), 0, 0, args.width, args.height, C.c_void_p(image.data_ptr()), C.byref(cstats)))
+    count_detail = {
+        "closest_inner_per_ray": (cstats.inner_visits - cstats.shadow_inner_visits) / max(cstats.closest_rays, 1),
+        "closest_leaf_per_ray": (cstats.leaf_visits - cstats.shadow_leaf_visits) / max(cstats.closest_rays, 1),
+        "shadow_inner_per_ray": cstats.shadow_inner_visits / max(cstats.shadow_rays, 1),
+        "shadow_leaf_per_ray": cstats.shadow_leaf_visits / max(cstats.shadow_rays, 1),
+    }
+    count_rays = sum_over_ranks(float(cstats.closest_rays + cstats.shadow_rays))
+    inner_per_ray = sum_over_ranks(float(cstats.inner_visits)) / max(count_rays, 1.0)
+    leaf_per_ray = sum_over_ranks(float(cstats.leaf_visits)) / max(count_rays, 1.0)
+    bytes_per_ray = INNER_BYTES * inner_per_ray + LEAF_BYTES * leaf_per_ray + RAY_RECORD_BYTES
 
     job_samples = sum_over_ranks(float(totals["samples"]))
     job_rays = sum_over_ranks(float(totals["closest"] + totals["shadow"]))
