@@ -373,6 +373,8 @@ def run_b200_arm(args):
         "shadow_inner_per_ray": cstats.shadow_inner_visits / max(cstats.shadow_rays, 1),
         "shadow_leaf_per_ray": cstats.shadow_leaf_visits / max(cstats.shadow_rays, 1),
     }
+    certificate_audit = {"primitive_tests": int(cstats.leaf_visits - cstats.shadow_leaf_visits), "suspect_hits": int(cstats.certified_suspect_hits),
+                         "closest_rays": int(cstats.closest_rays), "retraced": int(cstats.closest_rays_retraced)}
     count_rays = sum_over_ranks(float(cstats.closest_rays + cstats.shadow_rays))
     inner_per_ray = sum_over_ranks(float(cstats.inner_visits)) / max(count_rays, 1.0)
     leaf_per_ray = sum_over_ranks(float(cstats.leaf_visits)) / max(count_rays, 1.0)
@@ -486,6 +488,7 @@ def run_b200_arm(args):
                   "query_tree": "device LBVH" if info.query_tree_on_device else "host binned SAH", "query_tree_device_ms": info.query_tree_device_ms},
         "bounce_iterations_per_step": totals["iterations"] / args.steps,
         "per_rank": per_rank,
+        "certificate_audit": None if args.reference_closest else certificate_audit,
         "closest_hit": ("reference-topology tree" if args.reference_closest else
                         f"certified SAH walk; {totals['retraced']} of {totals['closest']} closest-hit rays had no certificate and were re-traced on the reference tree"),
     }

@@ -119,6 +119,7 @@ class RenderStats(C.Structure):
         ("shadow_inner_visits", C.c_uint64),
         ("shadow_leaf_visits", C.c_uint64),
         ("closest_rays_retraced", C.c_uint64),
+        ("certified_suspect_hits", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -52,6 +52,7 @@ namespace ptb {
     struct VisitCounters {
         unsigned long long inner;
         unsigned long long leaf;
+        unsigned long long suspect; // certified walk: hits reported more than 2^-8 in front of the primitive's own leaf box (see traverse.cuh)
     };
 
 }

@@ -19,6 +19,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace {
@@ -369,6 +370,18 @@ namespace {
         // at once.  The host reads the counters of every iteration of the batch afterwards (statistics, termination); a
         // descheduled host thread then delays one batch boundary instead of every iteration.  Queues never grow, so the
         // length known at the start of a batch bounds the grids of all its iterations.
+        // closest-hit trace of the paths in `queue` (length counters[queue_slot]) with the walk `mode`
+        auto launch_closest = [&](auto mode, const uint32_t *queue, int queue_slot, int cursor_slot) {
+            constexpr int kMode = decltype(mode)::value;
+            uint32_t *redo_out = kMode == kTraceCertified ? redo_queue : nullptr; // only the certified walk hands rays back
+            if(count_visits) {
+                traceClosestKernel<kMode, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queue, counters, queue_slot, cursor_slot, redo_out, visits);
+            }
+            else {
+                traceClosestKernel<kMode, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queue, counters, queue_slot, cursor_slot, redo_out, visits);
+            }
+        };
+
         const int batch = ctx->iterations_per_sync;
         while(n_cur > 0U) {
             int launched = 0;
@@ -383,26 +396,11 @@ namespace {
                     LaunchTimer timer(ctx, 0);
                     if(certified) {
                         // SAH walk with certificate, then the handed-back rays on the reference tree (usually a handful)
-                        if(count_visits) {
-                            traceClosestKernel<kTraceCertified, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur,
-                                                                                                             kCountFetchClosest, redo_queue, visits);
-                            traceClosestKernel<kTraceClosest, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, redo_queue, counters, kCountRedo,
-                                                                                                              kCountFetchRedo, redo_queue, visits);
-                        }
-                        else {
-                            traceClosestKernel<kTraceCertified, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur,
-                                                                                                              kCountFetchClosest, redo_queue, visits);
-                            traceClosestKernel<kTraceClosest, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, redo_queue, counters, kCountRedo,
-                                                                                                               kCountFetchRedo, redo_queue, visits);
-                        }
-                    }
-                    else if(count_visits) {
-                        traceClosestKernel<kTraceClosest, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur, kCountFetchClosest,
-                                                                                                       redo_queue, visits);
+                        launch_closest(std::integral_constant<int, kTraceCertified>{}, queues[cur], cur, kCountFetchClosest);
+                        launch_closest(std::integral_constant<int, kTraceClosest>{}, redo_queue, kCountRedo, kCountFetchRedo);
                     }
                     else {
-                        traceClosestKernel<kTraceClosest, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queues[cur], counters, cur, kCountFetchClosest,
-                                                                                                        redo_queue, visits);
+                        launch_closest(std::integral_constant<int, kTraceClosest>{}, queues[cur], cur, kCountFetchClosest);
                     }
                 }
                 {
@@ -612,6 +610,7 @@ namespace {
             stats->leaf_visits = v[0].leaf + v[1].leaf;
             stats->shadow_inner_visits = v[1].inner;
             stats->shadow_leaf_visits = v[1].leaf;
+            stats->certified_suspect_hits = v[0].suspect + v[1].suspect;
         }
         return PTB_OK;
     }

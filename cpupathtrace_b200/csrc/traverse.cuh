@@ -167,6 +167,7 @@ namespace ptb {
     // and re-traced on the reference tree, so ties keep the reference's later-visited-wins outcome.
     constexpr float kCertifiedPruneSlack = 1.0078125F;   // 1 + 2^-7
     constexpr float kCertifiedEntrySlack = 1.001953125F; // 1 + 2^-9
+    constexpr float kCertifiedSuspectFactor = 0.99609375F; // 1 - 2^-8
 
     // Hit test of one box in "visit" form: hit <=> the reference's slab result is >= 0, entry = that result.
     // (bounding_box.cpp:61-72: -1 iff t_max < 0 or t_min > t_max; otherwise max(t_min, 0).)
@@ -228,6 +229,7 @@ namespace ptb {
         bool exhausted = count == 0U;
         unsigned long long n_inner = 0;
         unsigned long long n_leaf = 0;
+        unsigned long long n_suspect = 0;
 
         // next deferred far child that still beats the best distance, or the ray is finished
         auto advance = [&]() {
@@ -393,6 +395,11 @@ namespace ptb {
                     }
                 }
                 else if(CERTIFIED) {
+                    // audit of the one assumption behind the certificate (counting builds only): a primitive the walk never
+                    // reaches could matter only if its test put the hit more than 2^-8 in front of its own leaf box
+                    if(COUNT && t >= 0.0F && t < leaf_entry * kCertifiedSuspectFactor) {
+                        n_suspect++;
+                    }
                     if(t >= 0.0F) {
                         if(t < best_t) {
                             // every primitive tested so far has t >= the old best; they clear the new rival bound iff it does
@@ -424,6 +431,9 @@ namespace ptb {
         if(COUNT && counters != nullptr) {
             atomicAdd(&counters->inner, n_inner);
             atomicAdd(&counters->leaf, n_leaf);
+            if(n_suspect != 0ULL) {
+                atomicAdd(&counters->suspect, n_suspect);
+            }
         }
     }
 

@@ -19,6 +19,16 @@
  *     fails with PTB_ERR_NO_DEVICE / PTB_ERR_CUDA;
  *   - pointers are host pointers unless the call's `flags` carry PTB_FLAG_DEVICE_IO, in which case the bulk
  *     input/output arrays are device pointers (same process, same device) and no host<->device copy is made.
+ *
+ * Environment (read when a context is created / a scene is built / a frame is rendered; none changes a result)
+ *   PTB_DEVICE, LOCAL_RANK        device of ptb_context_create(-1)
+ *   PTB_POOL_PATHS                paths in flight (default: 128 Mi, at most a fifth of the free HBM, at most half of a call's samples)
+ *   PTB_SAMPLE_BUFFER_MB          per-sample buffer budget of ptb_render (default: 40 % of the free HBM)
+ *   PTB_GPU_BVH=1                 build the query hierarchy on the GPU (PTB_BVH_REFERENCE_GPU_QUERY_TREE); PTB_OCCLUSION_BVH=0: none
+ *   PTB_BUILD_THREADS             host threads of the BVH builders
+ *   PTB_REFILL_VOTE, PTB_LEAF_VOTE, PTB_SHADOW_REFILL_VOTE, PTB_SHADOW_LEAF_VOTE, PTB_LEAF_BURST, PTB_INNER_BURST,
+ *   PTB_TRACE_BLOCKS_PER_SM, PTB_ITERATIONS_PER_SYNC    scheduling of the traversal kernels and of the bounce loop
+ *   PTB_PROFILE=0                 no per-launch CUDA events; PTB_LOG_ITERATIONS=1: one stderr line per bounce iteration
  */
 #ifndef PTB_H
 #define PTB_H
@@ -211,6 +221,9 @@ typedef struct ptb_render_stats {
     uint64_t shadow_inner_visits;   /* the shadow-ray share of inner_visits               */
     uint64_t shadow_leaf_visits;    /* the shadow-ray share of leaf_visits                */
     uint64_t closest_rays_retraced; /* PTB_FLAG_CERTIFIED_CLOSEST: queries without a certificate, re-traced on the reference tree */
+    uint64_t certified_suspect_hits; /* with PTB_FLAG_COUNT_VISITS: primitive tests of the certified walk that reported a hit */
+                                     /* more than 2^-8 in front of the primitive's own bounding box -- the only situation in */
+                                     /* which a primitive the walk never reaches could change the reference's answer         */
 } ptb_render_stats;
 
 /* ------------------------------------------------------------------------------------------------ entry points */

@@ -339,6 +339,8 @@ def test_full_size_scene_properties(ctx, ref):
     assert np.array_equal(prim_c, prim) and np.array_equal(t_c[hit], t[hit]) and (t_c[~hit] < 0).all()
     assert stats_c.inner_visits < stats.inner_visits // 2
     assert stats_c.closest_rays_retraced < len(rays) // 1000
+    # audit of the certificate's one assumption: hits reported more than 2^-8 in front of the primitive's own box
+    assert stats_c.certified_suspect_hits <= stats_c.leaf_visits // 1_000_000, stats_c.certified_suspect_hits
 
     # the reported primitive, intersected alone, gives the same distance (spot check on 200 rays)
     idx = np.nonzero(hit)[0][:: max(1, hit.sum() // 200)][:200]
