@@ -469,6 +469,162 @@ void pto_intersect(const pto_scene *s, const float *rays, uint64_t n, float *t_o
     }
 }
 
+/* ------------------------------------------------------------------------------------------------ certificate
+ *
+ * CPU statement of the "certified closest hit" the CUDA kernels use (cpupathtrace_b200/csrc/traverse.cuh): walk ANY
+ * hierarchy whose inner boxes are the exact unions of their children's boxes, nearest child first, pruning subtrees
+ * whose entry exceeds t_best (1 + 2^-7), and keep the result only if it is strictly nearer than every other hit found,
+ * no other hit lies at or before its own leaf-box entry, that entry does not exceed t_best (1 + 2^-9), and t_best > 0.
+ * The claim under test: whenever the walk returns certain = 1, (t, primitive) equals what the reference walk
+ * (scene_hit above, scene.cpp:104-150) returns on the reference tree -- whatever the shape of the hierarchy walked here.
+ * The hierarchy is built from `tree_seed`: a random permutation of the primitives split at random positions
+ * (shape 0), at position 1 (shape 1: a chain, the most unbalanced tree) or in the middle (shape 2).
+ */
+typedef struct {
+    float lo[3], hi[3];
+    int left, right; /* >= 0: inner node, < 0: ~primitive */
+} cnode;
+
+static uint64_t cert_rand(uint64_t *state) { /* splitmix64 */
+    uint64_t z = (*state += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+static void cert_ref_box(const pto_scene *s, const cnode *nodes, int ref, float lo[3], float hi[3]) {
+    if(ref < 0) {
+        prim_bounds(&s->prims[~ref], lo, hi);
+    }
+    else {
+        for(int c = 0; c < 3; c++) {
+            lo[c] = nodes[ref].lo[c];
+            hi[c] = nodes[ref].hi[c];
+        }
+    }
+}
+
+static int cert_build(const pto_scene *s, cnode *nodes, int *n_nodes, int *items, int n, int shape, uint64_t *state) {
+    if(n == 1) return ~items[0];
+    int split = shape == 1 ? 1 : (shape == 2 ? n / 2 : 1 + (int)(cert_rand(state) % (uint64_t)(n - 1)));
+    int left = cert_build(s, nodes, n_nodes, items, split, shape, state);
+    int right = cert_build(s, nodes, n_nodes, items + split, n - split, shape, state);
+    int id = (*n_nodes)++;
+    float llo[3], lhi[3], rlo[3], rhi[3];
+    cert_ref_box(s, nodes, left, llo, lhi);
+    cert_ref_box(s, nodes, right, rlo, rhi);
+    for(int c = 0; c < 3; c++) {
+        nodes[id].lo[c] = fminstd(llo[c], rlo[c]);
+        nodes[id].hi[c] = fmaxstd(lhi[c], rhi[c]);
+    }
+    nodes[id].left = left;
+    nodes[id].right = right;
+    return id;
+}
+
+typedef struct {
+    int ref;
+    float entry;
+} cert_entry;
+
+void pto_intersect_certified(const pto_scene *s, const float *rays, uint64_t n, uint64_t tree_seed, int shape, float *t_out, int32_t *prim_out,
+                             uint8_t *certain_out) {
+    const float prune_slack = 1.0078125F;   /* 1 + 2^-7 */
+    const float entry_slack = 1.001953125F; /* 1 + 2^-9 */
+    if(s->n_prims == 0) {
+        for(uint64_t i = 0; i < n; i++) {
+            t_out[i] = -1.0F;
+            prim_out[i] = -1;
+            certain_out[i] = 1;
+        }
+        return;
+    }
+    int np = (int)s->n_prims;
+    int *items = (int *)malloc(sizeof(int) * (size_t)np);
+    uint64_t state = tree_seed;
+    for(int i = 0; i < np; i++) items[i] = i;
+    for(int i = np - 1; i > 0; i--) {
+        int j = (int)(cert_rand(&state) % (uint64_t)(i + 1));
+        int tmp = items[i];
+        items[i] = items[j];
+        items[j] = tmp;
+    }
+    cnode *nodes = (cnode *)malloc(sizeof(cnode) * (size_t)(np > 1 ? np - 1 : 1));
+    int n_nodes = 0;
+    int root = cert_build(s, nodes, &n_nodes, items, np, shape, &state);
+    free(items);
+    cert_entry *stack = (cert_entry *)malloc(sizeof(cert_entry) * (size_t)(np + 1));
+
+    for(uint64_t i = 0; i < n; i++) {
+        ray r = {V(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), V(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])};
+        float rlo[3], rhi[3];
+        cert_ref_box(s, nodes, root, rlo, rhi);
+        float root_t = box_hit(rlo, rhi, &r);
+        float best_t = FLT_MAX, prune_t = FLT_MAX, rival_t = 0.0F, hit_t = -1.0F;
+        int best = -1, certain = 1, sp = 0;
+        if(!(root_t >= 0.0F)) {
+            t_out[i] = root_t;
+            prim_out[i] = -1;
+            certain_out[i] = 1;
+            continue;
+        }
+        stack[sp].ref = root;
+        stack[sp].entry = root_t;
+        sp++;
+        while(sp > 0) {
+            cert_entry e = stack[--sp];
+            if(!(e.entry < prune_t)) continue; /* deferred sibling re-tested against the current bound */
+            int ref = e.ref;
+            float entry = e.entry;
+            for(;;) {
+                if(ref < 0) {
+                    float t = prim_hit(&s->prims[~ref], &r);
+                    if(t >= 0.0F) {
+                        if(t < best_t) {
+                            float rival = fmaxstd(t, entry);
+                            certain = best_t > rival && entry <= t * entry_slack && t > 0.0F;
+                            rival_t = rival;
+                            best_t = t;
+                            prune_t = t * prune_slack;
+                            hit_t = t;
+                            best = ~ref;
+                        }
+                        else if(t <= rival_t) {
+                            certain = 0;
+                        }
+                    }
+                    break;
+                }
+                float llo[3], lhi[3], qlo[3], qhi[3];
+                cert_ref_box(s, nodes, nodes[ref].left, llo, lhi);
+                cert_ref_box(s, nodes, nodes[ref].right, qlo, qhi);
+                float lt = box_hit(llo, lhi, &r), rt = box_hit(qlo, qhi, &r);
+                int vl = lt >= 0.0F && lt < prune_t, vr = rt >= 0.0F && rt < prune_t;
+                if(vl && vr) {
+                    int left_first = lt < rt;
+                    stack[sp].ref = left_first ? nodes[ref].right : nodes[ref].left;
+                    stack[sp].entry = left_first ? rt : lt;
+                    sp++;
+                    entry = left_first ? lt : rt;
+                    ref = left_first ? nodes[ref].left : nodes[ref].right;
+                }
+                else if(vl || vr) {
+                    entry = vl ? lt : rt;
+                    ref = vl ? nodes[ref].left : nodes[ref].right;
+                }
+                else {
+                    break;
+                }
+            }
+        }
+        t_out[i] = hit_t;
+        prim_out[i] = best;
+        certain_out[i] = (uint8_t)certain;
+    }
+    free(stack);
+    free(nodes);
+}
+
 void pto_aabb_intersect(const float lo[3], const float hi[3], uint64_t n, const float *rays, float *t_out) {
     for(uint64_t i = 0; i < n; i++) {
         ray r = {V(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), V(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])};

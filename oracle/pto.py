@@ -21,6 +21,7 @@ def load():
         lib.pto_scene_emissive_count.argtypes = [_P]
         lib.pto_intersect.argtypes = [_P, _P, C.c_uint64, _P, _P]
         lib.pto_aabb_intersect.argtypes = [_P, _P, C.c_uint64, _P, _P]
+        lib.pto_intersect_certified.argtypes = [_P, _P, C.c_uint64, C.c_uint64, C.c_int, _P, _P, _P]
         lib.pto_sample_lights.argtypes = [_P, _P, C.c_uint64, C.c_int, _P]
         lib.pto_camera_shoot.argtypes = [_P, C.c_uint64, _P, C.c_float, C.c_float, _P, _P]
         lib.pto_render_samples.argtypes = [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_uint64, _P, _P, _P, _P]
@@ -64,6 +65,15 @@ class OracleScene:
         prim = np.empty(len(rays), np.int32)
         load().pto_intersect(self.h, _ptr(rays), len(rays), _ptr(t), _ptr(prim))
         return t, prim
+
+    def intersect_certified(self, rays, tree_seed, shape=0):
+        """Certified closest hit (CPU statement of csrc/traverse.cuh) on a random hierarchy: (t, prim, certain)."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        t = np.empty(len(rays), np.float32)
+        prim = np.empty(len(rays), np.int32)
+        certain = np.empty(len(rays), np.uint8)
+        load().pto_intersect_certified(self.h, _ptr(rays), len(rays), int(tree_seed), int(shape), _ptr(t), _ptr(prim), _ptr(certain))
+        return t, prim, certain.astype(bool)
 
     def sample_lights(self, pos, seed, max_out=64):
         pos = np.ascontiguousarray(pos, np.float32)

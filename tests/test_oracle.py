@@ -145,3 +145,27 @@ def test_libm_restatement_matches_system_libm(lib):
     out = (C.c_uint64 * 4)()
     check(3_000_000, 20261018, out)
     assert list(out) == [0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("name", GOLDEN_SCENES)
+def test_certificate_theorem_on_arbitrary_hierarchies(name):
+    """The claim behind PTB_FLAG_CERTIFIED_CLOSEST (csrc/traverse.cuh), checked on the CPU independently of the CUDA code:
+    walking ANY hierarchy with exact union boxes -- random splits of a random permutation, a chain, a balanced tree --
+    and keeping a hit only when it carries the certificate gives exactly what the reference walk returns on the
+    reference tree (here: the golden hits of the unmodified reference, a third of them aimed at shared vertices and edges).
+    Rays without a certificate are the ones the kernels re-trace on the reference tree; they must be the minority."""
+    g = load_golden("hits", name)
+    scene = _oracle_scene(g)
+    rays, want_t, want_prim = g["rays"][:20000], g["t"][:20000], g["prim"][:20000]
+    for seed, shape in ((1, 0), (2, 0), (3, 1), (4, 2)):
+        if shape == 1 and len(g["prims"]) > 3000:
+            continue  # the chain is quadratic in the primitive count
+        t, prim, certain = scene.intersect_certified(rays, seed, shape)
+        hit = want_t >= 0
+        assert certain.mean() > 0.5
+        assert np.array_equal(prim[certain], want_prim[certain]), (seed, shape)
+        assert np.array_equal(t[certain & hit], want_t[certain & hit]), (seed, shape)
+        assert (t[certain & ~hit] < 0).all()
+        # and the certificate is not vacuous: uncertified rays do differ from the reference now and then on a foreign tree
+        if name != "advanced":
+            assert (~certain).sum() > 0
