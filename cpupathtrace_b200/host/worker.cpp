@@ -37,7 +37,8 @@ namespace {
         opts.flags = (control.any_hit_shadows ? PTB_FLAG_ANY_HIT_SHADOWS : 0U) | (control.skip_null_shadows ? PTB_FLAG_SKIP_NULL_SHADOWS : 0U) |
                      (control.certified_closest ? PTB_FLAG_CERTIFIED_CLOSEST : 0U);
         opts.seed = seed;
-        opts.shard_count = 1;
+        opts.shard_count = std::max(control.shard_count, 1);
+        opts.shard_index = std::min(std::max(control.shard_index, 0), opts.shard_count - 1);
         return opts;
     }
 
@@ -49,7 +50,7 @@ namespace {
         return pod;
     }
 
-    Image<> renderRect(const FrameRenderJob &job, int x0, int y0, int w, int h, int tile_size, uint64_t seed) {
+    Image<> renderRect(const FrameRenderJob &job, int x0, int y0, int w, int h, int tile_size, uint64_t seed, bool sharded) {
         Image<> image(std::max(w, 0), std::max(h, 0));
         if(w <= 0 || h <= 0) {
             return image;
@@ -58,6 +59,11 @@ namespace {
         const ptb_camera camera = lowerCamera(job.camera);
         ptb_render_opts opts = makeOpts(job.options, seed, PTB_RNG_COUNTER);
         opts.tile_size = tile_size;
+        if(!sharded) {
+            // processItem renders exactly the tile it was asked for; only processJob splits the frame between processes
+            opts.shard_index = 0;
+            opts.shard_count = 1;
+        }
         ptb::host::check(ptb_render(job.scene.deviceScene(), &camera, &opts, x0, y0, w, h, reinterpret_cast<float *>(image.data()), nullptr), "render");
         return image;
     }
@@ -73,6 +79,8 @@ namespace ptb {
             c.any_hit_shadows = envLong("PTB_ANY_HIT_SHADOWS", 0) != 0;
             c.skip_null_shadows = envLong("PTB_SKIP_NULL_SHADOWS", 0) != 0;
             c.certified_closest = envLong("PTB_CERTIFIED_CLOSEST", 0) != 0;
+            c.shard_index = static_cast<int>(envLong("PTB_SHARD_INDEX", 0));
+            c.shard_count = static_cast<int>(std::max(1L, envLong("PTB_SHARD_COUNT", 1)));
             c.fixed_seed = static_cast<uint64_t>(envLong("PTB_SEED", 0));
             return c;
         }();
@@ -97,7 +105,7 @@ Image<> processItem(const WorkItem &item, RandomEngine &re) {
     const uint64_t high = re();
     const uint64_t seed = (high << 32) | low;
     // one tile: a single group of pixels, no further subdivision
-    return renderRect(*item.job, item.offset_x, item.offset_y, item.width, item.height, std::max(std::max(item.width, item.height), 1), seed);
+    return renderRect(*item.job, item.offset_x, item.offset_y, item.width, item.height, std::max(std::max(item.width, item.height), 1), seed, false);
 }
 
 Image<> processJob(const FrameRenderJob &job, const std::function<void(int, int)> &progress_callback, int /*worker_count*/) {
@@ -119,7 +127,7 @@ Image<> processJob(const FrameRenderJob &job, const std::function<void(int, int)
     const int vertical_tiles = (height + tile_size - 1) / tile_size;
     const int total_tiles = horizontal_tiles * vertical_tiles;
 
-    Image<> image = renderRect(job, 0, 0, width, height, tile_size, seed);
+    Image<> image = renderRect(job, 0, 0, width, height, tile_size, seed, true);
 
     for(int tile = 0; tile < total_tiles; tile++) {
         progress_callback(tile + 1, total_tiles);

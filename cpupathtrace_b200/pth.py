@@ -46,6 +46,7 @@ _OPTIONAL = {
     "pth_scene_device_handle": (_P, [_P]),
     "pth_png_roundtrip": (C.c_long, [C.c_int, C.c_int, _P, _P]),
     "pth_set_fast_queries": (None, [C.c_int, C.c_int, C.c_int]),
+    "pth_set_sharding": (None, [C.c_int, C.c_int, C.c_uint64]),
 }
 
 REF_PARITY = os.path.join(REPO_ROOT, "oracle", "_ref", "libpth_ref.so")
@@ -79,6 +80,10 @@ class Pth:
     def set_fast_queries(self, certified_closest, any_hit_shadows, skip_null_shadows):
         """b200 build only: ptb::RenderControl's result-neutral query options for every later call of this process."""
         self.lib.pth_set_fast_queries(int(certified_closest), int(any_hit_shadows), int(skip_null_shadows))
+
+    def set_sharding(self, shard_index, shard_count, fixed_seed=0):
+        """b200 build only: the share of processJob's tile grid this process renders, and the job seed (0 = random)."""
+        self.lib.pth_set_sharding(int(shard_index), int(shard_count), int(fixed_seed))
 
     # ---- camera
     def camera(self, origin, look_at, up, focal_length, height, aspect_ratio, aperture_width=0.0, aperture_height=0.0, sampler=0, hex_ratio=0.0,

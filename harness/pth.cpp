@@ -487,6 +487,15 @@ extern "C" void pth_set_fast_queries(int certified_closest, int any_hit_shadows,
     control.any_hit_shadows = any_hit_shadows != 0;
     control.skip_null_shadows = skip_null_shadows != 0;
 }
+
+// b200 build only: which share of processJob's tile grid this process renders (ptb::RenderControl::shard_index / shard_count)
+// and the job seed (0 = std::random_device per call).
+extern "C" void pth_set_sharding(int shard_index, int shard_count, unsigned long long fixed_seed) {
+    ptb::RenderControl &control = ptb::renderControl();
+    control.shard_index = shard_index;
+    control.shard_count = shard_count;
+    control.fixed_seed = fixed_seed;
+}
 #endif
 
 #ifdef PATHTRACE_B200

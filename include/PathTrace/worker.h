@@ -70,9 +70,11 @@ namespace ptb {
         bool skip_null_shadows = false; //!< do not trace shadow rays whose contribution is always zero (glass, mirror)
         bool certified_closest = false; //!< closest hits on the SAH hierarchy where a certificate proves the reference's result, else re-traced
         uint64_t fixed_seed = 0;      //!< processJob: non-zero replaces std::random_device
+        int shard_index = 0;          //!< multi-GPU, one process per GPU: this process renders tile k of the frame's tile grid iff
+        int shard_count = 1;          //!< k % shard_count == shard_index and leaves the other pixels 0 (sum-reduce the images)
     };
 
-    //! process-wide control block; initialised from PTB_MAX_DEPTH, PTB_ANY_HIT_SHADOWS, PTB_SKIP_NULL_SHADOWS, PTB_CERTIFIED_CLOSEST, PTB_SEED
+    //! process-wide control block; initialised from PTB_MAX_DEPTH, PTB_ANY_HIT_SHADOWS, PTB_SKIP_NULL_SHADOWS, PTB_CERTIFIED_CLOSEST, PTB_SEED, PTB_SHARD_INDEX, PTB_SHARD_COUNT
     RenderControl &renderControl();
 
     /**

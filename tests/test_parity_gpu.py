@@ -195,6 +195,30 @@ def test_fast_queries_through_the_cpp_api_change_nothing(ref, b200):
         b200.set_fast_queries(False, False, False)
 
 
+def test_process_job_shards_sum_to_the_frame(b200):
+    """Multi-GPU through the C++ API, one process per GPU: with ptb::RenderControl::shard_index / shard_count (env
+    PTB_SHARD_INDEX / PTB_SHARD_COUNT) processJob renders its interleaved share of the reference's tile grid and leaves
+    the rest 0, so the sum of the shards (what the NCCL reduce computes) is the unsharded frame, bit for bit; processItem
+    is not affected."""
+    cam = scenes.demo_camera(None, 96, 80)
+    sg = scenes.cornell_demo(("obj", scenes.standin_obj(40, 30))).build(b200)
+    camera = b200.camera(**cam)
+    try:
+        b200.set_sharding(0, 1, 77)
+        full, info = sg.process_job(camera, 96, 80, 4, 4, 1e-3)
+        total = np.zeros_like(full)
+        for rank in range(3):
+            b200.set_sharding(rank, 3, 77)
+            part, _ = sg.process_job(camera, 96, 80, 4, 4, 1e-3)
+            assert (part != 0).any() and (part == 0).all(axis=2).mean() > 0.5
+            total += part
+            tile = sg.process_item(camera, 96, 80, 4, 4, 1e-3, (8, 8, 16, 16), 5)
+            assert (tile[..., 3] > 0).any()  # a tile rendered on request is never somebody else's
+        assert np.array_equal(total, full)
+    finally:
+        b200.set_sharding(0, 1, 0)
+
+
 def test_render_kats(ref, b200):
     """reference test/render_test.cpp: empty scene -> (0,0,0,0); lit sphere: corner exactly 0, centre alpha > 0."""
     cam = dict(origin=(0.0, 0.0, 0.0), look_at=(0.0, 0.0, 1.0), up=(0.0, 1.0, 0.0), focal_length=1.0, height=1.0, aspect_ratio=1.0)
