@@ -104,7 +104,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -313,7 +313,7 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---- warm-up.  The clock sampler (one nvidia-smi process polling every 200 ms) is started here rather than at the
+    # ---- warm-up.  The clock sampler (one nvidia-smi process polling every 500 ms) is started here rather than at the
     # first timed step: its NVML start-up takes driver locks for a few hundred milliseconds, which showed up as idle gaps
     # between launches of the first timed step; the samples it reports cover the warm-up and the timed steps, all under
     # the same load.
