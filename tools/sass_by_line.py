@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Attributes executed warp instructions / stall samples of one kernel in an ncu report to CUDA source lines.
-usage: sass_by_line.py <nvdisasm -g -c output> <ncu --page source --csv output> <mangled-name-substring> [top]"""
+usage: sass_by_line.py <nvdisasm -g -c output> <ncu --page source --csv output> <mangled-name-substring> [top] [demangled-name-substring]
+The report may hold several kernels: the CSV is a sequence of sections, each introduced by a "Kernel Name" row; the
+optional fifth argument selects the sections of one kernel (e.g. 'traceClosestKernel<(int)2, (bool)0>')."""
 import collections
 import csv
 import re
@@ -23,6 +25,15 @@ for l in lines[start + 1:]:
         off2line[int(m.group(1), 16)] = cur
         n += 1
 rows = list(csv.reader(open(src_csv)))
+if len(sys.argv) > 5:
+    wanted, keep, selected = sys.argv[5], False, []
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            keep = len(r) > 1 and wanted in r[1]
+            continue
+        if keep:
+            selected.append(r)
+    rows = selected
 hi = next(i for i, r in enumerate(rows) if "Source" in r and "Instructions Executed" in r)
 hdr = rows[hi]
 ai, ii, si, ti = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
