@@ -156,8 +156,8 @@ def test_certificate_theorem_on_arbitrary_hierarchies(name):
     Rays without a certificate are the ones the kernels re-trace on the reference tree; they must be the minority."""
     g = load_golden("hits", name)
     scene = _oracle_scene(g)
-    rays, want_t, want_prim = g["rays"][:20000], g["t"][:20000], g["prim"][:20000]
-    for seed, shape in ((1, 0), (2, 0), (3, 1), (4, 2)):
+    rays, want_t, want_prim = g["rays"], g["t"], g["prim"]
+    for seed, shape in ((1, 0), (2, 0), (5, 0), (6, 0), (3, 1), (4, 2)):
         if shape == 1 and len(g["prims"]) > 3000:
             continue  # the chain is quadratic in the primitive count
         t, prim, certain = scene.intersect_certified(rays, seed, shape)
@@ -169,3 +169,23 @@ def test_certificate_theorem_on_arbitrary_hierarchies(name):
         # and the certificate is not vacuous: uncertified rays do differ from the reference now and then on a foreign tree
         if name != "advanced":
             assert (~certain).sum() > 0
+
+    # fresh rays, a third of them aimed at triangle vertices and edge midpoints (the tie cases), against the restatement's
+    # own reference-order walk (pinned bit for bit to the reference above)
+    from conftest import random_rays
+
+    tris = g["prims"]["p"][g["prims"]["kind"] == 0][:, :9]
+    aim = np.concatenate([tris.reshape(-1, 3), 0.5 * (tris[:, 0:3] + tris[:, 3:6])]) if len(tris) else None
+    if aim is not None:
+        aim = aim[np.random.Generator(np.random.PCG64(9)).permutation(len(aim))][:20000]
+    rays = random_rays(60000, seed=13, box=1.3, aim=aim)
+    want_t, want_prim = scene.intersect(rays)
+    differing = 0
+    for seed in (11, 12):
+        t, prim, certain = scene.intersect_certified(rays, seed, 0)
+        hit = want_t >= 0
+        assert np.array_equal(prim[certain], want_prim[certain]) and np.array_equal(t[certain & hit], want_t[certain & hit])
+        assert (t[certain & ~hit] < 0).all() and certain.mean() > 0.6
+        differing += int((prim[~certain] != want_prim[~certain]).sum())
+    if name == "cornell_mesh":
+        assert differing > 0  # ties on a foreign tree do come out differently: that is what the re-trace is for
