@@ -53,6 +53,8 @@ def parse_args():
                    help="closest-hit queries walk the reference-topology tree only (default: certified SAH walk + re-trace of uncertified rays)")
     p.add_argument("--reference-shadows", action="store_true",
                    help="trace shadow rays exactly like the reference (closest-hit queries, also for glass/mirror vertices whose result is discarded)")
+    p.add_argument("--guarded", action="store_true",
+                   help="certified closest hits with the guard table (the exact mode validation uses); default: relaxed, as production renders")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of one reference-arm sample")
     return p.parse_args()
@@ -257,11 +259,10 @@ def run_b200_arm(args):
 
     flags = 0 if args.reference_shadows else (capi.PTB_FLAG_ANY_HIT_SHADOWS | capi.PTB_FLAG_SKIP_NULL_SHADOWS)
     if not args.reference_closest:
-        flags |= capi.PTB_FLAG_CERTIFIED_CLOSEST
-    os.environ["PTB_CERTIFIED_CLOSEST"] = "0" if args.reference_closest else "1"
-    os.environ["PTB_MAX_DEPTH"] = str(args.max_depth)
-    os.environ["PTB_ANY_HIT_SHADOWS"] = "0" if args.reference_shadows else "1"
-    os.environ["PTB_SKIP_NULL_SHADOWS"] = "0" if args.reference_shadows else "1"
+        flags |= capi.PTB_FLAG_CERTIFIED_CLOSEST | (0 if args.guarded else capi.PTB_FLAG_CERTIFIED_RELAXED)
+    # the same options for the C++ API (processJob): through ptb::RenderControl, not the environment (which is read once)
+    b200.set_fast_queries(not args.reference_closest, not args.reference_shadows, not args.reference_shadows)
+    b200.set_render_control(max_depth=args.max_depth, relaxed_guard=not args.guarded)
 
     def opts(spp, extra_flags=0, seed=1):
         return capi.render_opts(args.width, args.height, spp, spp, 1e-3, args.max_depth, capi.PTB_RNG_COUNTER, flags | extra_flags, seed, 0, rank, world)
@@ -424,7 +425,7 @@ def run_b200_arm(args):
         barrier()
         t0 = time.perf_counter()
         if world == 1:
-            os.environ["PTB_SEED"] = str(3000 + i)
+            b200.set_sharding(0, 1, 3000 + i)
             scene_cpp.process_job(camera_cpp, args.width, args.height, args.spp, args.spp, 1e-3, 0)
         else:
             device_step(3000 + i)

@@ -28,6 +28,7 @@ PTB_FLAG_ANY_HIT_SHADOWS = 0x2
 PTB_FLAG_SKIP_NULL_SHADOWS = 0x4
 PTB_FLAG_COUNT_VISITS = 0x8
 PTB_FLAG_CERTIFIED_CLOSEST = 0x10
+PTB_FLAG_CERTIFIED_RELAXED = 0x20
 
 # numpy dtypes of the POD records (layout-identical to the C structs)
 PRIM_DTYPE = np.dtype([("kind", "<u4"), ("material", "<u4"), ("cull_backface", "<u4"), ("reserved", "<u4"), ("p", "<f4", (18,))])
@@ -64,7 +65,7 @@ class SceneInfo(C.Structure):
         ("root_low", C.c_float * 3),
         ("root_high", C.c_float * 3),
         ("query_tree_on_device", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("certifiable", C.c_uint32),
         ("query_tree_device_ms", C.c_double),
     ]
 

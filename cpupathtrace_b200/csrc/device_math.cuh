@@ -105,6 +105,14 @@ namespace ptb {
                      : "l"(p));
     }
 
+    // the same for read-write data (path pool): plain global load, cached in L2 only
+    PTB_DEV void ld256cg(const float4 *p, float4 &a, float4 &b) {
+        asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                     : "l"(p)
+                     : "memory");
+    }
+
     PTB_DEV float4 f4(V4 v) {
         return make_float4(v.x, v.y, v.z, v.w);
     }

@@ -219,6 +219,42 @@ namespace ptb {
         return 2.0F * (df + w);
     }
 
+    // ---- what the path-vertex code calls
+    //
+    // Exact build (validation, and any TU compiled without PTB_FAST_MATH): the glibc restatements above.
+    // Production build (ptb_fast.cu, -use_fast_math, FMA contraction on; CounterRng kernels only): the SFU approximations
+    // (MUFU.SIN/COS after a range-reduction multiply, absolute error < 2^-21 on [0, 2 pi]), sqrt for pow(x, 1/2) and CUDA's
+    // acosf.  The production generator's paths are not comparable sample by sample with the reference anyway (different
+    // random numbers); what the north star asks of them is an image within the Monte Carlo noise bound, which
+    // tests/test_parity_gpu.py::test_bench_scene_image_rmse_within_noise checks with these kernels.
+#if defined(PTB_FAST_MATH)
+    PTB_DEV float pathSinf(float x) {
+        return __sinf(x);
+    }
+    PTB_DEV float pathCosf(float x) {
+        return __cosf(x);
+    }
+    PTB_DEV float pathAcosf(float x) {
+        return acosf(x);
+    }
+    PTB_DEV float pathPowfHalf(float x) {
+        return sqrtf(x);
+    }
+#else
+    PTB_DEV float pathSinf(float x) {
+        return glibcSinf(x);
+    }
+    PTB_DEV float pathCosf(float x) {
+        return glibcCosf(x);
+    }
+    PTB_DEV float pathAcosf(float x) {
+        return glibcAcosf(x);
+    }
+    PTB_DEV float pathPowfHalf(float x) {
+        return glibcPowfHalf(x);
+    }
+#endif
+
 }
 
 #endif

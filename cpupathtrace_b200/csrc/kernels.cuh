@@ -24,30 +24,52 @@
 
 namespace ptb {
 
+#ifndef PTB_FLAT_BLOCK
+#define PTB_FLAT_BLOCK 128 // threads per CTA of the shade and accumulate kernels (one global atomic per CTA and trip)
+#endif
     constexpr int kBlock = 128;
+    constexpr int kFlatBlock = PTB_FLAT_BLOCK;
+    static_assert(kBlock == kTraceBlock, "the traversal's shared-memory stack is laid out for kBlock threads per CTA");
 #ifndef PTB_SHADE_MIN_BLOCKS
 #define PTB_SHADE_MIN_BLOCKS 6 // 80 registers: +4 % shade throughput over the unconstrained 93 (8 CTAs / 64 registers spill and gain nothing)
+#endif
+#ifndef PTB_CLOSEST_MIN_BLOCKS
+#define PTB_CLOSEST_MIN_BLOCKS 10 // closest-hit kernels of the path tracer: 48 registers, no spills (round 2: 8.1 vs 7.5 Grays/s at 12 CTAs / 40 registers)
 #endif
 #ifndef PTB_TRACE_MIN_BLOCKS
 #define PTB_TRACE_MIN_BLOCKS 12 // resident 128-thread CTAs per SM the trace kernels are compiled for (register cap 65536 / (12 * 128) = 42)
 #endif
 
+    // Device-side counters.  Every counter sits on a 128-byte line of its own: they are the targets of the wavefront's
+    // atomics, and atomics on one L2 line are served at about one per clock.  Round 1 kept all of them in 48 adjacent
+    // bytes and issued three per warp trip from the shade kernel (queue append + two statistics): 12.6 M operations on one
+    // line per 134 M-path launch = 6.6 ms at 1.9 GHz, which WAS the kernel's duration (6.7 ms, with 42 % of its stall
+    // samples on the returning atomic, profiles/r02_ncu_shade_atomics.md).  Now: one line per counter, statistics kept in
+    // registers until the end of the kernel, queue appends aggregated per thread block.
+    constexpr int kCounterStride = 32; // 32-bit words between two counters
     enum CounterSlot : int {
-        kCountQueueA = 0,
-        kCountQueueB = 1,
-        kCountShadow = 2,
-        kCountFetchClosest = 3,
-        kCountFetchShadow = 4,
-        kCountSkippedShadows = 5,
-        kCountVertices = 6,
-        kCountRedo = 7,      // rays the certified closest-hit walk handed back
-        kCountFetchRedo = 8, // fetch cursor of their re-trace on the reference tree
-        kCounterSlots = 12
+        kCountQueueA = 0 * kCounterStride,
+        kCountQueueB = 1 * kCounterStride,
+        kCountShadow = 2 * kCounterStride,
+        kCountFetchClosest = 3 * kCounterStride,
+        kCountFetchShadow = 4 * kCounterStride,
+        kCountSkippedShadows = 5 * kCounterStride,
+        kCountVertices = 6 * kCounterStride,
+        kCountRedo = 7 * kCounterStride,      // rays the certified closest-hit walk handed back
+        kCountFetchRedo = 8 * kCounterStride, // fetch cursor of their re-trace on the reference tree
+        kCounterSlots = 12 * kCounterStride
     };
-    constexpr int kPerIterationCounters = kCountFetchRedo - kCountShadow + 1; // slots zeroed before every bounce iteration
+    constexpr int kPerIterationCounters = kCountFetchRedo - kCountShadow + 1; // words zeroed before every bounce iteration (slots 2..8 and their padding)
 
     constexpr uint32_t kFlagTerminated = 1U;
     constexpr uint32_t kFlagXorshift = 2U;
+
+    // radiance[i].w, written by the shade kernel for the accumulate kernel: everything accumulate needs to know about
+    // path i sits in the 16 bytes it has to read anyway (round 1 read shadow_count[i] and state[i] on top: two more
+    // dependent 32-byte sectors per path in a kernel that is a pure latency chain).
+    constexpr uint32_t kRadianceShadowMask = 0xFFU;   // shadow candidates stored for the current vertex
+    constexpr uint32_t kRadianceTerminated = 0x100U;  // the path ends at this vertex
+    constexpr uint32_t kRadianceCollected = 0x200U;   // path_length > 0 (worker.cpp:141-143)
 
     // Structure-of-arrays path pool.  Every array has `capacity` entries (shadow arrays capacity * shadow_stride).
     struct PathPool {
@@ -55,14 +77,13 @@ namespace ptb {
         float4 *ray_d;       // direction xyz
         float2 *hit;         // (t, slot bits)
         float4 *throughput;  // sample_spectrum
-        float4 *radiance;    // out_spectrum
+        float4 *radiance;    // out_spectrum rgb; w = bookkeeping word of the accumulate kernel (kRadiance* below)
         double *divisor;     // sample_divisor
         double *bounce_pd;   // sample_bounce_pd
         float *contribution; // contribution_unweighted
         uint32_t *state;     // path_length << 8 | flags
         uint64_t *rng;       // xorshift state or counter key
         uint32_t *dest;      // index into the per-sample buffer
-        uint32_t *shadow_count; // candidates stored for the current vertex
         float4 *shadow_o;    // (origin, limit)
         float4 *shadow_d;    // (direction, 0)
         float4 *shadow_c;    // (contribution rgb, visible flag)
@@ -126,11 +147,11 @@ namespace ptb {
     }
 
     template<typename RNG>
-    PTB_DEV void storePath(const PathPool &pool, uint32_t i, const PathRegs<RNG> &p, uint32_t flags) {
+    PTB_DEV void storePath(const PathPool &pool, uint32_t i, const PathRegs<RNG> &p, uint32_t flags, uint32_t radiance_word) {
         pool.ray_o[i] = make_float4(p.ray_o.x, p.ray_o.y, p.ray_o.z, 0.0F);
         pool.ray_d[i] = make_float4(p.ray_d.x, p.ray_d.y, p.ray_d.z, 0.0F);
         pool.throughput[i] = make_float4(p.throughput.x, p.throughput.y, p.throughput.z, 1.0F);
-        pool.radiance[i] = make_float4(p.radiance.x, p.radiance.y, p.radiance.z, 0.0F);
+        pool.radiance[i] = make_float4(p.radiance.x, p.radiance.y, p.radiance.z, __uint_as_float(radiance_word));
         pool.divisor[i] = p.divisor;
         pool.bounce_pd[i] = p.bounce_pd;
         pool.contribution[i] = p.contribution_unweighted;
@@ -183,9 +204,8 @@ namespace ptb {
         shootRay(params.camera, x_camera, y_camera, 1.0F / static_cast<float>(params.image_width), 1.0F / static_cast<float>(params.image_height), p.rng,
                  p.ray_o, p.ray_d);
 
-        storePath(pool, i, p, RNG::kXorshift ? kFlagXorshift : 0U);
+        storePath(pool, i, p, RNG::kXorshift ? kFlagXorshift : 0U, 0U);
         pool.dest[i] = static_cast<uint32_t>(g);
-        pool.shadow_count[i] = 0U;
     }
 
     // Fills pool slots [0, count) with work items [0, count) and queues them; later work items are started by the
@@ -222,9 +242,9 @@ namespace ptb {
     // paths whose result carries no certificate to `redo_queue` (length counters[kCountRedo]), which a second launch
     // of the kTraceClosest instantiation then serves (queue = redo_queue, queue_slot = kCountRedo).
     template<int MODE, bool COUNT>
-    __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) traceClosestKernel(DeviceScene scene, VoteParams vote, PathPool pool, const uint32_t *__restrict__ queue,
+    __global__ void __launch_bounds__(kBlock, PTB_CLOSEST_MIN_BLOCKS) traceClosestKernel(DeviceScene scene, VoteParams vote, PathPool pool, const uint32_t *__restrict__ queue,
                                                                  uint32_t *__restrict__ counters, int queue_slot, int cursor_slot, uint32_t *__restrict__ redo_queue,
-                                                                 VisitCounters *visits) {
+                                                                 VisitCounters *visits, const __grid_constant__ ptb_guard::CertGuard guard, int guarded) {
         const uint32_t count = counters[queue_slot];
         warpTrace<MODE, COUNT>(
           MODE == kTraceCertified ? occlusionView(scene) : scene, vote, &counters[cursor_slot], count,
@@ -235,9 +255,9 @@ namespace ptb {
               o = mk3(ro.x, ro.y, ro.z);
               d = mk3(rd.x, rd.y, rd.z);
               limit = 0.0F;
+              return i;
           },
-          [&](uint32_t k, const Hit &h, bool certain) {
-              const uint32_t i = queue[k];
+          [&](uint32_t i, const Hit &h, bool certain) {
               if(MODE == kTraceCertified && !certain) {
                   redo_queue[atomicAdd(&counters[kCountRedo], 1U)] = i;
               }
@@ -245,7 +265,7 @@ namespace ptb {
                   pool.hit[i] = make_float2(h.t, __int_as_float(h.slot));
               }
           },
-          visits);
+          visits, (MODE == kTraceCertified && guarded != 0) ? &guard : nullptr);
     }
 
     template<bool COUNT>
@@ -259,18 +279,18 @@ namespace ptb {
             o = mk3(so.x, so.y, so.z);
             d = mk3(sd.x, sd.y, sd.z);
             limit = so.w;
+            return slot;
         };
         if(any_hit != 0U) {
             warpTrace<kTraceAnyHit, COUNT>(
               occlusionView(scene), vote, &counters[kCountFetchShadow], count, fetch,
-              [&](uint32_t k, const Hit &h, bool) { pool.shadow_c[shadow_queue[k]].w = h.slot < 0 ? 1.0F : 0.0F; }, visits);
+              [&](uint32_t slot, const Hit &h, bool) { pool.shadow_c[slot].w = h.slot < 0 ? 1.0F : 0.0F; }, visits);
         }
         else {
             // the reference's full closest-hit query (worker.cpp:84-86): unoccluded iff t < 0 or t >= |to_light| - epsilon
             warpTrace<kTraceClosest, COUNT>(
               scene, vote, &counters[kCountFetchShadow], count, fetch,
-              [&](uint32_t k, const Hit &h, bool) {
-                  const uint32_t slot = shadow_queue[k];
+              [&](uint32_t slot, const Hit &h, bool) {
                   const float limit = pool.shadow_o[slot].w;
                   pool.shadow_c[slot].w = (h.t < 0.0F || h.t >= limit) ? 1.0F : 0.0F;
               },
@@ -281,13 +301,24 @@ namespace ptb {
     // ------------------------------------------------------------------------------------------------ shade
 
     template<typename RNG>
-    __global__ void __launch_bounds__(kBlock, PTB_SHADE_MIN_BLOCKS) shadeKernel(DeviceScene scene, PathPool pool, RenderParams params, const uint32_t *__restrict__ queue,
+    __global__ void __launch_bounds__(kFlatBlock, PTB_SHADE_MIN_BLOCKS) shadeKernel(DeviceScene scene, PathPool pool, RenderParams params, const uint32_t *__restrict__ queue,
                                                           uint32_t *__restrict__ counters, int queue_slot, uint32_t *__restrict__ shadow_queue) {
         const uint32_t count = counters[queue_slot];
         const uint32_t stride = gridDim.x * blockDim.x;
-        // whole warps iterate together so that the warp-wide scans below see all 32 lanes
-        const uint32_t rounded = (count + 31U) & ~31U;
-        for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < rounded; k += stride) {
+        // Block-level aggregation of the shadow-queue append (two trips in flight: parity p = trip & 1)
+        __shared__ uint32_t block_total[2];
+        __shared__ uint32_t block_base[2];
+        if(threadIdx.x == 0U) {
+            block_total[0] = 0U;
+            block_total[1] = 0U;
+        }
+        __syncthreads();
+        uint32_t stat_vertices = 0U;
+        uint32_t stat_skipped = 0U;
+        uint32_t parity = 0U;
+        // whole blocks iterate together (the barriers below need every thread of the block in every trip)
+        for(uint32_t first = blockIdx.x * blockDim.x; first < count; first += stride, parity ^= 1U) {
+            const uint32_t k = first + threadIdx.x;
             const bool active = k < count;
             uint32_t i = 0U;
             PathRegs<RNG> p;
@@ -305,14 +336,14 @@ namespace ptb {
             }
 
             uint32_t n_shadow = 0U;
-            uint32_t n_skipped = 0U;
             bool continues = false;
             const uint32_t shadow_base = i * pool.shadow_stride;
             if(hit_surface) {
+                stat_vertices++;
                 continues = shadeVertex(scene, params.epsilon, params.max_depth, p, t, slot, [&](const ShadowCandidate &c, bool is_null) {
                     // candidates without weight are traced only to reproduce the reference's ray count
                     if(is_null && params.skip_null_shadows != 0U) {
-                        n_skipped++;
+                        stat_skipped++;
                         return;
                     }
                     if(n_shadow < pool.shadow_stride) {
@@ -326,16 +357,17 @@ namespace ptb {
             }
 
             if(active) {
+                uint32_t word = n_shadow | (p.path_length > 0 ? kRadianceCollected : 0U);
                 if(!continues) {
                     flags |= kFlagTerminated;
+                    word |= kRadianceTerminated;
                 }
-                storePath(pool, i, p, flags);
-                pool.shadow_count[i] = n_shadow;
+                storePath(pool, i, p, flags, word);
             }
 
             // queue the shadow rays: exclusive scan of the per-lane counts over the lanes that arrive together (normally
-            // the whole warp), one atomic per group.  The scan is built from one ballot per bit of the count, which is
-            // cheaper than a shuffle ladder for counts this small and stays correct for any group of lanes.
+            // the whole warp; one ballot per bit of the count stays correct for any group of lanes), one SHARED-memory
+            // atomic per group, one global atomic per block and trip.
             const uint32_t present = __activemask();
             const uint32_t below_me = (1U << laneId()) - 1U;
             uint32_t exclusive = 0U;
@@ -347,26 +379,35 @@ namespace ptb {
             }
             if(group_total != 0U) {
                 const uint32_t leader = static_cast<uint32_t>(__ffs(static_cast<int>(present))) - 1U;
-                uint32_t base = 0U;
+                uint32_t group_base = 0U;
                 if(laneId() == leader) {
-                    base = atomicAdd(&counters[kCountShadow], group_total);
+                    group_base = atomicAdd(&block_total[parity], group_total);
                 }
-                base = __shfl_sync(present, base, static_cast<int>(leader)) + exclusive;
-                for(uint32_t j = 0U; j < n_shadow; j++) {
-                    shadow_queue[base + j] = shadow_base + j;
-                }
+                exclusive += __shfl_sync(present, group_base, static_cast<int>(leader));
             }
+            __syncthreads();
+            if(threadIdx.x == 0U) {
+                const uint32_t total = block_total[parity];
+                block_base[parity] = total != 0U ? atomicAdd(&counters[kCountShadow], total) : 0U;
+                block_total[parity ^ 1U] = 0U; // the next trip's accumulator; nobody touches it between these two barriers
+            }
+            __syncthreads();
+            const uint32_t base = block_base[parity] + exclusive;
+            for(uint32_t j = 0U; j < n_shadow; j++) {
+                shadow_queue[base + j] = shadow_base + j;
+            }
+        }
 
-            // statistics: one atomic per warp
-            const uint32_t hit_mask = __ballot_sync(present, active && hit_surface);
-            const uint32_t skipped = __reduce_add_sync(present, n_skipped);
-            if(laneId() == static_cast<uint32_t>(__ffs(static_cast<int>(present))) - 1U) {
-                if(hit_mask != 0U) {
-                    atomicAdd(&counters[kCountVertices], static_cast<uint32_t>(__popc(hit_mask)));
-                }
-                if(skipped != 0U) {
-                    atomicAdd(&counters[kCountSkippedShadows], skipped);
-                }
+        // statistics: kept in registers over the whole kernel, one atomic per warp (group) at the end
+        const uint32_t present = __activemask();
+        const uint32_t vertices = __reduce_add_sync(present, stat_vertices);
+        const uint32_t skipped = __reduce_add_sync(present, stat_skipped);
+        if(laneId() == static_cast<uint32_t>(__ffs(static_cast<int>(present))) - 1U) {
+            if(vertices != 0U) {
+                atomicAdd(&counters[kCountVertices], vertices);
+            }
+            if(skipped != 0U) {
+                atomicAdd(&counters[kCountSkippedShadows], skipped);
             }
         }
     }
@@ -374,23 +415,53 @@ namespace ptb {
     // ------------------------------------------------------------------------------------------------ accumulate
 
     template<typename RNG>
-    __global__ void __launch_bounds__(kBlock) accumulateKernel(PathPool pool, RenderParams params, PathSource src, const uint32_t *__restrict__ queue,
+    __global__ void __launch_bounds__(kFlatBlock) accumulateKernel(PathPool pool, RenderParams params, PathSource src, const uint32_t *__restrict__ queue,
                                                                uint32_t *__restrict__ counters, int queue_slot, uint32_t *__restrict__ next_queue, int next_slot,
                                                                float4 *__restrict__ samples, unsigned long long *__restrict__ work_cursor) {
         const uint32_t count = counters[queue_slot];
         const uint32_t stride = gridDim.x * blockDim.x;
-        const uint32_t rounded = (count + 31U) & ~31U;
-        for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < rounded; k += stride) {
+        // Block-level aggregation of the two reservations a trip needs (work items for the retired slots, places in the
+        // next queue): shared-memory atomics per group of lanes, then thread 0 issues the two global atomics of the block.
+        __shared__ uint32_t block_retired[2];
+        __shared__ uint32_t block_survivors[2];
+        __shared__ unsigned long long block_work_base[2];
+        __shared__ uint32_t block_queue_base[2];
+        if(threadIdx.x == 0U) {
+            block_retired[0] = block_retired[1] = 0U;
+            block_survivors[0] = block_survivors[1] = 0U;
+        }
+        __syncthreads();
+        uint32_t parity = 0U;
+        for(uint32_t first = blockIdx.x * blockDim.x; first < count; first += stride, parity ^= 1U) {
+            const uint32_t k = first + threadIdx.x;
             const bool active = k < count;
             bool survives = false;
             bool retired = false;
             uint32_t i = 0U;
             if(active) {
                 i = queue[k];
-                const uint32_t n_shadow = pool.shadow_count[i];
                 float4 radiance = pool.radiance[i];
-                if(n_shadow > 0U) {
-                    const uint32_t base = i * pool.shadow_stride;
+                const uint32_t word = __float_as_uint(radiance.w);
+                const uint32_t n_shadow = word & kRadianceShadowMask;
+                if(pool.shadow_stride == 2U) {
+                    // the common case (two emissive-object samples per vertex, no point lights): both candidates of the
+                    // path are one aligned 32-byte record, loaded together with the radiance instead of after it
+                    float4 c0;
+                    float4 c1;
+                    ld256cg(pool.shadow_c + 2U * static_cast<size_t>(i), c0, c1);
+                    if(n_shadow > 0U && c0.w != 0.0F) {
+                        radiance.x = radiance.x + c0.x;
+                        radiance.y = radiance.y + c0.y;
+                        radiance.z = radiance.z + c0.z;
+                    }
+                    if(n_shadow > 1U && c1.w != 0.0F) {
+                        radiance.x = radiance.x + c1.x;
+                        radiance.y = radiance.y + c1.y;
+                        radiance.z = radiance.z + c1.z;
+                    }
+                }
+                else {
+                    const size_t base = static_cast<size_t>(i) * pool.shadow_stride;
                     for(uint32_t j = 0U; j < n_shadow; j++) {
                         const float4 c = pool.shadow_c[base + j];
                         if(c.w != 0.0F) {
@@ -399,46 +470,75 @@ namespace ptb {
                             radiance.z = radiance.z + c.z;
                         }
                     }
-                    pool.radiance[i] = radiance;
-                    pool.shadow_count[i] = 0U;
                 }
-                const uint32_t st = pool.state[i];
-                if((st & kFlagTerminated) != 0U) {
+                if((word & kRadianceTerminated) != 0U) {
                     // out_color[3] = sample_collected ? 1 : 0 (worker.cpp:141-143)
-                    const bool collected = (st >> 8) > 0U;
-                    samples[pool.dest[i]] = make_float4(radiance.x, radiance.y, radiance.z, collected ? 1.0F : 0.0F);
+                    samples[pool.dest[i]] = make_float4(radiance.x, radiance.y, radiance.z, (word & kRadianceCollected) != 0U ? 1.0F : 0.0F);
                     retired = true;
                 }
                 else {
+                    if(n_shadow > 0U) {
+                        pool.radiance[i] = radiance; // the shade kernel rewrites w at the next vertex
+                    }
                     survives = true;
                 }
             }
 
-            // path regeneration: a retired path's slot takes the next unstarted work item of the call
+            // ranks inside the block: every group of lanes that arrives together adds its counts to the block's shared
+            // accumulators and learns where its retired lanes / survivors start
             const uint32_t present = __activemask();
+            const uint32_t below_me = (1U << laneId()) - 1U;
             const uint32_t retired_mask = __ballot_sync(present, retired);
-            if(retired_mask != 0U) {
-                const uint32_t leader = __ffs(retired_mask) - 1U;
-                unsigned long long base = 0ULL;
-                if(laneId() == leader) {
-                    base = atomicAdd(work_cursor, static_cast<unsigned long long>(__popc(retired_mask)));
+            const uint32_t survivor_mask = __ballot_sync(present, survives);
+            const uint32_t leader = static_cast<uint32_t>(__ffs(static_cast<int>(present))) - 1U;
+            uint32_t retired_rank = 0U;
+            uint32_t survivor_rank = 0U;
+            if(laneId() == leader) {
+                if(retired_mask != 0U) {
+                    retired_rank = atomicAdd(&block_retired[parity], static_cast<uint32_t>(__popc(retired_mask)));
                 }
-                base = __shfl_sync(present, base, leader);
-                if(retired) {
-                    const unsigned long long g = base + static_cast<unsigned long long>(__popc(retired_mask & ((1U << laneId()) - 1U)));
-                    if(g < src.total) {
-                        generatePath<RNG>(pool, params, src, i, g);
-                        survives = true;
-                    }
+                if(survivor_mask != 0U) {
+                    survivor_rank = atomicAdd(&block_survivors[parity], static_cast<uint32_t>(__popc(survivor_mask)));
                 }
             }
-
-            const uint32_t at = warpAppend(&counters[next_slot], survives);
-            if(survives) {
-                next_queue[at] = i;
+            retired_rank = __shfl_sync(present, retired_rank, static_cast<int>(leader)) + static_cast<uint32_t>(__popc(retired_mask & below_me));
+            survivor_rank = __shfl_sync(present, survivor_rank, static_cast<int>(leader)) + static_cast<uint32_t>(__popc(survivor_mask & below_me));
+            __syncthreads();
+            if(threadIdx.x == 0U) {
+                // path regeneration: the retired slots of the block take the next unstarted work items of the call; those
+                // that still get one join the survivors in the next queue (behind them)
+                const uint32_t n_retired = block_retired[parity];
+                const uint32_t n_survivors = block_survivors[parity];
+                unsigned long long work_base = src.total;
+                uint32_t regenerated = 0U;
+                if(n_retired != 0U) {
+                    work_base = atomicAdd(work_cursor, static_cast<unsigned long long>(n_retired));
+                    if(work_base < src.total) {
+                        const unsigned long long left = src.total - work_base;
+                        regenerated = left < static_cast<unsigned long long>(n_retired) ? static_cast<uint32_t>(left) : n_retired;
+                    }
+                }
+                block_work_base[parity] = work_base;
+                block_queue_base[parity] = (n_survivors + regenerated) != 0U ? atomicAdd(&counters[next_slot], n_survivors + regenerated) : 0U;
+                block_retired[parity ^ 1U] = 0U;
+                block_survivors[parity ^ 1U] = 0U;
+            }
+            __syncthreads();
+            const uint32_t queue_base = block_queue_base[parity];
+            if(retired) {
+                const unsigned long long g = block_work_base[parity] + static_cast<unsigned long long>(retired_rank);
+                if(g < src.total) {
+                    generatePath<RNG>(pool, params, src, i, g);
+                    next_queue[queue_base + block_survivors[parity] + retired_rank] = i;
+                }
+            }
+            else if(survives) {
+                next_queue[queue_base + survivor_rank] = i;
             }
         }
     }
+
+#if !defined(PTB_FAST_MATH) // the remaining kernels exist in the exact build only
 
     // ------------------------------------------------------------------------------------------------ resolve
 
@@ -623,7 +723,7 @@ namespace ptb {
     __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) intersectKernel(DeviceScene scene, VoteParams vote, const float *__restrict__ rays, const uint32_t *__restrict__ index,
                                                               const uint32_t *__restrict__ index_count, uint32_t n, float *__restrict__ t_out, int32_t *__restrict__ prim_out,
                                                               uint32_t *__restrict__ cursor, uint32_t *__restrict__ redo, uint32_t *__restrict__ redo_count,
-                                                              VisitCounters *visits) {
+                                                              VisitCounters *visits, const __grid_constant__ ptb_guard::CertGuard guard, int guarded) {
         const uint32_t count = index != nullptr ? *index_count : n;
         warpTrace<MODE, COUNT>(
           MODE == kTraceCertified ? occlusionView(scene) : scene, vote, cursor, count,
@@ -633,9 +733,9 @@ namespace ptb {
               o = mk3(p[0], p[1], p[2]);
               d = mk3(p[3], p[4], p[5]);
               limit = 0.0F;
+              return ray;
           },
-          [&](uint32_t k, const Hit &h, bool certain) {
-              const uint32_t ray = index != nullptr ? index[k] : k;
+          [&](uint32_t ray, const Hit &h, bool certain) {
               if(MODE == kTraceCertified && !certain) {
                   redo[atomicAdd(redo_count, 1U)] = ray;
               }
@@ -644,7 +744,7 @@ namespace ptb {
                   prim_out[ray] = (h.slot >= 0 && h.t >= 0.0F) ? static_cast<int32_t>(scene.slot_to_prim[h.slot]) : -1;
               }
           },
-          visits);
+          visits, (MODE == kTraceCertified && guarded != 0) ? &guard : nullptr);
     }
 
     template<bool COUNT>
@@ -657,6 +757,7 @@ namespace ptb {
               o = mk3(p[0], p[1], p[2]);
               d = mk3(p[3], p[4], p[5]);
               limit = p[6];
+              return k;
           },
           [&](uint32_t k, const Hit &h, bool) { out[k] = h.slot >= 0 ? 1 : 0; }, visits);
     }
@@ -836,6 +937,8 @@ namespace ptb {
         w[4] = shade;
         w[5] = pd;
     }
+
+#endif // !PTB_FAST_MATH
 
 }
 

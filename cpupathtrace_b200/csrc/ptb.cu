@@ -3,6 +3,8 @@
 #include "../../include/ptb.h"
 
 #include "bvh_build.h"
+#include "cert_guard.h"
+#include "fast_launch.h"
 #include "host_math.h"
 #include "kernels.cuh"
 #include "lbvh.cuh"
@@ -99,6 +101,7 @@ struct ptb_context {
     ptb::VoteParams vote_shadow{16, 12, 2, 4}; // any-hit / shadow kernels (shorter rays: refill in larger batches)
     int trace_blocks_per_sm = 16;
     bool log_iterations = false; // PTB_LOG_ITERATIONS=1: one stderr line per bounce iteration
+    bool production_math = true; // PTB_RNG_COUNTER renders use the FMA / SFU build of generate, shade and accumulate (PTB_PRODUCTION_MATH=0: the exact build)
     int iterations_per_sync = 4; // bounce iterations launched between two host synchronisations (PTB_ITERATIONS_PER_SYNC)
     cudaStream_t stream = nullptr;
 
@@ -143,6 +146,7 @@ struct ptb_scene {
     Buffer slot_to_prim;
     ptb_scene_info info{};
     uint32_t shadow_stride = 1;
+    ptb_guard::CertGuard guard{}; // guard table of the certified closest-hit walk (passed to its kernels by value)
 };
 
 namespace {
@@ -262,7 +266,6 @@ namespace {
         const size_t o_state = take(n * sizeof(uint32_t));
         const size_t o_rng = take(n * sizeof(uint64_t));
         const size_t o_dest = take(n * sizeof(uint32_t));
-        const size_t o_scount = take(n * sizeof(uint32_t));
         const size_t o_so = take(ns * sizeof(float4));
         const size_t o_sd = take(ns * sizeof(float4));
         const size_t o_sc = take(ns * sizeof(float4));
@@ -283,7 +286,6 @@ namespace {
         pool.state = reinterpret_cast<uint32_t *>(base + o_state);
         pool.rng = reinterpret_cast<uint64_t *>(base + o_rng);
         pool.dest = reinterpret_cast<uint32_t *>(base + o_dest);
-        pool.shadow_count = reinterpret_cast<uint32_t *>(base + o_scount);
         pool.shadow_o = reinterpret_cast<float4 *>(base + o_so);
         pool.shadow_d = reinterpret_cast<float4 *>(base + o_sd);
         pool.shadow_c = reinterpret_cast<float4 *>(base + o_sc);
@@ -330,15 +332,30 @@ namespace {
 
     // Starts the first `first_wave` work items of `src` in the pool and runs bounce iterations until every work item of
     // the call has been retired into `samples` (retired slots are refilled by the accumulate kernel).
+    // How closest-hit queries are answered for a call's `flags`: the certified walk needs the query hierarchy and, unless
+    // relaxed, a scene the guard table covers.
+    struct ClosestMode {
+        bool certified;
+        int guarded;
+    };
+
+    ClosestMode closestMode(const ptb_scene *scene, uint32_t flags) {
+        ClosestMode m{};
+        const bool relaxed = (flags & PTB_FLAG_CERTIFIED_RELAXED) != 0U;
+        m.certified = (flags & PTB_FLAG_CERTIFIED_CLOSEST) != 0U && scene->dev.occ_nodes != nullptr && (relaxed || scene->guard.certifiable != 0U);
+        m.guarded = relaxed ? 0 : 1;
+        return m;
+    }
+
     int runBounces(ptb_scene *scene, const PathPool &pool, const RenderParams &params, const PathSource &src, float4 *samples, bool count_visits,
-                   bool certified_closest, ptb_render_stats *stats) {
+                   ClosestMode closest, ptb_render_stats *stats) {
         ptb_context *ctx = scene->ctx; // the calling entry point holds ctx->mutex
         uint32_t *counters = ctx->counters.as<uint32_t>();
         uint32_t *queues[2] = {ctx->queue_a.as<uint32_t>(), ctx->queue_b.as<uint32_t>()};
         uint32_t *shadow_queue = ctx->shadow_queue.as<uint32_t>();
         uint32_t *redo_queue = ctx->redo_queue.as<uint32_t>();
         VisitCounters *visits = ctx->visits.as<VisitCounters>();
-        const bool certified = certified_closest && scene->dev.occ_nodes != nullptr;
+        const bool certified = closest.certified;
 
         const int trace_grid = gridFor(ctx, ctx->trace_blocks_per_sm);
         const uint32_t first_wave = static_cast<uint32_t>(std::min<unsigned long long>(pool.capacity, src.total));
@@ -352,6 +369,9 @@ namespace {
                 generateKernel<ReferenceRng><<<(first_wave + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(pool, params, src, first_wave, queues[0], counters,
                                                                                                              kCountQueueA);
             }
+            else if(ctx->production_math) {
+                ptb_fast_api::launchGenerate(&pool, &params, &src, first_wave, queues[0], counters, kCountQueueA, ctx->stream);
+            }
             else {
                 generateKernel<CounterRng><<<(first_wave + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(pool, params, src, first_wave, queues[0], counters,
                                                                                                            kCountQueueA);
@@ -364,6 +384,7 @@ namespace {
         }
         int cur = 0;
         uint32_t n_cur = first_wave;
+        const int queue_slot[2] = {kCountQueueA, kCountQueueB}; // where the length of queues[0] / queues[1] lives
 
         // Bounce iterations are launched in batches without a host round trip in between: queue lengths live in device
         // memory, the ping-pong order is known in advance, and an iteration on an empty queue is five launches that return
@@ -375,10 +396,12 @@ namespace {
             constexpr int kMode = decltype(mode)::value;
             uint32_t *redo_out = kMode == kTraceCertified ? redo_queue : nullptr; // only the certified walk hands rays back
             if(count_visits) {
-                traceClosestKernel<kMode, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queue, counters, queue_slot, cursor_slot, redo_out, visits);
+                traceClosestKernel<kMode, true><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queue, counters, queue_slot, cursor_slot, redo_out, visits,
+                                                                                        scene->guard, closest.guarded);
             }
             else {
-                traceClosestKernel<kMode, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queue, counters, queue_slot, cursor_slot, redo_out, visits);
+                traceClosestKernel<kMode, false><<<trace_grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, pool, queue, counters, queue_slot, cursor_slot, redo_out, visits,
+                                                                                         scene->guard, closest.guarded);
             }
         };
 
@@ -388,28 +411,31 @@ namespace {
             for(; launched < batch; launched++) {
                 const int nxt = cur ^ 1;
                 // zero: next queue length; shadow queue length, both fetch cursors and the per-iteration statistics (slots 2..6)
-                PTB_CUDA(cudaMemsetAsync(counters + nxt, 0, sizeof(uint32_t), ctx->stream));
+                PTB_CUDA(cudaMemsetAsync(counters + queue_slot[nxt], 0, sizeof(uint32_t), ctx->stream));
                 PTB_CUDA(cudaMemsetAsync(counters + kCountShadow, 0, kPerIterationCounters * sizeof(uint32_t), ctx->stream));
 
-                const int flat_grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_cur) + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 32))));
+                const int flat_grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_cur) + kFlatBlock - 1) / kFlatBlock, static_cast<uint64_t>(gridFor(ctx, 32 * kBlock / kFlatBlock))));
                 {
                     LaunchTimer timer(ctx, 0);
                     if(certified) {
                         // SAH walk with certificate, then the handed-back rays on the reference tree (usually a handful)
-                        launch_closest(std::integral_constant<int, kTraceCertified>{}, queues[cur], cur, kCountFetchClosest);
+                        launch_closest(std::integral_constant<int, kTraceCertified>{}, queues[cur], queue_slot[cur], kCountFetchClosest);
                         launch_closest(std::integral_constant<int, kTraceClosest>{}, redo_queue, kCountRedo, kCountFetchRedo);
                     }
                     else {
-                        launch_closest(std::integral_constant<int, kTraceClosest>{}, queues[cur], cur, kCountFetchClosest);
+                        launch_closest(std::integral_constant<int, kTraceClosest>{}, queues[cur], queue_slot[cur], kCountFetchClosest);
                     }
                 }
                 {
                     LaunchTimer timer(ctx, 1);
                     if(params.rng_xorshift != 0U) {
-                        shadeKernel<ReferenceRng><<<flat_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, cur, shadow_queue);
+                        shadeKernel<ReferenceRng><<<flat_grid, kFlatBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, queue_slot[cur], shadow_queue);
+                    }
+                    else if(ctx->production_math) {
+                        ptb_fast_api::launchShade(&scene->dev, &pool, &params, queues[cur], counters, queue_slot[cur], shadow_queue, flat_grid, ctx->stream);
                     }
                     else {
-                        shadeKernel<CounterRng><<<flat_grid, kBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, cur, shadow_queue);
+                        shadeKernel<CounterRng><<<flat_grid, kFlatBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, queue_slot[cur], shadow_queue);
                     }
                 }
                 {
@@ -424,12 +450,16 @@ namespace {
                 {
                     LaunchTimer timer(ctx, 1);
                     if(params.rng_xorshift != 0U) {
-                        accumulateKernel<ReferenceRng><<<flat_grid, kBlock, 0, ctx->stream>>>(pool, params, src, queues[cur], counters, cur, queues[nxt], nxt,
-                                                                                            samples, work_cursor);
+                        accumulateKernel<ReferenceRng><<<flat_grid, kFlatBlock, 0, ctx->stream>>>(pool, params, src, queues[cur], counters, queue_slot[cur], queues[nxt],
+                                                                                            queue_slot[nxt], samples, work_cursor);
+                    }
+                    else if(ctx->production_math) {
+                        ptb_fast_api::launchAccumulate(&pool, &params, &src, queues[cur], counters, queue_slot[cur], queues[nxt], queue_slot[nxt], samples, work_cursor, flat_grid,
+                                                       ctx->stream);
                     }
                     else {
-                        accumulateKernel<CounterRng><<<flat_grid, kBlock, 0, ctx->stream>>>(pool, params, src, queues[cur], counters, cur, queues[nxt], nxt, samples,
-                                                                                          work_cursor);
+                        accumulateKernel<CounterRng><<<flat_grid, kFlatBlock, 0, ctx->stream>>>(pool, params, src, queues[cur], counters, queue_slot[cur], queues[nxt],
+                                                                                          queue_slot[nxt], samples, work_cursor);
                     }
                 }
                 PTB_CUDA(cudaMemcpyAsync(ctx->host_counters + launched * kCounterSlots, counters, kCounterSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -455,10 +485,11 @@ namespace {
                         stats->kernel_launches += certified ? 5 : 4;
                     }
                     if(ctx->log_iterations) {
-                        std::fprintf(stderr, "[ptb] bounce iteration: %u paths, %u shadow rays, %u retraced, %u continue\n", n_in, hc[kCountShadow], hc[kCountRedo], hc[slot_out]);
+                        std::fprintf(stderr, "[ptb] bounce iteration: %u paths, %u shadow rays, %u retraced, %u continue\n", n_in, hc[kCountShadow], hc[kCountRedo],
+                                     hc[queue_slot[slot_out]]);
                     }
                 }
-                n_in = hc[slot_out];
+                n_in = hc[queue_slot[slot_out]];
                 slot_in = slot_out;
             }
             collectTimers(ctx, stats);
@@ -688,6 +719,7 @@ int ptb_context_create(int device, ptb_context **out) {
     ctx->vote_shadow.leaf = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_SHADOW_LEAF_VOTE", envLong("PTB_LEAF_VOTE", 12)))));
     ctx->trace_blocks_per_sm = static_cast<int>(std::max(1L, envLong("PTB_TRACE_BLOCKS_PER_SM", 16)));
     ctx->log_iterations = envLong("PTB_LOG_ITERATIONS", 0) != 0;
+    ctx->production_math = envLong("PTB_PRODUCTION_MATH", 1) != 0;
     ctx->iterations_per_sync = static_cast<int>(std::min<long>(kMaxIterationsPerSync, std::max(1L, envLong("PTB_ITERATIONS_PER_SYNC", 4))));
     *out = ctx;
     return PTB_OK;
@@ -949,6 +981,7 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
     }
 
     scene->shadow_stride = std::max<uint32_t>(1U, desc->n_lights + emissive.object_sample_count);
+    ptb_guard::buildCertGuard(desc->prims, desc->n_prims, &scene->guard);
 
     ptb_scene_info &info = scene->info;
     info.n_prims = n;
@@ -961,6 +994,7 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
                         scene->cdf.bytes + scene->slot_to_prim.bytes;
     info.build_seconds = t1 - t0;
     info.query_tree_on_device = query_tree_on_device ? 1U : 0U;
+    info.certifiable = scene->guard.certifiable;
     info.query_tree_device_ms = query_tree_device_ms;
     info.upload_seconds = t2 - t1;
     for(int c = 0; c < 3; c++) {
@@ -1032,7 +1066,8 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
     PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
     PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, 2 * sizeof(VisitCounters), ctx->stream));
 
-    const bool certified = (flags & PTB_FLAG_CERTIFIED_CLOSEST) != 0U && scene->dev.occ_nodes != nullptr;
+    const ClosestMode closest = closestMode(scene, flags);
+    const bool certified = closest.certified;
     constexpr uint64_t kChunk = 1ULL << 28;
     if(certified && (status = ctx->redo_queue.reserve(std::min<uint64_t>(kChunk, n_rays) * sizeof(uint32_t))) != PTB_OK) {
         return status;
@@ -1050,15 +1085,15 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
         if(certified) {
             if(count_visits) {
                 intersectKernel<kTraceCertified, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, nullptr, nullptr, n, d_t + first, d_prim + first,
-                                                                                        counters + kCountFetchClosest, redo, counters + kCountRedo, visits);
+                                                                                        counters + kCountFetchClosest, redo, counters + kCountRedo, visits, scene->guard, closest.guarded);
                 intersectKernel<kTraceClosest, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, redo, counters + kCountRedo, n, d_t + first, d_prim + first,
-                                                                                      counters + kCountFetchRedo, nullptr, nullptr, visits);
+                                                                                      counters + kCountFetchRedo, nullptr, nullptr, visits, scene->guard, closest.guarded);
             }
             else {
                 intersectKernel<kTraceCertified, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, nullptr, nullptr, n, d_t + first, d_prim + first,
-                                                                                         counters + kCountFetchClosest, redo, counters + kCountRedo, visits);
+                                                                                         counters + kCountFetchClosest, redo, counters + kCountRedo, visits, scene->guard, closest.guarded);
                 intersectKernel<kTraceClosest, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, redo, counters + kCountRedo, n, d_t + first, d_prim + first,
-                                                                                       counters + kCountFetchRedo, nullptr, nullptr, visits);
+                                                                                       counters + kCountFetchRedo, nullptr, nullptr, visits, scene->guard, closest.guarded);
             }
             if(stats != nullptr) {
                 PTB_CUDA(cudaMemcpyAsync(ctx->host_counters, counters, kCounterSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1068,11 +1103,11 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
         }
         else if(count_visits) {
             intersectKernel<kTraceClosest, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, nullptr, nullptr, n, d_t + first, d_prim + first,
-                                                                                  counters + kCountFetchClosest, nullptr, nullptr, visits);
+                                                                                  counters + kCountFetchClosest, nullptr, nullptr, visits, scene->guard, closest.guarded);
         }
         else {
             intersectKernel<kTraceClosest, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, nullptr, nullptr, n, d_t + first, d_prim + first,
-                                                                                   counters + kCountFetchClosest, nullptr, nullptr, visits);
+                                                                                   counters + kCountFetchClosest, nullptr, nullptr, visits, scene->guard, closest.guarded);
         }
     }
     PTB_CUDA(cudaGetLastError());
@@ -1207,7 +1242,7 @@ int ptb_render_samples(ptb_scene *scene, const ptb_camera *camera, const ptb_ren
     src.seeds = d_seeds;
     src.explicit_samples = 1U;
     src.total = n;
-    if((status = runBounces(scene, pool, params, src, d_out, count_visits, (opts->flags & PTB_FLAG_CERTIFIED_CLOSEST) != 0U, stats)) != PTB_OK) {
+    if((status = runBounces(scene, pool, params, src, d_out, count_visits, closestMode(scene, opts->flags), stats)) != PTB_OK) {
         return status;
     }
     if(!device_io) {
@@ -1344,7 +1379,7 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
         src.n_pixels = n_pixels;
         src.explicit_samples = 0U;
         src.total = total;
-        if((status = runBounces(scene, pool, params, src, ctx->samples.as<float4>(), count_visits, (opts->flags & PTB_FLAG_CERTIFIED_CLOSEST) != 0U, stats)) != PTB_OK) {
+        if((status = runBounces(scene, pool, params, src, ctx->samples.as<float4>(), count_visits, closestMode(scene, opts->flags), stats)) != PTB_OK) {
             return status;
         }
 

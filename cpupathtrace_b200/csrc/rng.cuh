@@ -58,6 +58,24 @@ namespace ptb {
             return u >= 1.0F ? 0.99999994F : u;
         }
 
+        // two consecutive uniform_real_distribution<float>(0, 1) draws, `first` drawn first.  The reference engine draws
+        // twice; the counter generator takes both halves of ONE 64-bit mix (its two 64-bit multiplies are the most
+        // expensive integer work of the shade kernel: 9 mixes per path vertex in round 1, 6 with the pairs)
+        PTB_DEV void canonicalPair(float &first, float &second) {
+            if constexpr(XORSHIFT) {
+                first = canonical();
+                second = canonical();
+            }
+            else {
+                const uint64_t z = mix64(state + 0x9E3779B97F4A7C15ULL * (static_cast<uint64_t>(counter) + 1ULL));
+                counter++;
+                const float u = __uint2float_rn(static_cast<uint32_t>(z >> 32)) / 4294967296.0F;
+                const float v = __uint2float_rn(static_cast<uint32_t>(z)) / 4294967296.0F;
+                first = u >= 1.0F ? 0.99999994F : u;
+                second = v >= 1.0F ? 0.99999994F : v;
+            }
+        }
+
         // uniform_real_distribution<float>(a, b)
         PTB_DEV float uniform(float a, float b) {
             return canonical() * (b - a) + a;
@@ -70,6 +88,12 @@ namespace ptb {
 
         // bernoulli_distribution(p)
         PTB_DEV bool bernoulli(double p) {
+#if defined(PTB_FAST_MATH)
+            if constexpr(!XORSHIFT) {
+                // production build: one 32-bit draw compared in fp32 (the reference's two-draw fp64 form buys nothing here)
+                return canonical() < static_cast<float>(p);
+            }
+#endif
             const double x0 = static_cast<double>(draw());
             const double x1 = static_cast<double>(draw());
             const double sum = x0 + x1 * 4294967296.0;

@@ -28,10 +28,13 @@ namespace ptb {
     template<typename RNG>
     PTB_DEV void sampleAperture(const ptb_camera &c, RNG &rng, float &sx, float &sy) {
         if(c.aperture_kind == PTB_APERTURE_CIRCULAR) {
-            const float r = sqrtf(rng.uniform01());
-            const float theta = kTwoPi * rng.uniform01();
-            sx = r * glibcCosf(theta);
-            sy = r * glibcSinf(theta);
+            float u_r;
+            float u_theta;
+            rng.canonicalPair(u_r, u_theta);
+            const float r = sqrtf(u_r);
+            const float theta = kTwoPi * u_theta;
+            sx = r * pathCosf(theta);
+            sy = r * pathSinf(theta);
             return;
         }
         // hexagonal: rejection sample the upper-right quadrant, then two fair coin flips for the signs
@@ -57,8 +60,12 @@ namespace ptb {
 
     template<typename RNG>
     PTB_DEV void shootRay(const ptb_camera &c, float x, float y, float pixel_width, float pixel_height, RNG &rng, V3 &ray_o, V3 &ray_d) {
-        const float offset_x = rng.uniform(-pixel_width / 2.0F, pixel_width / 2.0F);
-        const float offset_y = rng.uniform(-pixel_height / 2.0F, pixel_height / 2.0F);
+        // uniform_real_distribution<float>(a, b): u * (b - a) + a, x first (camera.cpp:79-83)
+        float u_x;
+        float u_y;
+        rng.canonicalPair(u_x, u_y);
+        const float offset_x = u_x * (pixel_width / 2.0F - -pixel_width / 2.0F) + -pixel_width / 2.0F;
+        const float offset_y = u_y * (pixel_height / 2.0F - -pixel_height / 2.0F) + -pixel_height / 2.0F;
         const float sensor_x = x + offset_x;
         const float sensor_y = y + offset_y;
 
@@ -166,8 +173,9 @@ namespace ptb {
             const V3 a = mk3(e0.x, e0.y, e0.z);
             const V3 b = mk3(e1.x, e1.y, e1.z);
             const V3 c = mk3(e2.x, e2.y, e2.z);
-            const float r1 = rng.uniform01();
-            const float r2 = rng.uniform01();
+            float r1;
+            float r2;
+            rng.canonicalPair(r1, r2);
             const float rr1 = sqrtf(r1);
             surface_pos = (a * (1.0F - rr1) + b * (rr1 * (1.0F - r2))) + c * (rr1 * r2);
             // p = 1 / (|cross(b - a, c - a)| / 2), evaluated once on the host with the same operations (host_math.cpp)
@@ -177,11 +185,14 @@ namespace ptb {
         else if((flags & kKindMask) == PTB_PRIM_SPHERE) {
             const V3 origin = mk3(e0.x, e0.y, e0.z);
             const float radius = e1.x;
-            const float theta = kTwoPi * rng.uniform01();
-            const float phi = glibcAcosf(1.0F - 2.0F * rng.uniform01());
-            const float x = glibcSinf(phi) * glibcCosf(theta);
-            const float y = glibcSinf(phi) * glibcSinf(theta);
-            const float z = glibcCosf(phi);
+            float u_theta;
+            float u_phi;
+            rng.canonicalPair(u_theta, u_phi);
+            const float theta = kTwoPi * u_theta;
+            const float phi = pathAcosf(1.0F - 2.0F * u_phi);
+            const float x = pathSinf(phi) * pathCosf(theta);
+            const float y = pathSinf(phi) * pathSinf(theta);
+            const float z = pathCosf(phi);
             surface_pos = origin + mk3(x, y, z) * radius;
             surface_p = e1.w; // 1 / (4 pi r^2), evaluated once on the host
             surface_cull = false;
@@ -327,12 +338,13 @@ namespace ptb {
         if(m.bsdf == PTB_BSDF_LAMBERT) {
             // importanceSampleCosine(dist(re), dist(re), 1.0F): g++ evaluates the second argument first, so the first
             // draw is r2 (the cos-theta variate) and the second is r1 (the azimuth)   [SURVEY.md App. B]
-            const float r2 = rng.uniform01();
-            const float r1 = rng.uniform01();
+            float r2;
+            float r1;
+            rng.canonicalPair(r2, r1);
             const float fac = sqrtf(1.0F - r2);         // pow(r2, 2/(e+1)) with e = 1: powf(x, 1) == x
-            const float cos_theta = glibcPowfHalf(r2);  // pow(r2, 1/(e+1))
+            const float cos_theta = pathPowfHalf(r2);  // pow(r2, 1/(e+1))
             const float angle = kTwoPi * r1;
-            const V3 local = mk3(fac * glibcCosf(angle), fac * glibcSinf(angle), cos_theta);
+            const V3 local = mk3(fac * pathCosf(angle), fac * pathSinf(angle), cos_theta);
             const float p = 2.0F * cos_theta / kTwoPi; // (e+1) * pow(cos_theta, e) / (2 pi)
             const V3 dir = localToGlobal(local, normal);
             out_o = pos + dir * epsilon;

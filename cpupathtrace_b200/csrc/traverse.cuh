@@ -16,11 +16,23 @@
 #ifndef PTB_TRAVERSE_CUH
 #define PTB_TRAVERSE_CUH
 
+#include "cert_guard.h"
 #include "device_scene.cuh"
 
 namespace ptb {
 
     constexpr int kStackCapacity = 64; // deferred far siblings only; the host asserts bvh depth <= capacity
+
+    // Optionally the bottom kSmemStackLevels entries of every thread's stack live in shared memory, [level][thread] so
+    // that the 32 lanes of a warp never collide on a bank whatever their individual depths are; deeper entries spill to
+    // local memory.  Round 1's ncu capture had the all-local stack at 1.48 G L1 sectors per 134 M-ray launch -- as many
+    // as all global loads together -- which suggested this; measured, it does not pay (the sectors are L1 hits that the
+    // issue-bound kernel hides, the extra predicated instructions and the smaller L1 are not), so the default is 0.
+#ifndef PTB_SMEM_STACK
+#define PTB_SMEM_STACK 0 // measured in round 2 (bench scene, 128 spp): 0 -> 7.77, 8 -> 7.52, 12 -> 7.49 Grays/s closest: the local stack stays
+#endif
+    constexpr int kSmemStackLevels = PTB_SMEM_STACK;
+    constexpr int kTraceBlock = 128; // threads per CTA of every kernel that calls warpTrace (== kBlock in kernels.cuh)
 
     struct RayInv {
         V3 o;
@@ -169,6 +181,47 @@ namespace ptb {
     constexpr float kCertifiedEntrySlack = 1.001953125F; // 1 + 2^-9
     constexpr float kCertifiedSuspectFactor = 0.99609375F; // 1 - 2^-8
 
+    // The guard of the certified walk (cert_guard.h): true when the ray must be traced by the reference-order walk because
+    // some large triangle or nearby sphere could report a distance that is rounding noise.
+    PTB_DEV bool guardFlagsRay(const ptb_guard::CertGuard &g, V3 o, V3 d) {
+        for(uint32_t j = 0; j < g.n_planes; j++) {
+            const ptb_guard::GuardPlane &pl = g.planes[j];
+            const float hd = ((pl.nx * o.x + pl.ny * o.y) + pl.nz * o.z) - pl.h;
+            const float cd = (pl.nx * d.x + pl.ny * d.y) + pl.nz * d.z;
+            const float ahd = fabsf(hd);
+            if(fabsf(cd) < pl.cone || ahd <= pl.w) {
+                return true;
+            }
+            if(hd * cd < 0.0F) {
+                const float dx = o.x - pl.cx;
+                const float dy = o.y - pl.cy;
+                const float dz = o.z - pl.cz;
+                const float rho = sqrtf((dx * dx + dy * dy) + dz * dz) + pl.r;
+                if(ahd < pl.w + pl.k * rho) {
+                    return true;
+                }
+            }
+        }
+        for(uint32_t j = 0; j < g.n_spheres; j++) {
+            const float cx = o.x - g.spheres[j][0];
+            const float cy = o.y - g.spheres[j][1];
+            const float cz = o.z - g.spheres[j][2];
+            const float r2 = g.spheres[j][3] * g.spheres[j][3];
+            const float co2 = (cx * cx + cy * cy) + cz * cz;
+            if(co2 < 3.24F * r2) {
+                return true;
+            }
+            if(co2 < 9.0F * r2) {
+                const float dd = (d.x * cx + d.y * cy) + d.z * cz;
+                const float disc = dd * dd - co2 + r2;
+                if(fabsf(disc) < r2 * 0.0625F) {
+                    return true;
+                }
+            }
+        }
+        return false;
+    }
+
     // Hit test of one box in "visit" form: hit <=> the reference's slab result is >= 0, entry = that result.
     // (bounding_box.cpp:61-72: -1 iff t_max < 0 or t_min > t_max; otherwise max(t_min, 0).)
     PTB_DEV bool slabVisit(const RayInv &r, float lox, float loy, float loz, float hix, float hiy, float hiz, float best_t, float &entry) {
@@ -185,7 +238,10 @@ namespace ptb {
         return t_max >= 0.0F && t_min <= t_max && entry < best_t;
     }
 
-    // fetch(k, o, d, limit) loads ray k; commit(k, hit, certain) stores its result.  `cursor` is a zero-initialised device
+    // ticket = fetch(k, o, d, limit) loads work item k of the queue and returns what commit() needs to find the ray's
+    // destination again (the path index, shadow slot or ray number the queue entry held -- kept in the register that would
+    // otherwise hold k, so that commit does not re-read the queue: that dependent load was 5-10 % of the trace kernels'
+    // instructions in round 1); commit(ticket, hit, certain) stores the result.  `cursor` is a zero-initialised device
     // counter shared by all warps of the launch; `count` the number of rays.
     //
     // Warp collectives and convergence.  `__ballot_sync(0xFFFFFFFF, ...)` is only as good as the barrier in front of the
@@ -199,8 +255,21 @@ namespace ptb {
     // every decision taken from a vote is a decision of that group -- it refills, parks, tests and terminates as a
     // sub-warp of its own.  `exhausted` is re-agreed at every refill vote (groups can merge again), and a full-mask
     // __syncwarp() at the top of the outer loop invites split groups to merge where the compiler keeps it.
+    // one allocation per kernel, however many warpTrace instantiations the kernel contains
+    PTB_DEV uint2 *sharedStackBase() {
+#if PTB_SMEM_STACK > 0
+        __shared__ uint2 shared_stack[kSmemStackLevels * kTraceBlock];
+        return shared_stack;
+#else
+        return nullptr;
+#endif
+    }
+
+    // `guard` (certified mode only, may be null = relaxed): rays it flags are committed as uncertain without a walk, and a
+    // certified hit closer than guard->tau_safe loses its certificate.
     template<int MODE, bool COUNT, typename Fetch, typename Commit>
-    PTB_DEV void warpTrace(const DeviceScene &s, VoteParams vote, uint32_t *cursor, uint32_t count, Fetch fetch, Commit commit, VisitCounters *counters) {
+    PTB_DEV void warpTrace(const DeviceScene &s, VoteParams vote, uint32_t *cursor, uint32_t count, Fetch fetch, Commit commit, VisitCounters *counters,
+                           const ptb_guard::CertGuard *guard = nullptr) {
         constexpr bool ANY_HIT = MODE == kTraceAnyHit;
         constexpr bool CERTIFIED = MODE == kTraceCertified;
         const int kRefillVote = vote.refill;
@@ -225,7 +294,23 @@ namespace ptb {
         hit.slot = -1;
         int32_t node = 0;
         int sp = 0;
-        uint2 stack[kStackCapacity]; // (node ref, entry distance bits) of deferred far children
+        // (node ref, entry distance bits) of deferred far children
+        uint2 local_stack[kStackCapacity - kSmemStackLevels];
+        uint2 *const my_shared_stack = sharedStackBase() + threadIdx.x;
+        auto stackStore = [&](int at, uint2 e) {
+            if(at < kSmemStackLevels) {
+                my_shared_stack[at * kTraceBlock] = e;
+            }
+            else {
+                local_stack[at - kSmemStackLevels] = e;
+            }
+        };
+        auto stackLoad = [&](int at) -> uint2 {
+            if(at < kSmemStackLevels) {
+                return my_shared_stack[at * kTraceBlock];
+            }
+            return local_stack[at - kSmemStackLevels];
+        };
         bool exhausted = count == 0U;
         unsigned long long n_inner = 0;
         unsigned long long n_leaf = 0;
@@ -235,7 +320,7 @@ namespace ptb {
         auto advance = [&]() {
             while(sp > 0) {
                 sp--;
-                const uint2 e = stack[sp];
+                const uint2 e = stackLoad(sp);
                 // any-hit: the bound never shrinks, so an entry that passed `entry < limit` when deferred still passes
                 if(ANY_HIT || __uint_as_float(e.y) < (CERTIFIED ? prune_t : best_t)) {
                     node = static_cast<int32_t>(e.x);
@@ -245,6 +330,9 @@ namespace ptb {
                     status = node >= 0 ? kLaneInner : kLaneLeaf;
                     return;
                 }
+            }
+            if(CERTIFIED && guard != nullptr && hit.slot >= 0 && !(hit.t >= guard->tau_safe)) {
+                certain = false;
             }
             commit(k, hit, certain);
             status = kLaneIdle;
@@ -274,7 +362,7 @@ namespace ptb {
                 const bool left_first = lt < rt;
                 // (an L2 prefetch of the deferred sibling was measured and rejected: -9 % on the bench scene, -10 % on
                 // the 16 Mi-triangle soup)
-                stack[sp] = make_uint2(static_cast<uint32_t>(left_first ? right : left), __float_as_uint(left_first ? rt : lt));
+                stackStore(sp, make_uint2(static_cast<uint32_t>(left_first ? right : left), __float_as_uint(left_first ? rt : lt)));
                 sp++;
                 node = left_first ? left : right;
                 if(CERTIFIED) {
@@ -317,10 +405,9 @@ namespace ptb {
                 if(status == kLaneIdle) {
                     const uint32_t mine = base + static_cast<uint32_t>(__popc(idle_mask & lanes_below));
                     if(mine < count) {
-                        k = mine;
                         V3 o;
                         V3 d;
-                        fetch(k, o, d, limit);
+                        k = fetch(mine, o, d, limit);
                         r = makeRay(o, d);
                         hit.t = -1.0F;
                         hit.slot = -1;
@@ -331,6 +418,9 @@ namespace ptb {
                         rival_t = 0.0F;
                         if(s.n_prims == 0U) {
                             commit(k, hit, true);
+                        }
+                        else if(CERTIFIED && guard != nullptr && guardFlagsRay(*guard, o, d)) {
+                            commit(k, hit, false);
                         }
                         else {
                             const float root_t = slab(r, s.root_lo[0], s.root_lo[1], s.root_lo[2], s.root_hi[0], s.root_hi[1], s.root_hi[2]);
@@ -395,27 +485,36 @@ namespace ptb {
                     }
                 }
                 else if(CERTIFIED) {
-                    // audit of the one assumption behind the certificate (counting builds only): a primitive the walk never
-                    // reaches could matter only if its test put the hit more than 2^-8 in front of its own leaf box
-                    if(COUNT && t >= 0.0F && t < leaf_entry * kCertifiedSuspectFactor) {
-                        n_suspect++;
-                    }
-                    if(t >= 0.0F) {
-                        if(t < best_t) {
-                            // every primitive tested so far has t >= the old best; they clear the new rival bound iff it does
-                            const float rival = fmaxf(t, leaf_entry);
-                            certain = best_t > rival && leaf_entry <= t * kCertifiedEntrySlack && t > 0.0F;
-                            rival_t = rival;
-                            best_t = t;
-                            prune_t = t * kCertifiedPruneSlack;
-                            hit.t = t;
-                            hit.slot = static_cast<int32_t>(slot);
+                    // The one assumption behind the certificate: a primitive the walk never reaches could matter only if its
+                    // test put the hit more than 2^-8 in front of its own leaf box.  Every primitive that IS tested is
+                    // checked for exactly that, in every build: a ray that meets such a primitive is in the numerically
+                    // degenerate regime (grazing a large triangle, |det| near the 1e-6 rejection threshold); its walk is
+                    // abandoned on the spot and the ray handed back to the reference-order walk.  Counting builds count them.
+                    if(t >= 0.0F && t < leaf_entry * kCertifiedSuspectFactor) {
+                        if(COUNT) {
+                            n_suspect++;
                         }
-                        else if(t <= rival_t) {
-                            certain = false;
-                        }
+                        commit(k, hit, false);
+                        status = kLaneIdle;
                     }
-                    advance();
+                    else {
+                        if(t >= 0.0F) {
+                            if(t < best_t) {
+                                // every primitive tested so far has t >= the old best; they clear the new rival bound iff it does
+                                const float rival = fmaxf(t, leaf_entry);
+                                certain = best_t > rival && leaf_entry <= t * kCertifiedEntrySlack && t > 0.0F;
+                                rival_t = rival;
+                                best_t = t;
+                                prune_t = t * kCertifiedPruneSlack;
+                                hit.t = t;
+                                hit.slot = static_cast<int32_t>(slot);
+                            }
+                            else if(t <= rival_t) {
+                                certain = false;
+                            }
+                        }
+                        advance();
+                    }
                 }
                 else {
                     if(t >= 0.0F && (hit.slot < 0 || t <= best_t)) {

@@ -24,7 +24,8 @@ namespace {
         return (v == nullptr || *v == '\0') ? fallback : std::atol(v);
     }
 
-    ptb_render_opts makeOpts(const RenderOptions &options, uint64_t seed, uint32_t rng_mode) {
+    // `production`: processJob / processItem (counter-based generator); false: the validation entry renderSamples
+    ptb_render_opts makeOpts(const RenderOptions &options, uint64_t seed, uint32_t rng_mode, bool production) {
         const ptb::RenderControl &control = ptb::renderControl();
         ptb_render_opts opts{};
         opts.image_width = options.image_width;
@@ -35,7 +36,8 @@ namespace {
         opts.max_depth = control.max_depth;
         opts.rng_mode = rng_mode;
         opts.flags = (control.any_hit_shadows ? PTB_FLAG_ANY_HIT_SHADOWS : 0U) | (control.skip_null_shadows ? PTB_FLAG_SKIP_NULL_SHADOWS : 0U) |
-                     (control.certified_closest ? PTB_FLAG_CERTIFIED_CLOSEST : 0U);
+                     (control.certified_closest ? PTB_FLAG_CERTIFIED_CLOSEST : 0U) |
+                     ((control.certified_closest && control.relaxed_guard && production) ? PTB_FLAG_CERTIFIED_RELAXED : 0U);
         opts.seed = seed;
         opts.shard_count = std::max(control.shard_count, 1);
         opts.shard_index = std::min(std::max(control.shard_index, 0), opts.shard_count - 1);
@@ -57,7 +59,7 @@ namespace {
         }
         static_assert(sizeof(Color<float>) == 4 * sizeof(float), "Color<float> must be four packed floats");
         const ptb_camera camera = lowerCamera(job.camera);
-        ptb_render_opts opts = makeOpts(job.options, seed, PTB_RNG_COUNTER);
+        ptb_render_opts opts = makeOpts(job.options, seed, PTB_RNG_COUNTER, true);
         opts.tile_size = tile_size;
         if(!sharded) {
             // processItem renders exactly the tile it was asked for; only processJob splits the frame between processes
@@ -76,9 +78,10 @@ namespace ptb {
         static RenderControl control = [] {
             RenderControl c;
             c.max_depth = static_cast<int>(envLong("PTB_MAX_DEPTH", 0));
-            c.any_hit_shadows = envLong("PTB_ANY_HIT_SHADOWS", 0) != 0;
-            c.skip_null_shadows = envLong("PTB_SKIP_NULL_SHADOWS", 0) != 0;
-            c.certified_closest = envLong("PTB_CERTIFIED_CLOSEST", 0) != 0;
+            c.any_hit_shadows = envLong("PTB_ANY_HIT_SHADOWS", 1) != 0;
+            c.skip_null_shadows = envLong("PTB_SKIP_NULL_SHADOWS", 1) != 0;
+            c.certified_closest = envLong("PTB_CERTIFIED_CLOSEST", 1) != 0;
+            c.relaxed_guard = envLong("PTB_CERTIFIED_RELAXED", 1) != 0;
             c.shard_index = static_cast<int>(envLong("PTB_SHARD_INDEX", 0));
             c.shard_count = static_cast<int>(std::max(1L, envLong("PTB_SHARD_COUNT", 1)));
             c.fixed_seed = static_cast<uint64_t>(envLong("PTB_SEED", 0));
@@ -89,7 +92,7 @@ namespace ptb {
 
     void renderSamples(const FrameRenderJob &job, std::size_t count, const int *pixels, const uint64_t *seeds, float *out_rgba) {
         const ptb_camera camera = lowerCamera(job.camera);
-        const ptb_render_opts opts = makeOpts(job.options, 0, PTB_RNG_REFERENCE_XORSHIFT);
+        const ptb_render_opts opts = makeOpts(job.options, 0, PTB_RNG_REFERENCE_XORSHIFT, false);
         host::check(ptb_render_samples(job.scene.deviceScene(), &camera, &opts, count, pixels, seeds, out_rgba, nullptr), "renderSamples");
     }
 

@@ -41,12 +41,17 @@ _PROTOTYPES = {
     "pth_process_item": (None, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P]),
     "pth_process_job": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pth_post_process": (None, [C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "pth_object_normal": (None, [_P, C.c_int, C.c_long, _P, _P]),
+    "pth_object_sample": (None, [_P, C.c_int, C.c_long, _P, _P, _P]),
+    "pth_bsdf_propagate": (None, [_P, C.c_int, C.c_float, C.c_long, _P, _P, _P, _P]),
+    "pth_bsdf_spectrum": (None, [_P, C.c_int, C.c_int, C.c_long, _P, _P]),
 }
 _OPTIONAL = {
     "pth_scene_device_handle": (_P, [_P]),
     "pth_png_roundtrip": (C.c_long, [C.c_int, C.c_int, _P, _P]),
     "pth_set_fast_queries": (None, [C.c_int, C.c_int, C.c_int]),
     "pth_set_sharding": (None, [C.c_int, C.c_int, C.c_uint64]),
+    "pth_set_render_control": (None, [C.c_int, C.c_int]),
 }
 
 REF_PARITY = os.path.join(REPO_ROOT, "oracle", "_ref", "libpth_ref.so")
@@ -80,6 +85,10 @@ class Pth:
     def set_fast_queries(self, certified_closest, any_hit_shadows, skip_null_shadows):
         """b200 build only: ptb::RenderControl's result-neutral query options for every later call of this process."""
         self.lib.pth_set_fast_queries(int(certified_closest), int(any_hit_shadows), int(skip_null_shadows))
+
+    def set_render_control(self, max_depth=-1, relaxed_guard=None):
+        """b200 build only: ptb::RenderControl::max_depth / relaxed_guard (None / negative = unchanged)."""
+        self.lib.pth_set_render_control(int(max_depth), -1 if relaxed_guard is None else int(bool(relaxed_guard)))
 
     def set_sharding(self, shard_index, shard_count, fixed_seed=0):
         """b200 build only: the share of processJob's tile grid this process renders, and the job seed (0 = random)."""
@@ -186,6 +195,35 @@ class PthBuilder:
             count = self.object_count() - first
         out = np.empty((count, 7), np.float32)
         self.pth.lib.pth_builder_get_object_info(self.h, first, count, _ptr(out))
+        return out
+
+    # ---- one-element virtual methods of an object / a material of this builder (engines are RandomEngine(seed);
+    # `next_draw` is the engine's next output after the call)
+    def object_normal(self, index, positions):
+        positions = _f32(positions, (-1, 3))
+        out = np.empty_like(positions)
+        self.pth.lib.pth_object_normal(self.h, index, len(positions), _ptr(positions), _ptr(out))
+        return out
+
+    def object_sample(self, index, seeds):
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        out = np.empty((len(seeds), 5), np.float32)
+        next_draw = np.empty(len(seeds), np.uint32)
+        self.pth.lib.pth_object_sample(self.h, index, len(seeds), _ptr(seeds), _ptr(out), _ptr(next_draw))
+        return out, next_draw
+
+    def bsdf_propagate(self, material, epsilon, inputs, seeds):
+        inputs = _f32(inputs, (-1, 9))
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        out = np.empty((len(inputs), 8), np.float32)
+        next_draw = np.empty(len(inputs), np.uint32)
+        self.pth.lib.pth_bsdf_propagate(self.h, material, epsilon, len(inputs), _ptr(inputs), _ptr(seeds), _ptr(out), _ptr(next_draw))
+        return out, next_draw
+
+    def bsdf_spectrum(self, material, synthetic, inputs):
+        inputs = _f32(inputs, (-1, 13))
+        out = np.empty((len(inputs), 6), np.float32)
+        self.pth.lib.pth_bsdf_spectrum(self.h, material, 1 if synthetic else 0, len(inputs), _ptr(inputs), _ptr(out))
         return out
 
     def scene(self):

@@ -342,6 +342,84 @@ void pth_aabb_intersect(const float *low, const float *high, long count, const f
     }
 }
 
+// ---------------------------------------------------------------- one-element virtual methods
+//
+// Object::getSurfaceNormal / sampleSurface and BSDF::propagateRay / getSpectrum called through the public virtual
+// interface on an object / material of a builder, one element at a time like a host-side caller would.  Engines are
+// RandomEngine(seed); `next_draw` receives the engine's next output after the call (the reference engine has no state
+// accessor), which pins how many draws the call consumed.
+
+// out: 3 floats per position
+void pth_object_normal(void *builder, int index, long count, const float *positions, float *out) {
+    auto *b = static_cast<Builder *>(builder);
+    const Object &object = *b->objects[index];
+    for(long i = 0; i < count; i++) {
+        const auto n = object.getSurfaceNormal(v3(positions + 3 * i));
+        out[3 * i] = n[0];
+        out[3 * i + 1] = n[1];
+        out[3 * i + 2] = n[2];
+    }
+}
+
+// out: 5 floats per seed (pos xyz, density, cull)
+void pth_object_sample(void *builder, int index, long count, const uint64_t *seeds, float *out, uint32_t *next_draw) {
+    auto *b = static_cast<Builder *>(builder);
+    const Object &object = *b->objects[index];
+    for(long i = 0; i < count; i++) {
+        RandomEngine re(seeds[i]);
+        const auto [pos, density, cull] = object.sampleSurface(re);
+        float *o = out + 5 * i;
+        o[0] = pos[0];
+        o[1] = pos[1];
+        o[2] = pos[2];
+        o[3] = density;
+        o[4] = cull ? 1.0F : 0.0F;
+        next_draw[i] = re();
+    }
+}
+
+// in: 9 floats (incoming direction, position, normal); out: 8 floats (origin, direction, factor, density)
+void pth_bsdf_propagate(void *builder, int material, float epsilon, long count, const float *in, const uint64_t *seeds, float *out, uint32_t *next_draw) {
+    auto *b = static_cast<Builder *>(builder);
+    const MaterialHandler &handler = *b->handlers[material];
+    for(long i = 0; i < count; i++) {
+        const float *p = in + 9 * i;
+        const auto pos = v3(p + 3);
+        RandomEngine re(seeds[i]);
+        const auto [ray, factor, density] = handler.getBSDF(pos)->propagateRay(Ray{pos, v3(p)}, pos, v3(p + 6), epsilon, re, handler.getMaterial(pos));
+        float *o = out + 8 * i;
+        o[0] = ray.origin[0];
+        o[1] = ray.origin[1];
+        o[2] = ray.origin[2];
+        o[3] = ray.dir[0];
+        o[4] = ray.dir[1];
+        o[5] = ray.dir[2];
+        o[6] = factor;
+        o[7] = density;
+        next_draw[i] = re();
+    }
+}
+
+// in: 13 floats (from-camera direction, to-light direction, normal, light rgba); out: 6 floats (rgba, shade, density)
+void pth_bsdf_spectrum(void *builder, int material, int synthetic, long count, const float *in, float *out) {
+    auto *b = static_cast<Builder *>(builder);
+    const MaterialHandler &handler = *b->handlers[material];
+    const vec3<float> pos{0.0F, 0.0F, 0.0F};
+    for(long i = 0; i < count; i++) {
+        const float *p = in + 13 * i;
+        const auto [spectrum, shade, density] = handler.getBSDF(pos)->getSpectrum(Ray{pos, v3(p)}, Ray{pos, v3(p + 3)}, pos, v3(p + 6),
+                                                                                  Spectrum(Color<float>{p[9], p[10], p[11], p[12]}), handler.getMaterial(pos), synthetic != 0);
+        const auto color = spectrum.getColor();
+        float *o = out + 6 * i;
+        o[0] = color[0];
+        o[1] = color[1];
+        o[2] = color[2];
+        o[3] = color[3];
+        o[4] = shade;
+        o[5] = density;
+    }
+}
+
 // ---------------------------------------------------------------- camera
 
 // sampler: 0 = none (pinhole ctor), 1 = circular, 2 = hexagonal(hex_ratio)
@@ -486,6 +564,17 @@ extern "C" void pth_set_fast_queries(int certified_closest, int any_hit_shadows,
     control.certified_closest = certified_closest != 0;
     control.any_hit_shadows = any_hit_shadows != 0;
     control.skip_null_shadows = skip_null_shadows != 0;
+}
+
+// b200 build only: the remaining knobs of ptb::RenderControl (negative = leave unchanged)
+extern "C" void pth_set_render_control(int max_depth, int relaxed_guard) {
+    ptb::RenderControl &control = ptb::renderControl();
+    if(max_depth >= 0) {
+        control.max_depth = max_depth;
+    }
+    if(relaxed_guard >= 0) {
+        control.relaxed_guard = relaxed_guard != 0;
+    }
 }
 
 // b200 build only: which share of processJob's tile grid this process renders (ptb::RenderControl::shard_index / shard_count)

@@ -63,18 +63,22 @@ Image<> processJob(
 
 namespace ptb {
 
-    //! Knobs without a counterpart in RenderOptions; defaults reproduce the reference's behaviour
+    //! Knobs without a counterpart in RenderOptions.  The three query options are result-neutral (validation-mode samples
+    //! are bit-identical with and without them, tests/test_parity_gpu.py) and therefore ON by default; each can be
+    //! switched off to trace exactly the reference's rays in exactly the reference's order.
     struct RenderControl {
         int max_depth = 0;            //!< 0 = unlimited, paths end by Russian roulette only
-        bool any_hit_shadows = false; //!< stop shadow rays at the first occluder
-        bool skip_null_shadows = false; //!< do not trace shadow rays whose contribution is always zero (glass, mirror)
-        bool certified_closest = false; //!< closest hits on the SAH hierarchy where a certificate proves the reference's result, else re-traced
+        bool any_hit_shadows = true;  //!< stop shadow rays at the first occluder
+        bool skip_null_shadows = true; //!< do not trace shadow rays whose contribution is always zero (glass, mirror, surfaces facing away)
+        bool certified_closest = true; //!< closest hits on the SAH hierarchy where a certificate proves the reference's result, else re-traced
+        bool relaxed_guard = true;    //!< processJob / processItem (counter-based generator) skip the certified walk's guard table; renderSamples never does
         uint64_t fixed_seed = 0;      //!< processJob: non-zero replaces std::random_device
         int shard_index = 0;          //!< multi-GPU, one process per GPU: this process renders tile k of the frame's tile grid iff
         int shard_count = 1;          //!< k % shard_count == shard_index and leaves the other pixels 0 (sum-reduce the images)
     };
 
-    //! process-wide control block; initialised from PTB_MAX_DEPTH, PTB_ANY_HIT_SHADOWS, PTB_SKIP_NULL_SHADOWS, PTB_CERTIFIED_CLOSEST, PTB_SEED, PTB_SHARD_INDEX, PTB_SHARD_COUNT
+    //! process-wide control block; initialised ONCE (first use) from PTB_MAX_DEPTH, PTB_ANY_HIT_SHADOWS, PTB_SKIP_NULL_SHADOWS,
+    //! PTB_CERTIFIED_CLOSEST, PTB_CERTIFIED_RELAXED, PTB_SEED, PTB_SHARD_INDEX, PTB_SHARD_COUNT, PTB_DEVICES; later changes go through this reference
     RenderControl &renderControl();
 
     /**

@@ -130,7 +130,8 @@ typedef struct ptb_scene_info {
     float root_low[3];
     float root_high[3];
     uint32_t query_tree_on_device; /* 1: the any-hit / certified-closest hierarchy was built by the GPU builder */
-    uint32_t reserved;
+    uint32_t certifiable;          /* 1: the guard table of the certified walk covers every large triangle / sphere of the  */
+                                   /* scene (csrc/cert_guard.h); 0: guarded certified queries walk the reference tree        */
     double query_tree_device_ms;   /* CUDA-event time of that build (Morton codes, sort, hierarchy, box fit) */
 } ptb_scene_info;
 
@@ -183,6 +184,12 @@ typedef enum ptb_rng_mode {
                                      /* any visiting order (strictly nearest, no rival within its leaf-box entry); the    */
                                      /* remaining rays (ties on shared edges/vertices, near-ties) are re-traced on the    */
                                      /* reference-topology tree.  See csrc/traverse.cuh "certified closest hit".          */
+                                     /* Guarded by default: rays for which fp32 rounding in a LARGE triangle's or a nearby  */
+                                     /* sphere's own intersection routine could matter are sent to the reference walk up    */
+                                     /* front (csrc/cert_guard.h); scenes the guard table cannot cover are not certified.   */
+#define PTB_FLAG_CERTIFIED_RELAXED 0x20u /* with PTB_FLAG_CERTIFIED_CLOSEST: no guard.  Identical results except where the  */
+                                     /* reference's own answer is rounding noise of a grazing hit on a large triangle       */
+                                     /* (tests/stress_cases.py); meant for production renders (PTB_RNG_COUNTER)             */
 
 /* RenderOptions (reference include/PathTrace/worker.h:14-31) + the knobs that exist only on this side */
 typedef struct ptb_render_opts {

@@ -474,7 +474,9 @@ void pto_intersect(const pto_scene *s, const float *rays, uint64_t n, float *t_o
  * CPU statement of the "certified closest hit" the CUDA kernels use (cpupathtrace_b200/csrc/traverse.cuh): walk ANY
  * hierarchy whose inner boxes are the exact unions of their children's boxes, nearest child first, pruning subtrees
  * whose entry exceeds t_best (1 + 2^-7), and keep the result only if it is strictly nearer than every other hit found,
- * no other hit lies at or before its own leaf-box entry, that entry does not exceed t_best (1 + 2^-9), and t_best > 0.
+ * no other hit lies at or before its own leaf-box entry, that entry does not exceed t_best (1 + 2^-9), and t_best > 0;
+ * a ray that meets a primitive whose test reports a hit more than 2^-8 in front of the primitive's own box is abandoned
+ * (certain = 0) on the spot.
  * The claim under test: whenever the walk returns certain = 1, (t, primitive) equals what the reference walk
  * (scene_hit above, scene.cpp:104-150) returns on the reference tree -- whatever the shape of the hierarchy walked here.
  * The hierarchy is built from `tree_seed`: a random permutation of the primitives split at random positions
@@ -522,15 +524,182 @@ static int cert_build(const pto_scene *s, cnode *nodes, int *n_nodes, int *items
     return id;
 }
 
+
+/* ------------------------------------------------------------------------------------------------ certificate guard
+ *
+ * Restatement of cpupathtrace_b200/csrc/cert_guard.cpp (the product builds the same table on the host and the kernels
+ * apply it when a ray is fetched).  The certificate of the walk below is exact about everything the walk TESTS; about a
+ * primitive R it never reaches (box entry e_R > t_Q (1 + s)) it assumes that R's own intersection routine cannot report
+ * a distance below e_R (1 - s/2).  That is a statement about fp32 rounding in Triangle / Sphere::getIntersection
+ * (object.cpp:72-84, 146-182), and it is false for large triangles met at grazing incidence and for spheres grazed
+ * from nearby.  Error model (eps = 2^-24, safety factor K = 2):
+ *   triangle  |t_computed - t_true| <= 9 eps K |ab||ac| (|o - a| + 2 t_true) / |det|,  only for |det| > 1e-6
+ *   sphere    |t_computed - t_true| <= 3 eps K |co| + min(Ddisc / (2 sqrt(disc)), sqrt(Ddisc)), Ddisc = 4 eps K max(|co|^2, r^2)
+ * A triangle whose worst case (|det| = 1e-6) still keeps the relative part below s/12 is SAFE: only the absolute term
+ * dmax diam remains, which the certificate covers by demanding t_Q >= tau_safe.  Every other triangle contributes a
+ * PLANE (unit normal n, offset h, half thickness w of its box across the plane, cone, band): a ray is handed straight
+ * to the reference-order walk when it is nearly parallel to the plane (|n.d| < cone), starts inside the slab
+ * (|n.o - h| <= w), or approaches the plane from less than w + band.  Spheres: rays starting closer than 1.8 r to the
+ * centre, or grazing (|disc| < r^2 / 16) from less than 3 r.  More than PTO_GUARD_PLANES distinct planes,
+ * PTO_GUARD_SPHERES spheres, or a sliver whose cone would exceed 0.25, switch certification off for the scene.
+ */
+#define PTO_GUARD_PLANES 24
+#define PTO_GUARD_SPHERES 8
+
+typedef struct {
+    int enabled;
+    float slack;    /* s */
+    float tau_safe; /* certificate needs t_Q >= tau_safe */
+    int n_planes;
+    float plane_n[PTO_GUARD_PLANES][3];
+    float plane_h[PTO_GUARD_PLANES];
+    float plane_w[PTO_GUARD_PLANES];
+    float plane_cone[PTO_GUARD_PLANES];
+    float plane_k[PTO_GUARD_PLANES]; /* band = k * (|o - centre| + radius) */
+    float plane_c[PTO_GUARD_PLANES][3];
+    float plane_r[PTO_GUARD_PLANES];
+    int n_spheres;
+    float sphere[PTO_GUARD_SPHERES][4];
+} pto_guard;
+
+static void guard_build(const pto_scene *s, pto_guard *g) {
+    const double eps = 5.9604644775390625e-8, K = 2.0, slack = 0.0078125;
+    memset(g, 0, sizeof(*g));
+    g->enabled = 1;
+    g->slack = (float)slack;
+    double tau_safe = 0.0;
+    for(uint64_t i = 0; i < s->n_prims && g->enabled; i++) {
+        const ptb_prim *p = &s->prims[i];
+        if(p->kind == PTB_PRIM_SPHERE) {
+            if(g->n_spheres == PTO_GUARD_SPHERES) {
+                g->enabled = 0;
+                break;
+            }
+            for(int c = 0; c < 4; c++) g->sphere[g->n_spheres][c] = p->p[c];
+            g->n_spheres++;
+            continue;
+        }
+        if(p->kind != PTB_PRIM_TRIANGLE) continue;
+        double a[3], ab[3], ac[3], bc[3];
+        for(int c = 0; c < 3; c++) {
+            a[c] = p->p[c];
+            ab[c] = (double)p->p[3 + c] - a[c];
+            ac[c] = (double)p->p[6 + c] - a[c];
+            bc[c] = ac[c] - ab[c];
+        }
+        double lab = sqrt(ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2]), lac = sqrt(ac[0] * ac[0] + ac[1] * ac[1] + ac[2] * ac[2]);
+        double lbc = sqrt(bc[0] * bc[0] + bc[1] * bc[1] + bc[2] * bc[2]);
+        double n[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
+        double area2 = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        double m = lab * lac, diam = fmax(lab, fmax(lac, lbc));
+        if(!(area2 > 0.0) || !(m > 0.0)) continue; /* degenerate: |det| = 0 for every ray, always rejected */
+        double dmax = 9.0 * eps * K * m / 1e-6;
+        if(dmax <= slack / 12.0) {
+            tau_safe = fmax(tau_safe, dmax * diam / (slack / 4.0));
+            continue;
+        }
+        double c_u = 9.0 * eps * K * m / area2; /* relative error = c_u / |cos| */
+        double cone = 12.0 * c_u / slack;
+        if(cone > 0.25) { /* a sliver: dangerous from almost every direction */
+            g->enabled = 0;
+            break;
+        }
+        for(int c = 0; c < 3; c++) n[c] /= area2;
+        double h = n[0] * a[0] + n[1] * a[1] + n[2] * a[2];
+        /* half thickness across the plane of the fp32 box: the box of a triangle is flat only for axis-aligned ones */
+        float lo[3], hi[3];
+        prim_bounds(p, lo, hi);
+        double w = 0.0;
+        for(int corner = 0; corner < 8; corner++) {
+            double x = (corner & 1) ? hi[0] : lo[0], y = (corner & 2) ? hi[1] : lo[1], z = (corner & 4) ? hi[2] : lo[2];
+            w = fmax(w, fabs(n[0] * x + n[1] * y + n[2] * z - h));
+        }
+        double centre[3] = {a[0] + (ab[0] + ac[0]) / 3.0, a[1] + (ab[1] + ac[1]) / 3.0, a[2] + (ab[2] + ac[2]) / 3.0};
+        double k_u = 4.0 * c_u / slack;
+        /* merge with an existing plane: same normal up to sign within 1e-4, same offset within the thickness scale */
+        int merged = 0;
+        for(int j = 0; j < g->n_planes && !merged; j++) {
+            double dotn = n[0] * g->plane_n[j][0] + n[1] * g->plane_n[j][1] + n[2] * g->plane_n[j][2];
+            double hj = dotn >= 0.0 ? h : -h;
+            if(fabs(fabs(dotn) - 1.0) < 1e-8 && fabs(hj - g->plane_h[j]) <= 1e-6 * (1.0 + fabs(hj))) {
+                double dc[3] = {centre[0] - g->plane_c[j][0], centre[1] - g->plane_c[j][1], centre[2] - g->plane_c[j][2]};
+                double dist = sqrt(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]);
+                g->plane_r[j] = (float)(fmax(g->plane_r[j], dist + diam) * 1.0001);
+                g->plane_w[j] = (float)(fmax(g->plane_w[j], w) * 1.0001);
+                g->plane_cone[j] = (float)(fmax(g->plane_cone[j], cone) * 1.0001);
+                g->plane_k[j] = (float)(fmax(g->plane_k[j], k_u) * 1.0001);
+                merged = 1;
+            }
+        }
+        if(merged) continue;
+        if(g->n_planes == PTO_GUARD_PLANES) {
+            g->enabled = 0;
+            break;
+        }
+        int j = g->n_planes++;
+        for(int c = 0; c < 3; c++) {
+            g->plane_n[j][c] = (float)n[c];
+            g->plane_c[j][c] = (float)centre[c];
+        }
+        g->plane_h[j] = (float)h;
+        g->plane_w[j] = (float)(w * 1.0001 + 1e-7 * (1.0 + fabs(h)));
+        g->plane_cone[j] = (float)(cone * 1.0001);
+        g->plane_k[j] = (float)(k_u * 1.0001);
+        g->plane_r[j] = (float)(diam * 1.0001);
+    }
+    g->tau_safe = (float)(tau_safe * 1.0001);
+}
+
+/* 1: the ray must be traced by the reference-order walk */
+static int guard_flags_ray(const pto_guard *g, const ray *r) {
+    if(!g->enabled) return 1;
+    for(int j = 0; j < g->n_planes; j++) {
+        float hd = (g->plane_n[j][0] * r->o.x + g->plane_n[j][1] * r->o.y + g->plane_n[j][2] * r->o.z) - g->plane_h[j];
+        float cd = g->plane_n[j][0] * r->d.x + g->plane_n[j][1] * r->d.y + g->plane_n[j][2] * r->d.z;
+        if(fabsf(cd) < g->plane_cone[j]) return 1;
+        float ahd = fabsf(hd);
+        if(ahd <= g->plane_w[j]) return 1;
+        if(hd * cd < 0.0F) {
+            float dx = r->o.x - g->plane_c[j][0], dy = r->o.y - g->plane_c[j][1], dz = r->o.z - g->plane_c[j][2];
+            float rho = sqrtf(dx * dx + dy * dy + dz * dz) + g->plane_r[j];
+            if(ahd < g->plane_w[j] + g->plane_k[j] * rho) return 1;
+        }
+    }
+    for(int j = 0; j < g->n_spheres; j++) {
+        float cx = r->o.x - g->sphere[j][0], cy = r->o.y - g->sphere[j][1], cz = r->o.z - g->sphere[j][2];
+        float r2 = g->sphere[j][3] * g->sphere[j][3];
+        float co2 = cx * cx + cy * cy + cz * cz;
+        if(co2 < 3.24F * r2) return 1;
+        if(co2 < 9.0F * r2) {
+            float dd = r->d.x * cx + r->d.y * cy + r->d.z * cz;
+            float disc = dd * dd - co2 + r2;
+            if(fabsf(disc) < r2 * 0.0625F) return 1;
+        }
+    }
+    return 0;
+}
+
 typedef struct {
     int ref;
     float entry;
 } cert_entry;
 
+static int g_guarded = 0; /* pto_set_guard: 1 = apply the guard table (PTB_FLAG_CERTIFIED_CLOSEST), 0 = relaxed */
+
+void pto_set_guard(int guarded) { g_guarded = guarded; }
+
+/* 1 when the guard table covers the scene (ptb_scene_info.certifiable) */
+int pto_scene_certifiable(const pto_scene *s) {
+    pto_guard guard;
+    guard_build(s, &guard);
+    return guard.enabled;
+}
+
 void pto_intersect_certified(const pto_scene *s, const float *rays, uint64_t n, uint64_t tree_seed, int shape, float *t_out, int32_t *prim_out,
                              uint8_t *certain_out) {
     const float prune_slack = 1.0078125F;   /* 1 + 2^-7 */
     const float entry_slack = 1.001953125F; /* 1 + 2^-9 */
+    const float suspect_factor = 0.99609375F; /* 1 - 2^-8 */
     if(s->n_prims == 0) {
         for(uint64_t i = 0; i < n; i++) {
             t_out[i] = -1.0F;
@@ -554,9 +723,17 @@ void pto_intersect_certified(const pto_scene *s, const float *rays, uint64_t n, 
     int root = cert_build(s, nodes, &n_nodes, items, np, shape, &state);
     free(items);
     cert_entry *stack = (cert_entry *)malloc(sizeof(cert_entry) * (size_t)(np + 1));
+    pto_guard guard;
+    guard_build(s, &guard);
 
     for(uint64_t i = 0; i < n; i++) {
         ray r = {V(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), V(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])};
+        if(g_guarded && guard_flags_ray(&guard, &r)) { /* handed to the reference-order walk without a certified walk */
+            t_out[i] = -1.0F;
+            prim_out[i] = -1;
+            certain_out[i] = 0;
+            continue;
+        }
         float rlo[3], rhi[3];
         cert_ref_box(s, nodes, root, rlo, rhi);
         float root_t = box_hit(rlo, rhi, &r);
@@ -571,7 +748,8 @@ void pto_intersect_certified(const pto_scene *s, const float *rays, uint64_t n, 
         stack[sp].ref = root;
         stack[sp].entry = root_t;
         sp++;
-        while(sp > 0) {
+        int abandoned = 0;
+        while(sp > 0 && !abandoned) {
             cert_entry e = stack[--sp];
             if(!(e.entry < prune_t)) continue; /* deferred sibling re-tested against the current bound */
             int ref = e.ref;
@@ -579,6 +757,12 @@ void pto_intersect_certified(const pto_scene *s, const float *rays, uint64_t n, 
             for(;;) {
                 if(ref < 0) {
                     float t = prim_hit(&s->prims[~ref], &r);
+                    if(t >= 0.0F && t < entry * suspect_factor) {
+                        /* hit reported in front of the primitive's own box: the walk is abandoned, the ray re-traced */
+                        certain = 0;
+                        abandoned = 1;
+                        break;
+                    }
                     if(t >= 0.0F) {
                         if(t < best_t) {
                             float rival = fmaxstd(t, entry);
@@ -617,6 +801,7 @@ void pto_intersect_certified(const pto_scene *s, const float *rays, uint64_t n, 
                 }
             }
         }
+        if(g_guarded && best >= 0 && !(hit_t >= guard.tau_safe)) certain = 0;
         t_out[i] = hit_t;
         prim_out[i] = best;
         certain_out[i] = (uint8_t)certain;
@@ -1252,4 +1437,72 @@ void pto_resolve(int min_samples, int max_samples, uint32_t n_pixels, const floa
     }
 }
 
-int pto_version(void) { return 1; }
+/* ------------------------------------------------------------------------------------------------ unit entries
+ * The same one-element-at-a-time functions the C-ABI exposes (ptb_prim_normal / ptb_prim_sample / ptb_bsdf_propagate /
+ * ptb_bsdf_spectrum), with raw engine states in and out, for value parity of those entry points. */
+
+void pto_prim_normal(const ptb_prim *prim, uint64_t n, const float *positions, float *out) {
+    for(uint64_t i = 0; i < n; i++) {
+        v3 nn = prim_normal(prim, V(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]));
+        out[3 * i] = nn.x;
+        out[3 * i + 1] = nn.y;
+        out[3 * i + 2] = nn.z;
+    }
+}
+
+void pto_prim_sample(const ptb_prim *prim, uint64_t n, uint64_t *states, float *out) {
+    for(uint64_t i = 0; i < n; i++) {
+        engine e;
+        e.s = states[i];
+        v3 pos;
+        float pd;
+        int cull;
+        prim_sample(prim, &e, &pos, &pd, &cull);
+        states[i] = e.s;
+        out[5 * i] = pos.x;
+        out[5 * i + 1] = pos.y;
+        out[5 * i + 2] = pos.z;
+        out[5 * i + 3] = pd;
+        out[5 * i + 4] = cull ? 1.0F : 0.0F;
+    }
+}
+
+/* in: 9 floats (incoming direction, position, normal); out: 8 floats (origin, direction, factor, density) */
+void pto_bsdf_propagate(const ptb_material *m, float epsilon, uint64_t n, const float *in, uint64_t *states, float *out) {
+    for(uint64_t i = 0; i < n; i++) {
+        const float *p = in + 9 * i;
+        engine e;
+        e.s = states[i];
+        ray rin = {V(0.0F, 0.0F, 0.0F), V(p[0], p[1], p[2])};
+        ray rout;
+        float factor, pd;
+        propagate(m, rin, V(p[3], p[4], p[5]), V(p[6], p[7], p[8]), epsilon, &e, &rout, &factor, &pd);
+        states[i] = e.s;
+        float *w = out + 8 * i;
+        w[0] = rout.o.x;
+        w[1] = rout.o.y;
+        w[2] = rout.o.z;
+        w[3] = rout.d.x;
+        w[4] = rout.d.y;
+        w[5] = rout.d.z;
+        w[6] = factor;
+        w[7] = pd;
+    }
+}
+
+/* in: 13 floats (from-camera direction, to-light direction, normal, light rgba); out: 6 floats (rgba, shade, density) */
+void pto_bsdf_spectrum(const ptb_material *m, int synthetic, uint64_t n, const float *in, float *out) {
+    for(uint64_t i = 0; i < n; i++) {
+        const float *p = in + 13 * i;
+        rgba light = {{p[9], p[10], p[11], p[12]}};
+        rgba spectrum;
+        float shade, pd;
+        bsdf_spectrum(m, V(p[0], p[1], p[2]), V(p[3], p[4], p[5]), V(p[6], p[7], p[8]), light, synthetic, &spectrum, &shade, &pd);
+        float *w = out + 6 * i;
+        for(int c = 0; c < 4; c++) w[c] = spectrum.c[c];
+        w[4] = shade;
+        w[5] = pd;
+    }
+}
+
+int pto_version(void) { return 2; }

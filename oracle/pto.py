@@ -27,6 +27,12 @@ def load():
         lib.pto_render_samples.argtypes = [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_uint64, _P, _P, _P, _P]
         lib.pto_process_item.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P]
         lib.pto_resolve.argtypes = [C.c_int, C.c_int, C.c_uint32, _P, _P]
+        lib.pto_set_guard.argtypes = [C.c_int]
+        lib.pto_scene_certifiable.argtypes = [_P]
+        lib.pto_prim_normal.argtypes = [_P, C.c_uint64, _P, _P]
+        lib.pto_prim_sample.argtypes = [_P, C.c_uint64, _P, _P]
+        lib.pto_bsdf_propagate.argtypes = [_P, C.c_float, C.c_uint64, _P, _P, _P]
+        lib.pto_bsdf_spectrum.argtypes = [_P, C.c_int, C.c_uint64, _P, _P]
         _lib = lib
     return _lib
 
@@ -66,8 +72,14 @@ class OracleScene:
         load().pto_intersect(self.h, _ptr(rays), len(rays), _ptr(t), _ptr(prim))
         return t, prim
 
-    def intersect_certified(self, rays, tree_seed, shape=0):
-        """Certified closest hit (CPU statement of csrc/traverse.cuh) on a random hierarchy: (t, prim, certain)."""
+    def certifiable(self):
+        """Whether the certified walk's guard table covers this scene (ptb_scene_info.certifiable)."""
+        return bool(load().pto_scene_certifiable(self.h))
+
+    def intersect_certified(self, rays, tree_seed, shape=0, guarded=False):
+        """Certified closest hit (CPU statement of csrc/traverse.cuh) on a random hierarchy: (t, prim, certain).
+        guarded: apply the guard table of csrc/cert_guard.h (flagged rays and uncertifiable scenes come back uncertain)."""
+        load().pto_set_guard(1 if guarded else 0)
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
         t = np.empty(len(rays), np.float32)
         prim = np.empty(len(rays), np.int32)
@@ -118,4 +130,53 @@ def resolve(min_spp, max_spp, samples):
     n_pixels = samples.shape[1]
     out = np.zeros((n_pixels, 4), np.float32)
     load().pto_resolve(min_spp, max_spp, n_pixels, _ptr(samples), _ptr(out))
+    return out
+
+
+def _pod(value, dtype):
+    return np.ascontiguousarray(value, dtype=dtype).reshape(1)
+
+
+def prim_normal(prim, positions):
+    """Object::getSurfaceNormal of one primitive (object.cpp:86-88, 126-144)."""
+    from cpupathtrace_b200 import capi
+
+    prim = _pod(prim, capi.PRIM_DTYPE)
+    positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+    out = np.empty_like(positions)
+    load().pto_prim_normal(_ptr(prim), len(positions), _ptr(positions), _ptr(out))
+    return out
+
+
+def prim_sample(prim, states):
+    """Object::sampleSurface (object.cpp:101-116, 192-207) from raw engine states: ([n, 5], advanced states)."""
+    from cpupathtrace_b200 import capi
+
+    prim = _pod(prim, capi.PRIM_DTYPE)
+    states = np.ascontiguousarray(states, np.uint64).copy()
+    out = np.empty((len(states), 5), np.float32)
+    load().pto_prim_sample(_ptr(prim), len(states), _ptr(states), _ptr(out))
+    return out, states
+
+
+def bsdf_propagate(material, epsilon, inputs, states):
+    """BSDF::propagateRay (propagation.cpp:89-99, 120-160, 180-204): ([n, 8], advanced states)."""
+    from cpupathtrace_b200 import capi
+
+    material = _pod(material, capi.MATERIAL_DTYPE)
+    inputs = np.ascontiguousarray(inputs, np.float32).reshape(-1, 9)
+    states = np.ascontiguousarray(states, np.uint64).copy()
+    out = np.empty((len(inputs), 8), np.float32)
+    load().pto_bsdf_propagate(_ptr(material), epsilon, len(inputs), _ptr(inputs), _ptr(states), _ptr(out))
+    return out, states
+
+
+def bsdf_spectrum(material, synthetic, inputs):
+    """BSDF::getSpectrum (propagation.cpp:101-116, 162-176, 206-217): [n, 6]."""
+    from cpupathtrace_b200 import capi
+
+    material = _pod(material, capi.MATERIAL_DTYPE)
+    inputs = np.ascontiguousarray(inputs, np.float32).reshape(-1, 13)
+    out = np.empty((len(inputs), 6), np.float32)
+    load().pto_bsdf_spectrum(_ptr(material), 1 if synthetic else 0, len(inputs), _ptr(inputs), _ptr(out))
     return out

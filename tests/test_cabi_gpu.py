@@ -19,10 +19,13 @@ def _scene(ctx, g):
 
 
 @pytest.mark.parametrize("name", GOLDEN_SCENES)
-@pytest.mark.parametrize("flags", [0, capi.PTB_FLAG_CERTIFIED_CLOSEST], ids=["reference_tree", "certified_sah"])
+@pytest.mark.parametrize("flags", [0, capi.PTB_FLAG_CERTIFIED_CLOSEST, capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_CERTIFIED_RELAXED],
+                         ids=["reference_tree", "certified_guarded", "certified_relaxed"])
 def test_golden_hits(ctx, name, flags):
     """Golden closest hits of the unmodified reference (a third of the rays aimed at shared vertices / edges), through
-    the reference-topology walk and through the certified SAH walk + re-trace of the rays without a certificate."""
+    the reference-topology walk, through the guarded certified query (these coarse test scenes are outside the guard
+    table's reach, so it must fall back to the reference walk) and through the relaxed certified SAH walk + re-trace of
+    the rays without a certificate."""
     g = load_golden("hits", name)
     scene = _scene(ctx, g)
     t, prim, stats = scene.intersect(g["rays"], flags=flags)
@@ -31,12 +34,13 @@ def test_golden_hits(ctx, name, flags):
     assert np.array_equal(t[hit], g["t"][hit])
     assert (t[~hit] < 0).all()
     assert stats.closest_rays == len(g["rays"]) and stats.kernel_launches >= 1
-    if flags:
+    if flags & capi.PTB_FLAG_CERTIFIED_RELAXED:
         # the tie cases must have been handed back, and only a minority of all rays
         assert stats.closest_rays_retraced < len(g["rays"]) // 2
         assert stats.closest_rays_retraced > 0 or name == "advanced"  # (three primitives without a shared edge)
     else:
-        assert stats.closest_rays_retraced == 0
+        # the golden scenes' triangles are far too coarse for the guard table: guarded certification is off for them
+        assert stats.closest_rays_retraced == 0 and (flags == 0 or scene.info().certifiable == 0)
     scene.close()
 
 
@@ -116,17 +120,19 @@ def test_fresh_inputs_against_oracle(ctx):
     assert stats_fast.shadow_rays + stats_fast.shadow_rays_skipped == stats.shadow_rays and stats_fast.shadow_rays_skipped > 0
 
     # certified closest hits (SAH walk + re-trace without certificate): same hits, same samples, same ray counts
-    t_c, prim_c, stats_c = scene.intersect(rays, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST)
+    relaxed = capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_CERTIFIED_RELAXED
+    t_c, prim_c, stats_c = scene.intersect(rays, flags=relaxed)
     assert np.array_equal(prim_c, prim_o) and np.array_equal(t_c[hit], t_o[hit]) and (t_c[~hit] < 0).all()
     assert stats_c.closest_rays_retraced < len(rays) // 100
-    cert = capi.render_opts(160, 100, 1, 1, 1e-3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST)
+    cert = capi.render_opts(160, 100, 1, 1, 1e-3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT, flags=relaxed)
     got_cert, stats_cert = scene.render_samples(camera, cert, pixels, seeds)
     assert np.array_equal(got_cert, want)
     assert stats_cert.closest_rays == stats.closest_rays and stats_cert.shadow_rays == stats.shadow_rays
-    all_fast = capi.render_opts(160, 100, 1, 1, 1e-3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT,
-                                flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_ANY_HIT_SHADOWS | capi.PTB_FLAG_SKIP_NULL_SHADOWS)
-    got_all, _ = scene.render_samples(camera, all_fast, pixels, seeds)
-    assert np.array_equal(got_all, want)
+    for closest in (relaxed, capi.PTB_FLAG_CERTIFIED_CLOSEST):
+        all_fast = capi.render_opts(160, 100, 1, 1, 1e-3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT,
+                                    flags=closest | capi.PTB_FLAG_ANY_HIT_SHADOWS | capi.PTB_FLAG_SKIP_NULL_SHADOWS)
+        got_all, _ = scene.render_samples(camera, all_fast, pixels, seeds)
+        assert np.array_equal(got_all, want)
 
     # a depth cap only truncates: samples whose path is shorter than the cap are unchanged
     capped = capi.render_opts(160, 100, 1, 1, 1e-3, max_depth=3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT)
@@ -217,21 +223,25 @@ def test_unit_entries_match_oracle(ctx):
     assert np.array_equal(t_unit[entered], t_scene[entered])
     single.close()
 
-    # Object::getSurfaceNormal / sampleSurface, BSDF::propagateRay / getSpectrum: shapes, unit length, engine advance
-    pos = rng.uniform(-1, 1, size=(100, 3)).astype(np.float32)
-    normals = ctx.prim_normal(prim, pos)
-    assert np.allclose(np.linalg.norm(normals, axis=1), 1.0, atol=1e-5)
-    surf, st = ctx.prim_sample(prim, capi.xorshift_state(seeds[:100]))
-    assert np.isfinite(surf).all() and (surf[:, 3] > 0).all() and (st != capi.xorshift_state(seeds[:100])).all()
-    for material in g["materials"][:6]:
-        n = np.tile(np.array([0.0, 1.0, 0.0], np.float32), (100, 1))
-        d = rng.normal(size=(100, 3)).astype(np.float32)
-        d[:, 1] = -np.abs(d[:, 1]) - 0.1
-        d /= np.linalg.norm(d, axis=1, keepdims=True)
-        out, st = ctx.bsdf_propagate(material, 1e-3, np.concatenate([d, pos, n], axis=1), capi.xorshift_state(seeds[:100]))
-        assert np.allclose(np.linalg.norm(out[:, 3:6], axis=1), 1.0, atol=1e-4) and (out[:, 7] > 0).all()
-        spec = ctx.bsdf_spectrum(material, True, np.concatenate([d, out[:, 3:6], n, np.ones((100, 4), np.float32)], axis=1))
-        assert np.isfinite(spec).all() and ((spec[:, 5] == 0) | (int(material["bsdf"]) == 0)).all()
+    # Object::getSurfaceNormal / sampleSurface and BSDF::propagateRay / getSpectrum: value parity with the oracle
+    # restatement (itself pinned to the reference's virtual methods by tests/test_oracle.py), bit for bit, engine states
+    # included -- the entry points' argument packing and state write-back, not only the device functions behind them
+    import unit_cases as uc
+
+    x = uc.inputs()
+    states = capi.xorshift_state(x["seeds"])
+    for unit_prim in uc.prims():
+        assert np.array_equal(ctx.prim_normal(unit_prim, x["positions"]), pto.prim_normal(unit_prim, x["positions"]), equal_nan=True)
+        got, after = ctx.prim_sample(unit_prim, states)
+        want, after_want = pto.prim_sample(unit_prim, states)
+        assert np.array_equal(got, want) and np.array_equal(after, after_want) and (after != states).all()
+    for material in uc.materials():
+        got, after = ctx.bsdf_propagate(material, 1e-3, x["propagate"], states)
+        want, after_want = pto.bsdf_propagate(material, 1e-3, x["propagate"], states)
+        assert np.array_equal(got, want, equal_nan=True) and np.array_equal(after, after_want)
+        assert (after != states).all() or int(material["bsdf"]) == capi.PTB_BSDF_MIRROR  # the mirror draws nothing
+        for synthetic in (False, True):
+            assert np.array_equal(ctx.bsdf_spectrum(material, synthetic, x["spectrum"]), pto.bsdf_spectrum(material, synthetic, x["spectrum"]))
     scene.close()
 
 
@@ -334,8 +344,16 @@ def test_full_size_scene_properties(ctx, ref):
     t_ref, id_ref = spec.build(ref).intersect(rays[sub])
     assert np.array_equal(id_ref, prim[sub]) and np.array_equal(t_ref[t_ref >= 0], t[sub][t_ref >= 0])
 
-    # certified SAH walk: all 4 M results identical to the reference-topology walk, at a fraction of the node fetches
-    t_c, prim_c, stats_c = scene.intersect(rays, flags=capi.PTB_FLAG_COUNT_VISITS | capi.PTB_FLAG_CERTIFIED_CLOSEST)
+    # certified SAH walk: all 4 M results identical to the reference-topology walk, at a fraction of the node fetches.
+    # Guarded (the default): the scene's 27 large triangles and its sphere fit the guard table; the rays the guard flags
+    # (heading for a wall from centimetres away, grazing, near the sphere) go to the reference walk up front.
+    assert info.certifiable == 1
+    t_g, prim_g, stats_g = scene.intersect(rays, flags=capi.PTB_FLAG_COUNT_VISITS | capi.PTB_FLAG_CERTIFIED_CLOSEST)
+    assert np.array_equal(prim_g, prim) and np.array_equal(t_g[hit], t[hit]) and (t_g[~hit] < 0).all()
+    assert stats_g.inner_visits < stats.inner_visits * 2 // 3 and stats_g.closest_rays_retraced < len(rays) // 3
+    print(f"guarded certified walk: {stats_g.closest_rays_retraced / len(rays):.2%} of the rays re-traced, {stats_g.inner_visits / len(rays):.1f} inner fetches per ray")
+    # relaxed (production renders): no guard
+    t_c, prim_c, stats_c = scene.intersect(rays, flags=capi.PTB_FLAG_COUNT_VISITS | capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_CERTIFIED_RELAXED)
     assert np.array_equal(prim_c, prim) and np.array_equal(t_c[hit], t[hit]) and (t_c[~hit] < 0).all()
     assert stats_c.inner_visits < stats.inner_visits // 2
     assert stats_c.closest_rays_retraced < len(rays) // 1000
@@ -359,10 +377,15 @@ def test_full_size_scene_properties(ctx, ref):
     seeds = rng.integers(1, 2**63 - 1, n_samples, dtype=np.int64).astype(np.uint64)
     plain = capi.render_opts(1920, 1080, 1, 1, 1e-3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT)
     fast = capi.render_opts(1920, 1080, 1, 1, 1e-3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT,
-                            flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_ANY_HIT_SHADOWS | capi.PTB_FLAG_SKIP_NULL_SHADOWS)
+                            flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_CERTIFIED_RELAXED | capi.PTB_FLAG_ANY_HIT_SHADOWS | capi.PTB_FLAG_SKIP_NULL_SHADOWS)
+    guarded = capi.render_opts(1920, 1080, 1, 1, 1e-3, rng_mode=capi.PTB_RNG_REFERENCE_XORSHIFT,
+                               flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_ANY_HIT_SHADOWS | capi.PTB_FLAG_SKIP_NULL_SHADOWS)
     want, stats_plain = scene.render_samples(camera, plain, pixels, seeds)
     got, stats_fast = scene.render_samples(camera, fast, pixels, seeds)
     assert np.array_equal(got, want) and (want[:, 3] == 1).mean() > 0.9
+    got_guarded, stats_guarded = scene.render_samples(camera, guarded, pixels, seeds)
+    assert np.array_equal(got_guarded, want) and stats_guarded.closest_rays_retraced < stats_guarded.closest_rays // 2
+    print(f"guarded path samples: {stats_guarded.closest_rays_retraced / stats_guarded.closest_rays:.2%} of the closest-hit rays re-traced")
     assert stats_fast.closest_rays == stats_plain.closest_rays and stats_fast.path_vertices == stats_plain.path_vertices
     assert stats_fast.shadow_rays + stats_fast.shadow_rays_skipped == stats_plain.shadow_rays
     lbvh = capi.Scene(ctx, prims, mats, lights, bvh_mode=capi.PTB_BVH_REFERENCE_GPU_QUERY_TREE)
@@ -379,4 +402,48 @@ def test_full_size_scene_properties(ctx, ref):
     occ_before, _ = scene.occluded(before)
     h = hit[:n]
     assert occ_beyond[h].all() and not occ_before[h].any()
+    scene.close()
+
+
+def test_certified_walk_on_adversarial_geometry(ctx):
+    """VERDICT r1 W1.  (1) Slivers 40 units long and 1e-4..1e-2 wide, stacks of near-coplanar large triangles, rays grazing
+    them with |det| swept across the 1e-6 rejection threshold of Triangle::getIntersection (object.cpp:146-182): there the
+    reference's own answer can be cancellation noise (a "hit" far in front of the triangle's bounding box), which a walk
+    that prunes by distance never sees.  The guard table cannot cover such a scene, so the guarded certified query must
+    fall back to the reference walk -- and equal it bit for bit; the relaxed walk is allowed to differ (and the test
+    reports how often).  (2) A scene the guard does cover (large planes + finely tessellated sheet + sphere): guarded and
+    reference walks must agree bit for bit on grazing and random rays, with a real share of the rays certified."""
+    import stress_cases as sc
+
+    prims, mats, lights = sc.sliver_scene()
+    scene = capi.Scene(ctx, prims, mats, lights)
+    assert scene.info().certifiable == 0
+    rays = sc.grazing_rays(prims, 400_000)
+    t, prim, _ = scene.intersect(rays)
+    oracle = pto.OracleScene(prims, mats, lights)
+    t_o, prim_o = oracle.intersect(rays[:60_000])
+    hit_o = t_o >= 0
+    assert np.array_equal(prim[:60_000], prim_o) and np.array_equal(t[:60_000][hit_o], t_o[hit_o])
+    t_g, prim_g, stats_g = scene.intersect(rays, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST)
+    hit = t >= 0
+    assert np.array_equal(prim_g, prim) and np.array_equal(t_g[hit], t[hit]) and stats_g.closest_rays_retraced == 0
+    t_r, prim_r, stats_r = scene.intersect(rays, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_CERTIFIED_RELAXED | capi.PTB_FLAG_COUNT_VISITS)
+    differing = int((prim_r != prim).sum())
+    print(f"sliver scene, relaxed certified walk: {differing} of {len(rays)} rays differ from the reference walk; "
+          f"{stats_r.certified_suspect_hits} walks abandoned on a hit in front of its own box, {stats_r.closest_rays_retraced} rays re-traced")
+    assert differing < len(rays) // 500
+    scene.close()
+
+    prims, mats, lights = sc.fine_scene()
+    scene = capi.Scene(ctx, prims, mats, lights)
+    assert scene.info().certifiable == 1
+    rays = sc.mixed_rays(prims, 600_000)
+    t, prim, stats = scene.intersect(rays, flags=capi.PTB_FLAG_COUNT_VISITS)
+    hit = t >= 0
+    t_g, prim_g, stats_g = scene.intersect(rays, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_COUNT_VISITS)
+    assert np.array_equal(prim_g, prim) and np.array_equal(t_g[hit], t[hit]) and (t_g[~hit] < 0).all()
+    assert 0 < stats_g.closest_rays_retraced < len(rays) * 2 // 3
+    t_r, prim_r, stats_r = scene.intersect(rays, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_CERTIFIED_RELAXED)
+    print(f"fine scene: guarded re-traces {stats_g.closest_rays_retraced / len(rays):.1%}, relaxed {stats_r.closest_rays_retraced / len(rays):.1%}; "
+          f"relaxed differs from the reference walk on {int((prim_r != prim).sum())} rays")
     scene.close()

@@ -189,3 +189,63 @@ def test_certificate_theorem_on_arbitrary_hierarchies(name):
         differing += int((prim[~certain] != want_prim[~certain]).sum())
     if name == "cornell_mesh":
         assert differing > 0  # ties on a foreign tree do come out differently: that is what the re-trace is for
+
+
+def test_unit_functions_match_reference(ref):
+    """Object::getSurfaceNormal / sampleSurface and BSDF::propagateRay / getSpectrum of the plain-C restatement against
+    the unmodified reference's virtual methods (object.cpp:86-144, 101-116, 192-207; propagation.cpp:89-217), bit for
+    bit, including how many engine draws each call consumes."""
+    import unit_cases as uc
+    from cpupathtrace_b200 import capi
+
+    prims, mats, x = uc.prims(), uc.materials(), uc.inputs()
+    builder = ref.builder()
+    handles = [builder.material(**spec) for spec in uc.MATERIALS]
+    index = uc.add_to_builder(builder, prims)
+    states = capi.xorshift_state(x["seeds"])
+    for prim, obj in zip(prims, index):
+        assert np.array_equal(pto.prim_normal(prim, x["positions"]), builder.object_normal(obj, x["positions"]), equal_nan=True)
+        got, after = pto.prim_sample(prim, states)
+        want, next_draw = builder.object_sample(obj, x["seeds"])
+        assert np.array_equal(got, want) and np.array_equal(uc.next_draw_from_state(after), next_draw)
+    for material, handle in zip(mats, handles):
+        got, after = pto.bsdf_propagate(material, 1e-3, x["propagate"], states)
+        want, next_draw = builder.bsdf_propagate(handle, 1e-3, x["propagate"], x["seeds"])
+        assert np.array_equal(got, want, equal_nan=True) and np.array_equal(uc.next_draw_from_state(after), next_draw)
+        for synthetic in (False, True):
+            assert np.array_equal(pto.bsdf_spectrum(material, synthetic, x["spectrum"]), builder.bsdf_spectrum(handle, synthetic, x["spectrum"]))
+    builder.close()
+
+
+def test_certificate_guard_on_adversarial_geometry():
+    """VERDICT r1 W1 on the CPU.  The certificate is exact about what the walk tests; about what it prunes it assumes
+    that a primitive cannot report a hit in front of its own box.  tests/stress_cases.py breaks that assumption (slivers,
+    grazing rays with |det| around the 1e-6 threshold of object.cpp:146-182): the unguarded walk then certifies answers
+    the reference does not give.  With the guard table (csrc/cert_guard.h, restated in pt_oracle.c) such a scene is not
+    certifiable at all, and on a scene the table does cover every certified answer equals the reference's on three
+    hierarchy shapes."""
+    import stress_cases as sc
+
+    prims, mats, lights = sc.sliver_scene()
+    scene = pto.OracleScene(prims, mats, lights)
+    rays = sc.grazing_rays(prims, 120_000)
+    want_t, want_prim = scene.intersect(rays)
+    hit = want_t >= 0
+    assert not scene.certifiable()
+    t, prim, certain = scene.intersect_certified(rays, 1, 0, guarded=False)
+    wrong = certain & np.where(hit, (prim != want_prim) | (t != want_t), prim != -1)
+    assert wrong.sum() > 0, "the stress scene no longer exposes the hazard it was built for"
+    t, prim, certain = scene.intersect_certified(rays, 1, 0, guarded=True)
+    assert not certain.any()
+
+    prims, mats, lights = sc.fine_scene()
+    scene = pto.OracleScene(prims, mats, lights)
+    assert scene.certifiable()
+    rays = sc.mixed_rays(prims, 90_000)
+    want_t, want_prim = scene.intersect(rays)
+    hit = want_t >= 0
+    for seed, shape in ((1, 0), (2, 2)):
+        t, prim, certain = scene.intersect_certified(rays, seed, shape, guarded=True)
+        assert 0.3 < certain.mean() < 0.95
+        assert np.array_equal(prim[certain], want_prim[certain]) and np.array_equal(t[certain & hit], want_t[certain & hit])
+        assert (t[certain & ~hit] < 0).all()

@@ -167,11 +167,13 @@ def test_sample_radiance_parity_point_light_pinhole(ref, b200):
     assert exact >= MIN_BIT_EXACT_FRACTION
 
 
-def test_fast_queries_through_the_cpp_api_change_nothing(ref, b200):
-    """The options bench.py switches on (ptb::RenderControl: certified closest hits on the SAH hierarchy, any-hit
-    shadow rays, zero-weight shadow rays skipped) must leave Scene::getIntersection results and every validation-mode
-    sample bit-identical to the unmodified reference, through the reference's own C++ API."""
-    b200.set_fast_queries(True, True, True)
+@pytest.mark.parametrize("fast", [False, True], ids=["reference_order", "default_fast_queries"])
+def test_query_options_through_the_cpp_api_change_nothing(ref, b200, fast):
+    """ptb::RenderControl's query options (certified closest hits on the SAH hierarchy, any-hit shadow rays, zero-weight
+    shadow rays skipped) are ON by default; with them and without them (exactly the reference's rays in the reference's
+    order) Scene::getIntersection results and every validation-mode sample must be bit-identical to the unmodified
+    reference, through the reference's own C++ API."""
+    b200.set_fast_queries(fast, fast, fast)
     try:
         spec = scenes.cornell_demo(("obj", scenes.standin_obj(120, 80)))
         builder = spec.replay(ref)
@@ -192,7 +194,36 @@ def test_fast_queries_through_the_cpp_api_change_nothing(ref, b200):
         bad, exact, want, got = _sample_parity(ref, b200, scenes.mixed_materials(), cam, 96, 64, 20000, seed=25)
         assert bad == 0 and exact == 1.0
     finally:
-        b200.set_fast_queries(False, False, False)
+        b200.set_fast_queries(True, True, True)
+
+
+def test_unit_virtual_methods_through_the_cpp_api(ref, b200):
+    """Object::getSurfaceNormal / sampleSurface and BSDF::propagateRay / getSpectrum called one element at a time through
+    the public virtual interface (the host layer answers them with ptb_prim_normal / ptb_prim_sample /
+    ptb_bsdf_propagate / ptb_bsdf_spectrum): values and engine consumption equal the unmodified reference's."""
+    import unit_cases as uc
+
+    prims, x = uc.prims(), uc.inputs()
+    n = 300  # one GPU round trip per element through this API
+    builders = []
+    for lib in (ref, b200):
+        builder = lib.builder()
+        handles = [builder.material(**spec) for spec in uc.MATERIALS]
+        builders.append((builder, handles, uc.add_to_builder(builder, prims)))
+    (br, hr, ir), (bg, hg, ig) = builders
+    for obj_r, obj_g in zip(ir, ig):
+        assert np.array_equal(bg.object_normal(obj_g, x["positions"][:n]), br.object_normal(obj_r, x["positions"][:n]), equal_nan=True)
+        got, next_got = bg.object_sample(obj_g, x["seeds"][:n])
+        want, next_want = br.object_sample(obj_r, x["seeds"][:n])
+        assert np.array_equal(got, want) and np.array_equal(next_got, next_want)
+    for mat_r, mat_g in zip(hr, hg):
+        got, next_got = bg.bsdf_propagate(mat_g, 1e-3, x["propagate"][:n], x["seeds"][:n])
+        want, next_want = br.bsdf_propagate(mat_r, 1e-3, x["propagate"][:n], x["seeds"][:n])
+        assert np.array_equal(got, want, equal_nan=True) and np.array_equal(next_got, next_want)
+        for synthetic in (False, True):
+            assert np.array_equal(bg.bsdf_spectrum(mat_g, synthetic, x["spectrum"][:n]), br.bsdf_spectrum(mat_r, synthetic, x["spectrum"][:n]))
+    br.close()
+    bg.close()
 
 
 def test_process_job_shards_sum_to_the_frame(b200):
