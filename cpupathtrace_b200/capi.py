@@ -143,6 +143,11 @@ PROTOTYPES = {
     "ptb_intersect": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint32, C.POINTER(RenderStats)]),
     "ptb_occluded": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint32, C.POINTER(RenderStats)]),
     "ptb_render": (C.c_int, [_P, C.POINTER(Camera), C.POINTER(RenderOpts), C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(RenderStats)]),
+    "ptb_render_with_progress": (C.c_int, [_P, C.POINTER(Camera), C.POINTER(RenderOpts), C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(RenderStats), _P, _P]),
+    "ptb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "ptb_scene_clone": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "ptb_render_multi": (C.c_int, [C.POINTER(_P), C.c_int32, C.POINTER(Camera), C.POINTER(RenderOpts), C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P,
+                                   C.POINTER(RenderStats), _P, _P]),
     "ptb_render_samples": (C.c_int, [_P, C.POINTER(Camera), C.POINTER(RenderOpts), C.c_uint64, _P, _P, _P, C.POINTER(RenderStats)]),
     "ptb_camera_shoot": (C.c_int, [_P, C.POINTER(Camera), C.c_uint64, _P, C.c_float, C.c_float, _P, _P]),
     "ptb_aperture_sample": (C.c_int, [_P, C.c_uint32, C.c_float, C.c_uint64, _P, _P]),

@@ -85,7 +85,8 @@ namespace ptb_guard {
                             (corner & 4) ? std::max({a.z, b.z, c.z}) : std::min({a.z, b.z, c.z})};
                 w = std::max(w, std::fabs(dot(unit, q) - h));
             }
-            const Vec centre{a.x + (ab.x + ac.x) / 3.0, a.y + (ab.y + ac.y) / 3.0, a.z + (ab.z + ac.z) / 3.0};
+            const Vec lo{std::min({a.x, b.x, c.x}), std::min({a.y, b.y, c.y}), std::min({a.z, b.z, c.z})};
+            const Vec hi{std::max({a.x, b.x, c.x}), std::max({a.y, b.y, c.y}), std::max({a.z, b.z, c.z})};
             const double k = 4.0 * relative_at_normal_incidence / slack;
 
             bool merged = false;
@@ -94,11 +95,15 @@ namespace ptb_guard {
                 const double along = unit.x * pl.nx + unit.y * pl.ny + unit.z * pl.nz;
                 const double hj = along >= 0.0 ? h : -h;
                 if(std::fabs(std::fabs(along) - 1.0) < 1e-8 && std::fabs(hj - pl.h) <= 1e-6 * (1.0 + std::fabs(hj))) {
-                    const double dist = norm(sub(centre, Vec{pl.cx, pl.cy, pl.cz}));
-                    pl.r = static_cast<float>(std::max<double>(pl.r, dist + diameter) * kMargin);
-                    pl.w = static_cast<float>(std::max<double>(pl.w, w) * kMargin);
-                    pl.cone = static_cast<float>(std::max<double>(pl.cone, cone) * kMargin);
-                    pl.k = static_cast<float>(std::max<double>(pl.k, k) * kMargin);
+                    pl.lox = std::min(pl.lox, static_cast<float>(lo.x));
+                    pl.loy = std::min(pl.loy, static_cast<float>(lo.y));
+                    pl.loz = std::min(pl.loz, static_cast<float>(lo.z));
+                    pl.hix = std::max(pl.hix, static_cast<float>(hi.x));
+                    pl.hiy = std::max(pl.hiy, static_cast<float>(hi.y));
+                    pl.hiz = std::max(pl.hiz, static_cast<float>(hi.z));
+                    pl.w = static_cast<float>(std::max<double>(pl.w, w * kMargin + 1e-7 * (1.0 + std::fabs(h))));
+                    pl.cone = static_cast<float>(std::max<double>(pl.cone, cone * kMargin));
+                    pl.k = static_cast<float>(std::max<double>(pl.k, k * kMargin));
                     merged = true;
                 }
             }
@@ -114,14 +119,24 @@ namespace ptb_guard {
             pl.ny = static_cast<float>(unit.y);
             pl.nz = static_cast<float>(unit.z);
             pl.h = static_cast<float>(h);
-            pl.cx = static_cast<float>(centre.x);
-            pl.cy = static_cast<float>(centre.y);
-            pl.cz = static_cast<float>(centre.z);
-            pl.r = static_cast<float>(diameter * kMargin);
+            pl.lox = static_cast<float>(lo.x);
+            pl.loy = static_cast<float>(lo.y);
+            pl.loz = static_cast<float>(lo.z);
+            pl.hix = static_cast<float>(hi.x);
+            pl.hiy = static_cast<float>(hi.y);
+            pl.hiz = static_cast<float>(hi.z);
             pl.w = static_cast<float>(w * kMargin + 1e-7 * (1.0 + std::fabs(h)));
             pl.cone = static_cast<float>(cone * kMargin);
             pl.k = static_cast<float>(k * kMargin);
-            pl.pad = 0.0F;
+            pl.r = 0.0F;
+            pl.pad0 = pl.pad1 = 0.0F;
+        }
+        for(uint32_t j = 0; j < g.n_planes; j++) {
+            GuardPlane &pl = g.planes[j];
+            const double dx = static_cast<double>(pl.hix) - pl.lox;
+            const double dy = static_cast<double>(pl.hiy) - pl.loy;
+            const double dz = static_cast<double>(pl.hiz) - pl.loz;
+            pl.r = static_cast<float>(0.5 * std::sqrt(dx * dx + dy * dy + dz * dz) * kMargin);
         }
         g.tau_safe = static_cast<float>(tau_safe * kMargin);
     }

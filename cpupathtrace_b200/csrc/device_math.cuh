@@ -75,6 +75,41 @@ namespace ptb {
         return v - (n * 2.0F) * d;
     }
 
+    // ---- correctly rounded, never contracted: the same IEEE operations in every build.
+    //
+    // The production-math build of the shade kernels (ptb_fast.cu: FMA contraction, approximate division / square root)
+    // may evaluate BSDFs and weights any way it likes, but one chain of the reference's arithmetic decides a coin that
+    // the image's brightness depends on and must round identically: a next-event sample lies ON the emissive triangle,
+    // the shadow ray starts at pos + dir * eps and the reference calls the light unoccluded iff the closest hit --
+    // the light's own surface, at |to_light| - eps up to rounding -- has t >= |to_light| - eps (worker.cpp:80-86).
+    // Whether that holds is decided by the last bits of pos, of the sampled point, of the direction and of the limit.
+    // With contracted or approximate arithmetic the coin lands differently often and the image comes out 3-4 % brighter
+    // than the reference's (measured, tests/test_parity_gpu.py::test_bench_scene_image_rmse_within_noise).  Hence: hit
+    // position, sampled light position, shadow-ray direction, origin and limit use these helpers in every build.
+    PTB_DEV V3 exactAdd(V3 a, V3 b) {
+        return V3{__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)};
+    }
+
+    PTB_DEV V3 exactSub(V3 a, V3 b) {
+        return V3{__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)};
+    }
+
+    PTB_DEV V3 exactScale(V3 a, float s) {
+        return V3{__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s)};
+    }
+
+    PTB_DEV float exactLength2(V3 a) {
+        return __fadd_rn(__fadd_rn(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y)), __fmul_rn(a.z, a.z));
+    }
+
+    PTB_DEV float exactLength(V3 a) {
+        return __fsqrt_rn(exactLength2(a));
+    }
+
+    PTB_DEV V3 exactNormalize(V3 a) {
+        return exactScale(a, __fdiv_rn(1.0F, exactLength(a)));
+    }
+
     PTB_DEV V4 operator+(V4 a, V4 b) {
         return V4{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
     }

@@ -538,7 +538,7 @@ namespace ptb {
         }
     }
 
-#if !defined(PTB_FAST_MATH) // the remaining kernels exist in the exact build only
+#if !defined(PTB_FAST_MATH) && !defined(PTB_FAST_TU_EXACT) // the remaining kernels exist in the exact build only
 
     // ------------------------------------------------------------------------------------------------ resolve
 
@@ -938,7 +938,7 @@ namespace ptb {
         w[5] = pd;
     }
 
-#endif // !PTB_FAST_MATH
+#endif // !PTB_FAST_MATH && !PTB_FAST_TU_EXACT
 
 }
 

@@ -13,6 +13,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -21,6 +22,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -121,7 +123,10 @@ struct ptb_context {
     Buffer io_b;
     Buffer io_c;
     Buffer io_d;
+    Buffer multi_image;   // ptb_render_multi: this replica's share of the frame (its tiles, zeros elsewhere)
+    Buffer multi_staging; // ptb_render_multi on the first replica: copies of the other replicas' images when peers cannot map each other
     uint32_t *host_counters = nullptr; // pinned
+    unsigned long long *host_cursor = nullptr; // pinned: the work cursor as of the last batch of bounce iterations
 
     // profiling events: [pair][0 = start, 1 = stop], class 0 = closest-hit trace, 2 = shadow trace, 1 = everything else
     cudaEvent_t events[kEventPairs][2];
@@ -347,8 +352,16 @@ namespace {
         return m;
     }
 
+    // Where progress reports of a frame go: `done_before` pixel-samples were finished by earlier pixel groups of the call.
+    struct ProgressSink {
+        ptb_progress_fn fn;
+        void *user;
+        uint64_t done_before;
+        uint64_t total;
+    };
+
     int runBounces(ptb_scene *scene, const PathPool &pool, const RenderParams &params, const PathSource &src, float4 *samples, bool count_visits,
-                   ClosestMode closest, ptb_render_stats *stats) {
+                   ClosestMode closest, ptb_render_stats *stats, const ProgressSink *progress = nullptr) {
         ptb_context *ctx = scene->ctx; // the calling entry point holds ctx->mutex
         uint32_t *counters = ctx->counters.as<uint32_t>();
         uint32_t *queues[2] = {ctx->queue_a.as<uint32_t>(), ctx->queue_b.as<uint32_t>()};
@@ -465,6 +478,9 @@ namespace {
                 PTB_CUDA(cudaMemcpyAsync(ctx->host_counters + launched * kCounterSlots, counters, kCounterSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
                 cur = nxt;
             }
+            if(progress != nullptr) {
+                PTB_CUDA(cudaMemcpyAsync(ctx->host_cursor, work_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+            }
             PTB_CUDA(cudaStreamSynchronize(ctx->stream));
             PTB_CUDA(cudaGetLastError());
 
@@ -494,6 +510,12 @@ namespace {
             }
             collectTimers(ctx, stats);
             n_cur = n_in;
+            if(progress != nullptr && progress->fn != nullptr && n_cur > 0U) {
+                // started work items minus the paths still in flight = samples retired into the per-sample buffer
+                const uint64_t started = std::min<uint64_t>(*ctx->host_cursor, src.total);
+                const uint64_t retired = started > n_cur ? started - n_cur : 0;
+                progress->fn(progress->user, progress->done_before + retired, progress->total);
+            }
         }
         return PTB_OK;
     }
@@ -693,21 +715,36 @@ int ptb_context_create(int device, ptb_context **out) {
         return fail(PTB_ERR_OUT_OF_MEMORY, "ptb_context_create: host allocation failed");
     }
     ctx->device = device;
+    for(auto &pair : ctx->events) {
+        pair[0] = pair[1] = nullptr;
+    }
+    // every failure below frees what was created so far (ptb_context_destroy copes with a partly built context)
+    struct Guard {
+        ptb_context *ctx;
+        ~Guard() {
+            if(ctx != nullptr) {
+                const std::string keep = g_last_error;
+                ptb_context_destroy(ctx);
+                g_last_error = keep;
+            }
+        }
+    } guard{ctx};
     cudaDeviceProp prop{};
     PTB_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     if(prop.major < 10) {
-        delete ctx;
         return fail(PTB_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100-class; the kernels are built for sm_100a only");
     }
     PTB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     PTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->host_counters), kMaxIterationsPerSync * kCounterSlots * sizeof(uint32_t)));
+    PTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->host_cursor), sizeof(unsigned long long)));
     for(auto &pair : ctx->events) {
         PTB_CUDA(cudaEventCreate(&pair[0]));
         PTB_CUDA(cudaEventCreate(&pair[1]));
     }
     PTB_CUDA(cudaEventCreate(&ctx->call_start));
     PTB_CUDA(cudaEventCreate(&ctx->call_stop));
+    guard.ctx = nullptr; // fully built: ownership passes to the caller
     ctx->events_ready = envLong("PTB_PROFILE", 1) != 0;
     // tuned on the bench scene with the 128 Mi-path pool (with the earlier 4 Mi pool the drain phases dominated and smaller votes won)
     ctx->vote.refill = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_REFILL_VOTE", 12))));
@@ -730,21 +767,37 @@ int ptb_context_destroy(ptb_context *ctx) {
         return PTB_OK;
     }
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if(ctx->stream != nullptr) {
+        cudaStreamSynchronize(ctx->stream);
+    }
     for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->redo_queue, &ctx->counters, &ctx->visits, &ctx->work_cursor, &ctx->samples, &ctx->pixel_list,
-                     &ctx->io_a, &ctx->io_b, &ctx->io_c, &ctx->io_d}) {
+                     &ctx->io_a, &ctx->io_b, &ctx->io_c, &ctx->io_d, &ctx->multi_image, &ctx->multi_staging}) {
         b->release();
     }
     if(ctx->host_counters != nullptr) {
         cudaFreeHost(ctx->host_counters);
     }
-    for(auto &pair : ctx->events) {
-        cudaEventDestroy(pair[0]);
-        cudaEventDestroy(pair[1]);
+    if(ctx->host_cursor != nullptr) {
+        cudaFreeHost(ctx->host_cursor);
     }
-    cudaEventDestroy(ctx->call_start);
-    cudaEventDestroy(ctx->call_stop);
-    cudaStreamDestroy(ctx->stream);
+    for(auto &pair : ctx->events) {
+        if(pair[0] != nullptr) {
+            cudaEventDestroy(pair[0]);
+        }
+        if(pair[1] != nullptr) {
+            cudaEventDestroy(pair[1]);
+        }
+    }
+    if(ctx->call_start != nullptr) {
+        cudaEventDestroy(ctx->call_start);
+    }
+    if(ctx->call_stop != nullptr) {
+        cudaEventDestroy(ctx->call_stop);
+    }
+    if(ctx->stream != nullptr) {
+        cudaStreamDestroy(ctx->stream);
+    }
+    cudaGetLastError();
     delete ctx;
     return PTB_OK;
 }
@@ -778,6 +831,9 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
     *out = nullptr;
     if(desc->n_prims > 0 && (desc->prims == nullptr || desc->materials == nullptr || desc->n_materials == 0)) {
         return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_scene_create: primitives need a material table");
+    }
+    if(desc->n_lights > 0 && desc->lights == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_scene_create: n_lights > 0 but lights is null");
     }
     if(desc->n_prims >= (1ULL << 31) - 1) {
         return fail(PTB_ERR_UNSUPPORTED, "ptb_scene_create: more than 2^31 - 2 primitives");
@@ -1257,6 +1313,11 @@ int ptb_render_samples(ptb_scene *scene, const ptb_camera *camera, const ptb_ren
 
 int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts *opts, int32_t x0, int32_t y0, int32_t w, int32_t h, float *out_rgba,
                ptb_render_stats *stats) {
+    return ptb_render_with_progress(scene, camera, opts, x0, y0, w, h, out_rgba, stats, nullptr, nullptr);
+}
+
+int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts *opts, int32_t x0, int32_t y0, int32_t w, int32_t h,
+                             float *out_rgba, ptb_render_stats *stats, ptb_progress_fn progress, void *user) {
     if(scene == nullptr || camera == nullptr || opts == nullptr) {
         return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render: null argument");
     }
@@ -1310,13 +1371,24 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
     // pixels of tiles owned by other shards (and everything when spp == 0) stay 0
     PTB_CUDA(cudaMemsetAsync(d_out, 0, out_bytes, ctx->stream));
 
-    // pixel groups: as many whole tiles as fit the per-sample buffer budget
+    // Pixel groups: consecutive runs of the owned tiles' pixels (tile order) whose per-sample buffer fits the budget and
+    // whose sample count fits the 32-bit destination index of a path -- a single tile larger than either (processItem
+    // passes tile_size = max(w, h); a caller may pass any tile_size) is split between groups like everything else.
     const uint64_t pool_limit = poolLimit(ctx, scene->shadow_stride);
     const uint64_t budget_bytes = sampleBufferBudget(ctx);
-    const uint64_t per_tile_bytes = static_cast<uint64_t>(tile) * tile * std::max(spp, 1) * sizeof(float4);
-    uint64_t tiles_per_group = std::max<uint64_t>(1, budget_bytes / per_tile_bytes);
-    // destinations are 32-bit
-    tiles_per_group = std::min<uint64_t>(tiles_per_group, std::max<uint64_t>(1, (0xFFFFFFFFULL / std::max(spp, 1)) / (static_cast<uint64_t>(tile) * tile)));
+    std::vector<uint64_t> tile_first(owned.size() + 1, 0); // prefix sums of the owned tiles' pixel counts
+    for(size_t k = 0; k < owned.size(); k++) {
+        const int t = owned[k];
+        const int tx0 = (t % tiles_x) * tile;
+        const int ty0 = (t / tiles_x) * tile;
+        tile_first[k + 1] = tile_first[k] + static_cast<uint64_t>(std::min(tx0 + tile, w) - tx0) * static_cast<uint64_t>(std::min(ty0 + tile, h) - ty0);
+    }
+    const uint64_t n_owned_pixels = tile_first.back();
+    const uint64_t max_group_samples = std::min<uint64_t>(std::max<uint64_t>(budget_bytes / sizeof(float4), 1), 0xFFFFFFFFULL);
+    const uint64_t max_group_pixels = std::max<uint64_t>(1, max_group_samples / static_cast<uint64_t>(std::max(spp, 1)));
+    if(static_cast<uint64_t>(std::max(spp, 1)) > 0xFFFFFFFFULL) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_render: more than 2^32 - 1 samples per pixel");
+    }
 
     const RenderParams params = makeParams(*camera, *opts);
     if((status = ctx->counters.reserve(kCounterSlots * sizeof(uint32_t))) != PTB_OK || (status = ctx->visits.reserve(2 * sizeof(VisitCounters))) != PTB_OK) {
@@ -1325,23 +1397,14 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
     PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, 2 * sizeof(VisitCounters), ctx->stream));
     PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
 
+    ProgressSink sink{progress, user, 0, n_owned_pixels * static_cast<uint64_t>(std::max(spp, 0))};
     std::vector<uint32_t> pixel_list;
-    for(size_t group_begin = 0; group_begin < owned.size() && spp > 0; group_begin += tiles_per_group) {
-        const size_t group_end = std::min<size_t>(owned.size(), group_begin + tiles_per_group);
-        // pixels of the group's tiles in tile order; frames rendered repeatedly reuse the list already on the device
+    for(uint64_t group_begin = 0; group_begin < n_owned_pixels && spp > 0; group_begin += max_group_pixels) {
+        const uint64_t group_end = std::min<uint64_t>(n_owned_pixels, group_begin + max_group_pixels);
+        // pixels of the group in tile order; frames rendered repeatedly reuse the list already on the device
         const long long key[9] = {x0, y0, w, h, tile, shard_index, shard_count, static_cast<long long>(group_begin), static_cast<long long>(group_end)};
         const bool list_cached = std::equal(key, key + 9, ctx->pixel_list_key);
-        uint64_t n_group_pixels = 0;
-        for(size_t k = group_begin; k < group_end; k++) {
-            const int t = owned[k];
-            const int tx0 = (t % tiles_x) * tile;
-            const int ty0 = (t / tiles_x) * tile;
-            n_group_pixels += static_cast<uint64_t>(std::min(tx0 + tile, w) - tx0) * static_cast<uint64_t>(std::min(ty0 + tile, h) - ty0);
-        }
-        const uint32_t n_pixels = static_cast<uint32_t>(n_group_pixels);
-        if(n_pixels == 0U) {
-            continue;
-        }
+        const uint32_t n_pixels = static_cast<uint32_t>(group_end - group_begin);
         const uint64_t total = static_cast<uint64_t>(n_pixels) * spp;
         if((status = ctx->pixel_list.reserve(n_pixels * sizeof(uint32_t))) != PTB_OK || (status = ctx->samples.reserve(total * sizeof(float4))) != PTB_OK) {
             return status;
@@ -1349,17 +1412,19 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
         if(!list_cached) {
             pixel_list.clear();
             pixel_list.reserve(n_pixels);
-            for(size_t k = group_begin; k < group_end; k++) {
+            size_t k = static_cast<size_t>(std::upper_bound(tile_first.begin(), tile_first.end(), group_begin) - tile_first.begin()) - 1;
+            for(uint64_t at = group_begin; at < group_end; k++) {
                 const int t = owned[k];
                 const int tx0 = (t % tiles_x) * tile;
                 const int ty0 = (t / tiles_x) * tile;
-                const int tx1 = std::min(tx0 + tile, w);
-                const int ty1 = std::min(ty0 + tile, h);
-                for(int y = ty0; y < ty1; y++) {
-                    for(int x = tx0; x < tx1; x++) {
-                        pixel_list.push_back(static_cast<uint32_t>(x0 + x) | (static_cast<uint32_t>(y0 + y) << 16));
-                    }
+                const int tw = std::min(tx0 + tile, w) - tx0;
+                const uint64_t tile_end = std::min<uint64_t>(tile_first[k + 1], group_end);
+                for(uint64_t q = at - tile_first[k]; q < tile_end - tile_first[k]; q++) {
+                    const int x = tx0 + static_cast<int>(q % static_cast<uint64_t>(tw));
+                    const int y = ty0 + static_cast<int>(q / static_cast<uint64_t>(tw));
+                    pixel_list.push_back(static_cast<uint32_t>(x0 + x) | (static_cast<uint32_t>(y0 + y) << 16));
                 }
+                at = tile_end;
             }
             std::fill(ctx->pixel_list_key, ctx->pixel_list_key + 9, -1LL);
             // the list is consumed by kernels of this group only; a pageable copy on the stream is ordered before them
@@ -1379,9 +1444,10 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
         src.n_pixels = n_pixels;
         src.explicit_samples = 0U;
         src.total = total;
-        if((status = runBounces(scene, pool, params, src, ctx->samples.as<float4>(), count_visits, closestMode(scene, opts->flags), stats)) != PTB_OK) {
+        if((status = runBounces(scene, pool, params, src, ctx->samples.as<float4>(), count_visits, closestMode(scene, opts->flags), stats, &sink)) != PTB_OK) {
             return status;
         }
+        sink.done_before += total;
 
         ResolveParams rp{};
         rp.min_sample_count = opts->min_sample_count;
@@ -1398,6 +1464,9 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
         if(stats != nullptr) {
             stats->kernel_launches += 1;
         }
+        if(progress != nullptr && group_end < n_owned_pixels) {
+            progress(user, sink.done_before, sink.total);
+        }
     }
 
     if(!device_io) {
@@ -1406,6 +1475,9 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
     status = endCall(ctx, stats);
     if(status != PTB_OK) {
         return status;
+    }
+    if(progress != nullptr) {
+        progress(user, sink.total, sink.total);
     }
     return finishStats(ctx, count_visits, stats);
 }
@@ -1819,6 +1891,292 @@ int ptb_post_process(ptb_context *ctx, float *rgba, int32_t width, int32_t heigh
     }
     PTB_CUDA(cudaStreamSynchronize(ctx->stream));
     PTB_CUDA(cudaGetLastError());
+    return PTB_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------- several GPUs
+
+namespace {
+
+    constexpr int kMaxReplicas = 16;
+
+    struct GatherParams {
+        const float4 *src[kMaxReplicas];
+        int32_t n;
+        int32_t w;
+        int32_t h;
+        int32_t tile;
+        int32_t tiles_x;
+    };
+
+    // Assembles the frame from the replicas' images: pixel (x, y) belongs to tile (y / tile) * tiles_x + x / tile, which
+    // replica (tile index % n) rendered.  The sources are peer-device pointers (read over NVLink) or staged local copies.
+    __global__ void gatherTilesKernel(GatherParams g, float4 *__restrict__ dst) {
+        const int64_t count = static_cast<int64_t>(g.w) * g.h;
+        for(int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < count; p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+            const int x = static_cast<int>(p % g.w);
+            const int y = static_cast<int>(p / g.w);
+            const int owner = ((y / g.tile) * g.tiles_x + x / g.tile) % g.n;
+            dst[p] = g.src[owner][p];
+        }
+    }
+
+    struct MultiProgress {
+        std::mutex mutex;
+        std::atomic<uint64_t> done[kMaxReplicas];
+        std::atomic<uint64_t> total[kMaxReplicas];
+        ptb_progress_fn fn = nullptr;
+        void *user = nullptr;
+        int n = 0;
+    };
+
+    struct ReplicaProgress {
+        MultiProgress *all;
+        int index;
+    };
+
+    void replicaProgress(void *user, uint64_t done, uint64_t total) {
+        auto *self = static_cast<ReplicaProgress *>(user);
+        MultiProgress *all = self->all;
+        all->done[self->index].store(done);
+        all->total[self->index].store(total);
+        std::lock_guard<std::mutex> lock(all->mutex); // the caller's callback never runs concurrently (reference include/PathTrace/worker.h:76-79)
+        uint64_t sum_done = 0;
+        uint64_t sum_total = 0;
+        bool all_known = true;
+        for(int i = 0; i < all->n; i++) {
+            sum_done += all->done[i].load();
+            const uint64_t t = all->total[i].load();
+            all_known = all_known && t != ~0ULL;
+            sum_total += t != ~0ULL ? t : 0;
+        }
+        if(all_known && sum_done < sum_total) { // the final report (done == total) is issued once, after the gather
+            all->fn(all->user, sum_done, sum_total);
+        }
+    }
+
+}
+
+extern "C" {
+
+int ptb_device_count(int *count_out) {
+    if(count_out == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_device_count: null argument");
+    }
+    int count = 0;
+    const cudaError_t err = cudaGetDeviceCount(&count);
+    if(err != cudaSuccess) {
+        cudaGetLastError();
+        count = 0;
+    }
+    *count_out = count;
+    return PTB_OK;
+}
+
+int ptb_scene_clone(const ptb_scene *scene, ptb_context *ctx, ptb_scene **out) {
+    if(scene == nullptr || ctx == nullptr || out == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_scene_clone: null argument");
+    }
+    *out = nullptr;
+    std::lock_guard<std::mutex> lock(ctx->mutex);
+    int status = useDevice(ctx);
+    if(status != PTB_OK) {
+        return status;
+    }
+    auto *copy = new(std::nothrow) ptb_scene();
+    if(copy == nullptr) {
+        return fail(PTB_ERR_OUT_OF_MEMORY, "ptb_scene_clone: host allocation failed");
+    }
+    copy->ctx = ctx;
+    copy->info = scene->info;
+    copy->shadow_stride = scene->shadow_stride;
+    copy->guard = scene->guard;
+    copy->dev = scene->dev;
+    const int src_device = scene->ctx->device;
+    struct Pair {
+        const Buffer *from;
+        Buffer *to;
+    };
+    const Pair pairs[] = {{&scene->nodes, &copy->nodes}, {&scene->occ_nodes, &copy->occ_nodes}, {&scene->geom, &copy->geom}, {&scene->shade, &copy->shade}, {&scene->mats, &copy->mats},
+                          {&scene->lights, &copy->lights}, {&scene->emis, &copy->emis}, {&scene->cdf, &copy->cdf}, {&scene->slot_to_prim, &copy->slot_to_prim}};
+    for(const Pair &pair : pairs) {
+        if(pair.from->ptr == nullptr) {
+            continue;
+        }
+        if((status = pair.to->reserve(pair.from->bytes)) != PTB_OK) {
+            ptb_scene_destroy(copy);
+            return status;
+        }
+        const cudaError_t err = cudaMemcpyPeer(pair.to->ptr, ctx->device, pair.from->ptr, src_device, pair.from->bytes);
+        if(err != cudaSuccess) {
+            cudaGetLastError();
+            ptb_scene_destroy(copy);
+            return fail(PTB_ERR_CUDA, std::string("ptb_scene_clone: cudaMemcpyPeer: ") + cudaGetErrorString(err));
+        }
+    }
+    DeviceScene &d = copy->dev;
+    d.nodes = copy->nodes.as<float4>();
+    d.occ_nodes = scene->dev.occ_nodes != nullptr ? copy->occ_nodes.as<float4>() : nullptr;
+    d.geom = copy->geom.as<float4>();
+    d.shade = copy->shade.as<float4>();
+    d.mats = copy->mats.as<float4>();
+    d.lights = copy->lights.as<float4>();
+    d.emis = copy->emis.as<float4>();
+    d.cdf = copy->cdf.as<float>();
+    d.slot_to_prim = copy->slot_to_prim.as<uint32_t>();
+    *out = copy;
+    return PTB_OK;
+}
+
+int ptb_render_multi(ptb_scene *const *replicas, int32_t n, const ptb_camera *camera, const ptb_render_opts *opts, int32_t x0, int32_t y0, int32_t w, int32_t h,
+                     float *out_rgba, ptb_render_stats *stats, ptb_progress_fn progress, void *user) {
+    if(replicas == nullptr || n < 1 || camera == nullptr || opts == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render_multi: null argument");
+    }
+    if(n > kMaxReplicas) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_render_multi: more than 16 replicas");
+    }
+    for(int i = 0; i < n; i++) {
+        if(replicas[i] == nullptr) {
+            return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render_multi: null replica");
+        }
+        for(int j = 0; j < i; j++) {
+            if(replicas[j]->ctx == replicas[i]->ctx) {
+                return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render_multi: two replicas share a context");
+            }
+        }
+    }
+    if(opts->shard_count > 1) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render_multi: the call shards the frame itself; shard_count must be <= 1");
+    }
+    if(n == 1) {
+        return ptb_render_with_progress(replicas[0], camera, opts, x0, y0, w, h, out_rgba, stats, progress, user);
+    }
+    if(w < 0 || h < 0) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render_multi: negative rectangle");
+    }
+    if(w == 0 || h == 0) {
+        return PTB_OK;
+    }
+    if(out_rgba == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render_multi: out_rgba is null");
+    }
+    const size_t image_bytes = static_cast<size_t>(w) * h * sizeof(float4);
+    for(int i = 0; i < n; i++) {
+        ptb_context *ctx = replicas[i]->ctx;
+        std::lock_guard<std::mutex> lock(ctx->mutex);
+        int status = useDevice(ctx);
+        if(status != PTB_OK || (status = ctx->multi_image.reserve(image_bytes)) != PTB_OK) {
+            return status;
+        }
+    }
+
+    MultiProgress all;
+    all.fn = progress;
+    all.user = user;
+    all.n = n;
+    for(int i = 0; i < kMaxReplicas; i++) {
+        all.done[i].store(0);
+        all.total[i].store(~0ULL);
+    }
+    std::vector<ReplicaProgress> sinks(static_cast<size_t>(n));
+    std::vector<int> statuses(static_cast<size_t>(n), PTB_OK);
+    std::vector<std::string> errors(static_cast<size_t>(n));
+    auto render_share = [&](int i) {
+        ptb_render_opts mine = *opts;
+        mine.shard_index = i;
+        mine.shard_count = n;
+        mine.flags |= PTB_FLAG_DEVICE_IO;
+        sinks[i] = ReplicaProgress{&all, i};
+        statuses[i] = ptb_render_with_progress(replicas[i], camera, &mine, x0, y0, w, h, replicas[i]->ctx->multi_image.as<float>(), stats != nullptr ? &stats[i] : nullptr,
+                                               progress != nullptr ? replicaProgress : nullptr, &sinks[i]);
+        if(statuses[i] != PTB_OK) {
+            errors[i] = g_last_error; // thread-local: carried back to the caller's thread below
+        }
+    };
+    std::vector<std::thread> workers;
+    for(int i = 1; i < n; i++) {
+        workers.emplace_back(render_share, i);
+    }
+    render_share(0);
+    for(std::thread &t : workers) {
+        t.join();
+    }
+    for(int i = 0; i < n; i++) {
+        if(statuses[i] != PTB_OK) {
+            return fail(statuses[i], "ptb_render_multi: replica " + std::to_string(i) + ": " + errors[i]);
+        }
+    }
+
+    // gather on the first replica's device
+    ptb_context *ctx = replicas[0]->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mutex);
+    int status = useDevice(ctx);
+    if(status != PTB_OK) {
+        return status;
+    }
+    const bool device_io = (opts->flags & PTB_FLAG_DEVICE_IO) != 0U;
+    float4 *d_out = reinterpret_cast<float4 *>(out_rgba);
+    if(!device_io) {
+        if((status = ctx->io_d.reserve(image_bytes)) != PTB_OK) {
+            return status;
+        }
+        d_out = ctx->io_d.as<float4>();
+    }
+    int tile = opts->tile_size;
+    if(tile <= 0) {
+        tile = std::max(std::min(std::min(w, h) / 4, 32), 1);
+    }
+    GatherParams g{};
+    g.n = n;
+    g.w = w;
+    g.h = h;
+    g.tile = tile;
+    g.tiles_x = (w + tile - 1) / tile;
+    g.src[0] = ctx->multi_image.as<float4>();
+    size_t staged = 0;
+    for(int i = 1; i < n; i++) {
+        ptb_context *peer = replicas[i]->ctx;
+        int can_access = 0;
+        if(peer->device != ctx->device && cudaDeviceCanAccessPeer(&can_access, ctx->device, peer->device) == cudaSuccess && can_access != 0) {
+            const cudaError_t err = cudaDeviceEnablePeerAccess(peer->device, 0);
+            if(err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled) {
+                can_access = 0;
+            }
+            cudaGetLastError();
+        }
+        if(peer->device == ctx->device || can_access != 0) {
+            g.src[i] = peer->multi_image.as<float4>(); // same device, or mapped peer memory: the kernel reads it directly
+        }
+        else {
+            if((status = ctx->multi_staging.reserve(static_cast<size_t>(n - 1) * image_bytes)) != PTB_OK) {
+                return status;
+            }
+            char *slot = ctx->multi_staging.as<char>() + staged * image_bytes;
+            PTB_CUDA(cudaMemcpyPeerAsync(slot, ctx->device, peer->multi_image.ptr, peer->device, image_bytes, ctx->stream));
+            g.src[i] = reinterpret_cast<const float4 *>(slot);
+            staged++;
+        }
+    }
+    const int64_t pixels = static_cast<int64_t>(w) * h;
+    const int grid = static_cast<int>(std::min<int64_t>((pixels + 255) / 256, static_cast<int64_t>(gridFor(ctx, 8))));
+    gatherTilesKernel<<<grid, 256, 0, ctx->stream>>>(g, d_out);
+    PTB_CUDA(cudaGetLastError());
+    if(!device_io) {
+        PTB_CUDA(cudaMemcpyAsync(out_rgba, d_out, image_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    PTB_CUDA(cudaGetLastError());
+    if(progress != nullptr) {
+        uint64_t total = 0;
+        for(int i = 0; i < n; i++) {
+            const uint64_t t = all.total[i].load();
+            total += t != ~0ULL ? t : 0;
+        }
+        progress(user, total, total);
+    }
     return PTB_OK;
 }
 

@@ -2,7 +2,9 @@
 //   -fmad=true -use_fast_math -DPTB_FAST_MATH=1
 // Everything kernels.cuh declares lands in namespace ptb_fast here, so these instantiations never collide with the exact
 // ones of ptb.cu at link time.
+#ifndef PTB_FAST_TU_EXACT // (experiments only: the same translation unit with the exact arithmetic)
 #define PTB_FAST_MATH 1
+#endif
 #define ptb ptb_fast
 #include "kernels.cuh"
 #undef ptb

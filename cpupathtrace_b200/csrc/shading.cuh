@@ -176,8 +176,9 @@ namespace ptb {
             float r1;
             float r2;
             rng.canonicalPair(r1, r2);
-            const float rr1 = sqrtf(r1);
-            surface_pos = (a * (1.0F - rr1) + b * (rr1 * (1.0F - r2))) + c * (rr1 * r2);
+            // correctly rounded in every build: the point's last bits take part in the light's self-occlusion coin (device_math.cuh)
+            const float rr1 = __fsqrt_rn(r1);
+            surface_pos = exactAdd(exactAdd(exactScale(a, __fsub_rn(1.0F, rr1)), exactScale(b, __fmul_rn(rr1, __fsub_rn(1.0F, r2)))), exactScale(c, __fmul_rn(rr1, r2)));
             // p = 1 / (|cross(b - a, c - a)| / 2), evaluated once on the host with the same operations (host_math.cpp)
             surface_p = e1.w;
             surface_cull = (flags & kCullBit) != 0U;
@@ -462,7 +463,7 @@ namespace ptb {
     PTB_DEV bool shadeVertex(const DeviceScene &s, float epsilon, int max_depth, PathRegs<RNG> &p, float t, uint32_t slot, Shadow shadow) {
         p.path_length++;
 
-        const V3 pos = p.ray_o + p.ray_d * t;
+        const V3 pos = exactAdd(p.ray_o, exactScale(p.ray_d, t));
         uint32_t material_index;
         const V3 n = surfaceNormal(s, slot, pos, material_index);
         const Material m = loadMaterial(s, material_index);
@@ -480,16 +481,17 @@ namespace ptb {
         const bool do_bounce = p.rng.uniform01() < bounce_probability;
 
         sampleLights(s, pos, p.rng, [&](const LightSample &ls) {
-            const V3 to_light = ls.pos - pos;
-            const V3 light_dir = normalize(to_light);
+            // shadow-ray geometry: correctly rounded in every build (device_math.cuh "correctly rounded, never contracted")
+            const V3 to_light = exactSub(ls.pos, pos);
+            const V3 light_dir = exactNormalize(to_light);
             V4 base;
             float shading_factor;
             float shadow_ray_pd;
             bsdfSpectrum(m, p.ray_d, light_dir, n, ls.spectrum, true, base, shading_factor, shadow_ray_pd);
             ShadowCandidate c;
-            c.o = pos + light_dir * epsilon;
+            c.o = exactAdd(pos, exactScale(light_dir, epsilon));
             c.d = light_dir;
-            c.limit = length(to_light) - epsilon;
+            c.limit = __fsub_rn(exactLength(to_light), epsilon);
             if(shadow_ray_pd > 0.0F) {
                 const V4 combined = (base * shading_factor) * p.throughput;
                 c.contribution = combined / static_cast<float>(p.divisor * p.bounce_pd * ls.pd * shadow_ray_pd);

@@ -183,21 +183,25 @@ namespace ptb {
 
     // The guard of the certified walk (cert_guard.h): true when the ray must be traced by the reference-order walk because
     // some large triangle or nearby sphere could report a distance that is rounding noise.
-    PTB_DEV bool guardFlagsRay(const ptb_guard::CertGuard &g, V3 o, V3 d) {
+    PTB_DEV bool guardFlagsRay(const ptb_guard::CertGuard &g, const RayInv &r) {
+        const V3 o = r.o;
+        const V3 d = r.d;
         for(uint32_t j = 0; j < g.n_planes; j++) {
             const ptb_guard::GuardPlane &pl = g.planes[j];
             const float hd = ((pl.nx * o.x + pl.ny * o.y) + pl.nz * o.z) - pl.h;
             const float cd = (pl.nx * d.x + pl.ny * d.y) + pl.nz * d.z;
             const float ahd = fabsf(hd);
-            if(fabsf(cd) < pl.cone || ahd <= pl.w) {
-                return true;
-            }
-            if(hd * cd < 0.0F) {
-                const float dx = o.x - pl.cx;
-                const float dy = o.y - pl.cy;
-                const float dz = o.z - pl.cz;
-                const float rho = sqrtf((dx * dx + dy * dy) + dz * dz) + pl.r;
-                if(ahd < pl.w + pl.k * rho) {
+            const float dx = o.x - 0.5F * (pl.lox + pl.hix);
+            const float dy = o.y - 0.5F * (pl.loy + pl.hiy);
+            const float dz = o.z - 0.5F * (pl.loz + pl.hiz);
+            const float band = pl.k * (sqrtf((dx * dx + dy * dy) + dz * dz) + pl.r);
+            if(fabsf(cd) < pl.cone || ahd <= pl.w + band) {
+                // near the plane or grazing it: now the exact question -- does the ray enter the box of the triangles behind
+                // the plane (the union of their leaf boxes, same slab arithmetic as the reference's), and if so, closer
+                // than band / |n.d|?  A ray that misses this box is never tested against those triangles by the reference
+                // either (a ray LEAVING a wall it just bounced off misses the wall's flat box).
+                const float entry = slab(r, pl.lox, pl.loy, pl.loz, pl.hix, pl.hiy, pl.hiz);
+                if(entry >= 0.0F && (fabsf(cd) < pl.cone || entry * fabsf(cd) < band)) {
                     return true;
                 }
             }
@@ -206,16 +210,21 @@ namespace ptb {
             const float cx = o.x - g.spheres[j][0];
             const float cy = o.y - g.spheres[j][1];
             const float cz = o.z - g.spheres[j][2];
-            const float r2 = g.spheres[j][3] * g.spheres[j][3];
-            const float co2 = (cx * cx + cy * cy) + cz * cz;
-            if(co2 < 3.24F * r2) {
-                return true;
-            }
-            if(co2 < 9.0F * r2) {
-                const float dd = (d.x * cx + d.y * cy) + d.z * cz;
-                const float disc = dd * dd - co2 + r2;
-                if(fabsf(disc) < r2 * 0.0625F) {
+            const float radius = g.spheres[j][3];
+            const float r2 = radius * radius;
+            const float reach = fmaxf(fmaxf(fabsf(cx), fabsf(cy)), fabsf(cz));
+            // a ray that starts inside the sphere's box always reaches its leaf (entry 0) and is tested exactly
+            if(reach > radius) {
+                if(reach <= 1.01F * radius) {
                     return true;
+                }
+                const float co2 = (cx * cx + cy * cy) + cz * cz;
+                if(co2 < 9.0F * r2) {
+                    const float dd = (d.x * cx + d.y * cy) + d.z * cz;
+                    const float disc = dd * dd - co2 + r2;
+                    if(fabsf(disc) < r2 * 0.0625F) {
+                        return true;
+                    }
                 }
             }
         }
@@ -419,7 +428,7 @@ namespace ptb {
                         if(s.n_prims == 0U) {
                             commit(k, hit, true);
                         }
-                        else if(CERTIFIED && guard != nullptr && guardFlagsRay(*guard, o, d)) {
+                        else if(CERTIFIED && guard != nullptr && guardFlagsRay(*guard, r)) {
                             commit(k, hit, false);
                         }
                         else {

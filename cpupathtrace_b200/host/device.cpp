@@ -3,6 +3,7 @@
 #include <PathTrace/scene/propagation.h>
 
 #include <cstdio>
+#include <map>
 #include <mutex>
 #include <stdexcept>
 
@@ -20,6 +21,26 @@ namespace ptb::host {
             }
         }
         return context;
+    }
+
+    ptb_context *contextFor(int device) {
+        ptb_context *home = defaultContext();
+        int home_device = 0;
+        if(ptb_context_device(home, &home_device) == PTB_OK && home_device == device) {
+            return home;
+        }
+        static std::mutex mutex;
+        static std::map<int, ptb_context *> contexts;
+        std::lock_guard<std::mutex> lock(mutex);
+        auto found = contexts.find(device);
+        if(found == contexts.end()) {
+            ptb_context *context = nullptr;
+            if(ptb_context_create(device, &context) != PTB_OK) {
+                throw std::runtime_error(std::string("PathTrace (B200): cannot create a context on device ") + std::to_string(device) + ": " + ptb_last_error());
+            }
+            found = contexts.emplace(device, context).first;
+        }
+        return found->second;
     }
 
     void check(int status, const char *what) {

@@ -15,6 +15,9 @@ namespace ptb::host {
     //! use; throws std::runtime_error if no CUDA device is usable (there is no CPU fallback)
     ptb_context *defaultContext();
 
+    //! process-wide context of device `device` (the default context when that is its device), created on first use
+    ptb_context *contextFor(int device);
+
     //! throws std::runtime_error carrying ptb_last_error() unless status == PTB_OK
     void check(int status, const char *what);
 

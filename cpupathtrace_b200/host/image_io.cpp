@@ -40,12 +40,14 @@ namespace {
         putBE32(out, crc);
     }
 
+    // reference src/image/image_io.cpp:139-142: round(255.0 * v) evaluated in DOUBLE, then clamped to [0, 255] (a float
+    // product rounds some values across the .5 boundary: v = 0x1.383838p-1 gives 156 in float, 155 in double)
     unsigned char quantise(float v) {
-        const float scaled = std::round(v * 255.0F);
-        if(!(scaled > 0.0F)) {
+        const double scaled = std::round(255.0 * static_cast<double>(v));
+        if(!(scaled > 0.0)) {
             return 0;
         }
-        return scaled >= 255.0F ? 255 : static_cast<unsigned char>(scaled);
+        return scaled >= 255.0 ? 255 : static_cast<unsigned char>(scaled);
     }
 
     int paeth(int a, int b, int c) {
@@ -120,7 +122,25 @@ namespace io {
         writeRGBImage(path.string(), image);
     }
 
+    namespace {
+        Image<Color<float>> decodePng(std::basic_istream<char> &stream);
+    }
+
+    // Reads 8-bit, non-interlaced PNGs of every colour type (what writeRGBImage and common tools produce).  16-bit,
+    // sub-8-bit and Adam7-interlaced files, which the reference reads through libpng's EXPAND | PACKING | STRIP_16
+    // transforms (image_io.cpp:50-107), are rejected with std::logic_error -- like every other failure, including
+    // running out of memory on a hostile header.
     Image<Color<float>> readRGBImage(std::basic_istream<char> &stream) noexcept(false) {
+        try {
+            return decodePng(stream);
+        }
+        catch(const std::bad_alloc &) {
+            throw std::logic_error("readRGBImage: out of memory while decoding");
+        }
+    }
+
+    namespace {
+    Image<Color<float>> decodePng(std::basic_istream<char> &stream) {
         const std::vector<unsigned char> file((std::istreambuf_iterator<char>(stream)), std::istreambuf_iterator<char>());
         if(file.size() < 8 || std::memcmp(file.data(), kSignature, 8) != 0) {
             throw std::logic_error("readRGBImage: not a PNG stream");
@@ -198,6 +218,12 @@ namespace io {
         }
 
         const std::size_t stride = static_cast<std::size_t>(width) * channels;
+        // deflate expands at most ~1032:1: an IHDR that promises more pixels than the IDAT stream can possibly hold is
+        // rejected before anything is allocated (a 100-byte file must not trigger a multi-gigabyte allocation)
+        const long double promised = static_cast<long double>(height) * static_cast<long double>(stride + 1);
+        if(promised > 1040.0L * static_cast<long double>(packed.size()) + 1024.0L) {
+            throw std::logic_error("readRGBImage: image dimensions exceed what the compressed data can hold");
+        }
         std::vector<unsigned char> raw(static_cast<std::size_t>(height) * (stride + 1));
         uLongf raw_size = static_cast<uLongf>(raw.size());
         if(uncompress(raw.data(), &raw_size, packed.data(), static_cast<uLong>(packed.size())) != Z_OK || raw_size != raw.size()) {
@@ -280,6 +306,8 @@ namespace io {
         }
         return image;
     }
+
+    } // namespace
 
     Image<Color<float>> readRGBImage(const std::string &path) noexcept(false) {
         std::ifstream stream(path, std::ios_base::in | std::ios_base::binary);

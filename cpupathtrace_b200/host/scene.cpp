@@ -13,6 +13,7 @@
 #include <PathTrace/scene/scene.h>
 #include <PathTrace/worker.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <stdexcept>
 #include <typeinfo>
@@ -82,20 +83,50 @@ Scene::Scene(std::vector<std::unique_ptr<Object>> &&objects_in, std::vector<std:
 }
 
 Scene::~Scene() {
+    for(ptb_scene *replica : replicas) {
+        ptb_scene_destroy(replica);
+    }
     ptb_scene_destroy(device_scene);
 }
 
 Scene::Scene(Scene &&other) noexcept :
-  objects(std::move(other.objects)), light_sources(std::move(other.light_sources)), device_scene(std::exchange(other.device_scene, nullptr)) {}
+  objects(std::move(other.objects)), light_sources(std::move(other.light_sources)), device_scene(std::exchange(other.device_scene, nullptr)),
+  replicas(std::move(other.replicas)) {
+    other.replicas.clear();
+}
 
 Scene &Scene::operator=(Scene &&other) noexcept {
     if(this != &other) {
+        for(ptb_scene *replica : replicas) {
+            ptb_scene_destroy(replica);
+        }
         ptb_scene_destroy(device_scene);
         objects = std::move(other.objects);
         light_sources = std::move(other.light_sources);
         device_scene = std::exchange(other.device_scene, nullptr);
+        replicas = std::move(other.replicas);
+        other.replicas.clear();
     }
     return *this;
+}
+
+std::vector<ptb_scene *> Scene::deviceScenes(int count) const {
+    std::vector<ptb_scene *> all{device_scene};
+    int home = 0;
+    ptb::host::check(ptb_context_device(ptb::host::defaultContext(), &home), "context device");
+    int available = 0;
+    ptb::host::check(ptb_device_count(&available), "device count");
+    count = std::min(count, available);
+    // replica k lives on the k-th device after the home device (wrapping around)
+    for(int k = 1; k < count; k++) {
+        if(static_cast<std::size_t>(k) > replicas.size()) {
+            ptb_scene *copy = nullptr;
+            ptb::host::check(ptb_scene_clone(device_scene, ptb::host::contextFor((home + k) % available), &copy), "scene replica");
+            replicas.push_back(copy);
+        }
+        all.push_back(replicas[static_cast<std::size_t>(k) - 1]);
+    }
+    return all;
 }
 
 void Scene::getIntersections(const Ray *rays, std::size_t count, float *t_out, const Object **objects_out) const noexcept {

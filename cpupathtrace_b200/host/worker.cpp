@@ -2,7 +2,8 @@
 //
 // Mapping of the reference's control flow (src/worker.cpp:328-424):
 //   processJob   tile grid + thread pool + per-thread engines  ->  one ptb_render over the whole frame (the GPU grid
-//                is the worker pool); the progress callback fires from the calling thread once per tile, in order
+//                is the worker pool), or ptb_render_multi over several GPUs of this process; the progress callback fires
+//                once per tile, in order, WHILE the frame renders (as retired samples reach each tile's share)
 //   processItem  sequential per-pixel sampling with one engine ->  ptb_render over the tile's rectangle; the engine
 //                supplies the job key of the device's counter-based generator
 // The per-pixel statistics (batch Welford, adaptive acceptance, candidate merge) run in the resolve kernel.
@@ -52,7 +53,30 @@ namespace {
         return pod;
     }
 
-    Image<> renderRect(const FrameRenderJob &job, int x0, int y0, int w, int h, int tile_size, uint64_t seed, bool sharded) {
+    // Turns the render core's progress reports (pixel-samples retired so far) into the reference's callback protocol:
+    // progress_callback(k, total_tiles) for k = 1 .. total_tiles, in order, never concurrently (worker.h:76-79).  Tile k is
+    // reported as soon as k / total_tiles of the frame's samples are retired; the last tile only when the image is complete.
+    struct TileProgress {
+        const std::function<void(int, int)> *callback;
+        int total_tiles;
+        int reported;
+
+        static void onSamples(void *user, uint64_t done, uint64_t total) {
+            auto *self = static_cast<TileProgress *>(user);
+            if(total == 0) {
+                return;
+            }
+            const bool finished = done >= total;
+            int target = static_cast<int>((static_cast<long double>(done) / static_cast<long double>(total)) * self->total_tiles);
+            target = finished ? self->total_tiles : std::min(target, self->total_tiles - 1);
+            while(self->reported < target) {
+                self->reported++;
+                (*self->callback)(self->reported, self->total_tiles);
+            }
+        }
+    };
+
+    Image<> renderRect(const FrameRenderJob &job, int x0, int y0, int w, int h, int tile_size, uint64_t seed, bool whole_job, TileProgress *progress) {
         Image<> image(std::max(w, 0), std::max(h, 0));
         if(w <= 0 || h <= 0) {
             return image;
@@ -61,12 +85,23 @@ namespace {
         const ptb_camera camera = lowerCamera(job.camera);
         ptb_render_opts opts = makeOpts(job.options, seed, PTB_RNG_COUNTER, true);
         opts.tile_size = tile_size;
-        if(!sharded) {
-            // processItem renders exactly the tile it was asked for; only processJob splits the frame between processes
+        const int devices = whole_job && opts.shard_count <= 1 ? std::max(ptb::renderControl().devices, 1) : 1;
+        if(!whole_job) {
+            // processItem renders exactly the tile it was asked for; only processJob splits the frame
             opts.shard_index = 0;
             opts.shard_count = 1;
         }
-        ptb::host::check(ptb_render(job.scene.deviceScene(), &camera, &opts, x0, y0, w, h, reinterpret_cast<float *>(image.data()), nullptr), "render");
+        const ptb_progress_fn report = progress != nullptr ? &TileProgress::onSamples : nullptr;
+        if(devices > 1) {
+            const std::vector<ptb_scene *> replicas = job.scene.deviceScenes(devices);
+            ptb::host::check(ptb_render_multi(replicas.data(), static_cast<int32_t>(replicas.size()), &camera, &opts, x0, y0, w, h, reinterpret_cast<float *>(image.data()),
+                                              nullptr, report, progress),
+                             "render on several GPUs");
+        }
+        else {
+            ptb::host::check(ptb_render_with_progress(job.scene.deviceScene(), &camera, &opts, x0, y0, w, h, reinterpret_cast<float *>(image.data()), nullptr, report, progress),
+                             "render");
+        }
         return image;
     }
 
@@ -85,6 +120,14 @@ namespace ptb {
             c.shard_index = static_cast<int>(envLong("PTB_SHARD_INDEX", 0));
             c.shard_count = static_cast<int>(std::max(1L, envLong("PTB_SHARD_COUNT", 1)));
             c.fixed_seed = static_cast<uint64_t>(envLong("PTB_SEED", 0));
+            const char *devices = std::getenv("PTB_DEVICES");
+            if(devices != nullptr && std::strcmp(devices, "all") == 0) {
+                int count = 1;
+                c.devices = (ptb_device_count(&count) == PTB_OK && count > 0) ? count : 1;
+            }
+            else {
+                c.devices = static_cast<int>(std::max(1L, envLong("PTB_DEVICES", 1)));
+            }
             return c;
         }();
         return control;
@@ -108,7 +151,7 @@ Image<> processItem(const WorkItem &item, RandomEngine &re) {
     const uint64_t high = re();
     const uint64_t seed = (high << 32) | low;
     // one tile: a single group of pixels, no further subdivision
-    return renderRect(*item.job, item.offset_x, item.offset_y, item.width, item.height, std::max(std::max(item.width, item.height), 1), seed, false);
+    return renderRect(*item.job, item.offset_x, item.offset_y, item.width, item.height, std::max(std::max(item.width, item.height), 1), seed, false, nullptr);
 }
 
 Image<> processJob(const FrameRenderJob &job, const std::function<void(int, int)> &progress_callback, int /*worker_count*/) {
@@ -130,10 +173,16 @@ Image<> processJob(const FrameRenderJob &job, const std::function<void(int, int)
     const int vertical_tiles = (height + tile_size - 1) / tile_size;
     const int total_tiles = horizontal_tiles * vertical_tiles;
 
-    Image<> image = renderRect(job, 0, 0, width, height, tile_size, seed, true);
-
-    for(int tile = 0; tile < total_tiles; tile++) {
-        progress_callback(tile + 1, total_tiles);
+    if(ptb::renderControl().shard_count > 1) {
+        static bool warned = false;
+        if(!warned) {
+            warned = true;
+            std::fprintf(stderr, "PathTrace (B200): processJob renders shard %d of %d of the tile grid (ptb::RenderControl / PTB_SHARD_*); the image holds zeros in the other "
+                                 "shards' tiles until the shards are summed\n", ptb::renderControl().shard_index, ptb::renderControl().shard_count);
+        }
     }
+    TileProgress progress{&progress_callback, total_tiles, 0};
+    Image<> image = renderRect(job, 0, 0, width, height, tile_size, seed, true, &progress);
+    TileProgress::onSamples(&progress, 1, 1); // whatever the render core did not report (e.g. an image without samples)
     return image;
 }

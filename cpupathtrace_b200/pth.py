@@ -41,6 +41,7 @@ _PROTOTYPES = {
     "pth_process_item": (None, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P]),
     "pth_process_job": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pth_post_process": (None, [C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "pth_last_job_timeline": (None, [_P]),
     "pth_object_normal": (None, [_P, C.c_int, C.c_long, _P, _P]),
     "pth_object_sample": (None, [_P, C.c_int, C.c_long, _P, _P, _P]),
     "pth_bsdf_propagate": (None, [_P, C.c_int, C.c_float, C.c_long, _P, _P, _P, _P]),
@@ -49,9 +50,11 @@ _PROTOTYPES = {
 _OPTIONAL = {
     "pth_scene_device_handle": (_P, [_P]),
     "pth_png_roundtrip": (C.c_long, [C.c_int, C.c_int, _P, _P]),
+    "pth_png_decode_status": (C.c_int, [C.c_char_p, C.c_long]),
     "pth_set_fast_queries": (None, [C.c_int, C.c_int, C.c_int]),
     "pth_set_sharding": (None, [C.c_int, C.c_int, C.c_uint64]),
     "pth_set_render_control": (None, [C.c_int, C.c_int]),
+    "pth_set_devices": (C.c_int, [C.c_int]),
 }
 
 REF_PARITY = os.path.join(REPO_ROOT, "oracle", "_ref", "libpth_ref.so")
@@ -85,6 +88,10 @@ class Pth:
     def set_fast_queries(self, certified_closest, any_hit_shadows, skip_null_shadows):
         """b200 build only: ptb::RenderControl's result-neutral query options for every later call of this process."""
         self.lib.pth_set_fast_queries(int(certified_closest), int(any_hit_shadows), int(skip_null_shadows))
+
+    def set_devices(self, devices):
+        """b200 build only: GPUs of this process processJob renders on (ptb::RenderControl::devices); returns how many it will use."""
+        return self.lib.pth_set_devices(int(devices))
 
     def set_render_control(self, max_depth=-1, relaxed_guard=None):
         """b200 build only: ptb::RenderControl::max_depth / relaxed_guard (None / negative = unchanged)."""
@@ -122,6 +129,10 @@ class Pth:
         out = np.zeros_like(img)
         n = self.lib.pth_png_roundtrip(w, h, _ptr(img), _ptr(out))
         return out, n
+
+    def png_decode_status(self, data):
+        """b200 build only: io::readRGBImage on raw bytes; 0 = decoded, 1 = std::logic_error, 2 = any other exception."""
+        return self.lib.pth_png_decode_status(bytes(data), len(data))
 
     def builder(self):
         return PthBuilder(self)
@@ -275,7 +286,10 @@ class PthScene:
         out = np.zeros((max(height, 0), max(width, 0), 4), np.float32)
         total, mono = C.c_int(), C.c_int()
         calls = self.pth.lib.pth_process_job(self.h, camera.h, width, height, min_spp, max_spp, epsilon, workers, _ptr(out), C.byref(total), C.byref(mono))
-        return out, {"callbacks": calls, "total_tiles": total.value, "monotonic": bool(mono.value)}
+        timeline = np.zeros(3, np.float64)
+        self.pth.lib.pth_last_job_timeline(_ptr(timeline))
+        return out, {"callbacks": calls, "total_tiles": total.value, "monotonic": bool(mono.value), "seconds": float(timeline[0]),
+                     "first_callback_s": float(timeline[1]), "half_callbacks_s": float(timeline[2])}
 
     def device_handle(self):
         """b200 build only: the ptb_scene* behind the C++ Scene, for direct C-ABI calls on the same scene."""

@@ -22,7 +22,9 @@
 #include <PathTrace/scene/object.h>
 #include <PathTrace/scene/scene.h>
 
+#include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -43,6 +45,8 @@ namespace {
         std::unique_ptr<Scene> scene;
         std::unordered_map<const Object *, int> ids;
     };
+
+    double g_last_job_timeline[3] = {0.0, -1.0, -1.0};
 
     vec3<float> v3(const float *p) {
         return vec3<float>{p[0], p[1], p[2]};
@@ -507,13 +511,27 @@ int pth_process_job(void *scene, void *camera, int width, int height, int min_sa
     int last = 0;
     int total = 0;
     bool ok = true;
+    const auto start = std::chrono::steady_clock::now();
+    double first_callback = -1.0;
+    double middle_callback = -1.0;
     auto callback = [&](int completed, int tiles) {
         calls++;
         ok = ok && (completed == last + 1);
         last = completed;
         total = tiles;
+        const double now = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+        if(first_callback < 0.0) {
+            first_callback = now;
+        }
+        if(middle_callback < 0.0 && 2 * completed >= tiles) {
+            middle_callback = now;
+        }
     };
     Image<> image = processJob(job, callback, worker_count);
+    const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    g_last_job_timeline[0] = elapsed;
+    g_last_job_timeline[1] = first_callback;
+    g_last_job_timeline[2] = middle_callback;
     if(image.size() > 0) {
         std::memcpy(out, image.data(), sizeof(float) * 4 * image.size());
     }
@@ -524,6 +542,14 @@ int pth_process_job(void *scene, void *camera, int width, int height, int min_sa
         *monotonic = ok ? 1 : 0;
     }
     return calls;
+}
+
+// seconds: [0] duration of the last pth_process_job's processJob call, [1] when its first progress callback fired,
+// [2] when the callback for half of the tiles fired (both measured from the start of the call; -1 = never)
+void pth_last_job_timeline(double *out3) {
+    out3[0] = g_last_job_timeline[0];
+    out3[1] = g_last_job_timeline[1];
+    out3[2] = g_last_job_timeline[2];
 }
 
 // ---------------------------------------------------------------- post-processing (host-side API kept as is)
@@ -566,7 +592,20 @@ extern "C" void pth_set_fast_queries(int certified_closest, int any_hit_shadows,
     control.skip_null_shadows = skip_null_shadows != 0;
 }
 
-// b200 build only: the remaining knobs of ptb::RenderControl (negative = leave unchanged)
+#include <ptb.h> // b200 build only: ptb_device_count
+
+// b200 build only: the remaining knobs of ptb::RenderControl (negative = leave unchanged); returns the GPUs processJob
+// will really use (devices capped by the devices present)
+extern "C" int pth_set_devices(int devices) {
+    ptb::RenderControl &control = ptb::renderControl();
+    int present = 1;
+    ptb_device_count(&present);
+    if(devices > 0) {
+        control.devices = devices;
+    }
+    return std::min(control.devices, std::max(present, 1));
+}
+
 extern "C" void pth_set_render_control(int max_depth, int relaxed_guard) {
     ptb::RenderControl &control = ptb::renderControl();
     if(max_depth >= 0) {
@@ -607,6 +646,21 @@ extern "C" long pth_png_roundtrip(int width, int height, const float *pixels_in,
     }
     catch(const std::exception &) {
         return -1;
+    }
+}
+
+// b200 build only: io::readRGBImage on raw bytes; 0 = decoded, 1 = std::logic_error (the documented failure), 2 = anything else
+extern "C" int pth_png_decode_status(const unsigned char *bytes, long length) {
+    try {
+        std::stringstream stream(std::string(reinterpret_cast<const char *>(bytes), static_cast<size_t>(length)), std::ios_base::in | std::ios_base::binary);
+        io::readRGBImage(stream);
+        return 0;
+    }
+    catch(const std::logic_error &) {
+        return 1;
+    }
+    catch(...) {
+        return 2;
     }
 }
 #endif

@@ -23,6 +23,8 @@ class Scene {
     std::vector<std::unique_ptr<Object>> objects;
     std::vector<std::unique_ptr<LightSource>> light_sources;
     ptb_scene *device_scene = nullptr;
+    //! copies of the device scene on further GPUs of this process (B200 extension, see deviceScenes())
+    mutable std::vector<ptb_scene *> replicas;
 
   public:
     /**
@@ -53,6 +55,11 @@ class Scene {
 
     //! the device-resident scene (C-ABI handle, owned by this Scene)
     ptb_scene *deviceScene() const noexcept { return device_scene; }
+
+    //! the device scene followed by copies of it on up to count - 1 further GPUs of this process (created on first use by
+    //! device-to-device copies, no BVH rebuild; owned by this Scene): what processJob renders on when
+    //! ptb::RenderControl::devices > 1.  Not thread-safe against concurrent calls on the same Scene.
+    std::vector<ptb_scene *> deviceScenes(int count) const;
 
     std::size_t objectCount() const noexcept { return objects.size(); }
 };

@@ -72,6 +72,7 @@ namespace ptb {
         bool skip_null_shadows = true; //!< do not trace shadow rays whose contribution is always zero (glass, mirror, surfaces facing away)
         bool certified_closest = true; //!< closest hits on the SAH hierarchy where a certificate proves the reference's result, else re-traced
         bool relaxed_guard = true;    //!< processJob / processItem (counter-based generator) skip the certified walk's guard table; renderSamples never does
+        int devices = 1;              //!< processJob: GPUs of this process to render on (ptb_render_multi; capped by the devices present)
         uint64_t fixed_seed = 0;      //!< processJob: non-zero replaces std::random_device
         int shard_index = 0;          //!< multi-GPU, one process per GPU: this process renders tile k of the frame's tile grid iff
         int shard_count = 1;          //!< k % shard_count == shard_index and leaves the other pixels 0 (sum-reduce the images)

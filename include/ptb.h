@@ -265,6 +265,28 @@ int ptb_occluded(ptb_scene *scene, const float *rays, uint64_t n_rays, uint8_t *
 int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts *opts, int32_t x0, int32_t y0, int32_t w, int32_t h, float *out_rgba,
                ptb_render_stats *stats);
 
+/* ptb_render with progress reports: `progress(user, samples_done, samples_total)` is called from the calling thread while
+ * the frame renders (between batches of bounce iterations: samples_done = pixel-samples retired so far) and once more
+ * when everything is done.  It is what processJob's progress_callback (src/worker.cpp:354-360: fired as tiles complete)
+ * is driven by.  progress may be NULL. */
+typedef void (*ptb_progress_fn)(void *user, uint64_t samples_done, uint64_t samples_total);
+int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts *opts, int32_t x0, int32_t y0, int32_t w, int32_t h,
+                             float *out_rgba, ptb_render_stats *stats, ptb_progress_fn progress, void *user);
+
+/* ---- several GPUs, one process, one call (processJob's contract: one call -> the whole image, src/worker.cpp:389-424)
+ *
+ * ptb_scene_clone copies a scene's device arrays to the device of `ctx` (no BVH rebuild).  ptb_render_multi renders the
+ * rectangle on n replicas of one scene at once -- one host thread per replica, tile k of the tile grid on replica
+ * k % n, exactly the tiles ptb_render renders with shard_index = replica -- then ONE kernel on the first replica's device
+ * reads every replica's owned tiles over NVLink (peer access; staged copies where peers cannot map each other) into the
+ * final image, which is copied to out_rgba (host pointer, or a pointer on the first replica's device with
+ * PTB_FLAG_DEVICE_IO).  Bit-identical to ptb_render on one device.  stats: n entries (one per replica) or NULL.
+ * progress may be called from any of the n threads, never concurrently. */
+int ptb_device_count(int *count_out);
+int ptb_scene_clone(const ptb_scene *scene, ptb_context *ctx, ptb_scene **out);
+int ptb_render_multi(ptb_scene *const *replicas, int32_t n, const ptb_camera *camera, const ptb_render_opts *opts, int32_t x0, int32_t y0, int32_t w, int32_t h,
+                     float *out_rgba, ptb_render_stats *stats, ptb_progress_fn progress, void *user);
+
 /* Validation entry: one impl::getSample (src/worker.cpp:26-146) per (pixel, seed) with rng_mode
  * PTB_RNG_REFERENCE_XORSHIFT == RandomEngine(seed).  pixels: 2 ints each; out_rgba: 4 floats each (alpha = collected). */
 int ptb_render_samples(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts *opts, uint64_t n, const int32_t *pixels,

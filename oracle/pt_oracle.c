@@ -555,8 +555,9 @@ typedef struct {
     float plane_h[PTO_GUARD_PLANES];
     float plane_w[PTO_GUARD_PLANES];
     float plane_cone[PTO_GUARD_PLANES];
-    float plane_k[PTO_GUARD_PLANES]; /* band = k * (|o - centre| + radius) */
-    float plane_c[PTO_GUARD_PLANES][3];
+    float plane_k[PTO_GUARD_PLANES]; /* band = k * (|o - box centre| + half diagonal) */
+    float plane_lo[PTO_GUARD_PLANES][3]; /* box of the triangles behind the plane */
+    float plane_hi[PTO_GUARD_PLANES][3];
     float plane_r[PTO_GUARD_PLANES];
     int n_spheres;
     float sphere[PTO_GUARD_SPHERES][4];
@@ -614,20 +615,20 @@ static void guard_build(const pto_scene *s, pto_guard *g) {
             double x = (corner & 1) ? hi[0] : lo[0], y = (corner & 2) ? hi[1] : lo[1], z = (corner & 4) ? hi[2] : lo[2];
             w = fmax(w, fabs(n[0] * x + n[1] * y + n[2] * z - h));
         }
-        double centre[3] = {a[0] + (ab[0] + ac[0]) / 3.0, a[1] + (ab[1] + ac[1]) / 3.0, a[2] + (ab[2] + ac[2]) / 3.0};
         double k_u = 4.0 * c_u / slack;
-        /* merge with an existing plane: same normal up to sign within 1e-4, same offset within the thickness scale */
+        /* merge with an existing plane: same normal up to sign, same offset */
         int merged = 0;
         for(int j = 0; j < g->n_planes && !merged; j++) {
             double dotn = n[0] * g->plane_n[j][0] + n[1] * g->plane_n[j][1] + n[2] * g->plane_n[j][2];
             double hj = dotn >= 0.0 ? h : -h;
             if(fabs(fabs(dotn) - 1.0) < 1e-8 && fabs(hj - g->plane_h[j]) <= 1e-6 * (1.0 + fabs(hj))) {
-                double dc[3] = {centre[0] - g->plane_c[j][0], centre[1] - g->plane_c[j][1], centre[2] - g->plane_c[j][2]};
-                double dist = sqrt(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]);
-                g->plane_r[j] = (float)(fmax(g->plane_r[j], dist + diam) * 1.0001);
-                g->plane_w[j] = (float)(fmax(g->plane_w[j], w) * 1.0001);
-                g->plane_cone[j] = (float)(fmax(g->plane_cone[j], cone) * 1.0001);
-                g->plane_k[j] = (float)(fmax(g->plane_k[j], k_u) * 1.0001);
+                for(int c = 0; c < 3; c++) {
+                    g->plane_lo[j][c] = fminf(g->plane_lo[j][c], lo[c]);
+                    g->plane_hi[j][c] = fmaxf(g->plane_hi[j][c], hi[c]);
+                }
+                g->plane_w[j] = (float)fmax(g->plane_w[j], w * 1.0001 + 1e-7 * (1.0 + fabs(h)));
+                g->plane_cone[j] = (float)fmax(g->plane_cone[j], cone * 1.0001);
+                g->plane_k[j] = (float)fmax(g->plane_k[j], k_u * 1.0001);
                 merged = 1;
             }
         }
@@ -639,41 +640,50 @@ static void guard_build(const pto_scene *s, pto_guard *g) {
         int j = g->n_planes++;
         for(int c = 0; c < 3; c++) {
             g->plane_n[j][c] = (float)n[c];
-            g->plane_c[j][c] = (float)centre[c];
+            g->plane_lo[j][c] = lo[c];
+            g->plane_hi[j][c] = hi[c];
         }
         g->plane_h[j] = (float)h;
         g->plane_w[j] = (float)(w * 1.0001 + 1e-7 * (1.0 + fabs(h)));
         g->plane_cone[j] = (float)(cone * 1.0001);
         g->plane_k[j] = (float)(k_u * 1.0001);
-        g->plane_r[j] = (float)(diam * 1.0001);
+    }
+    for(int j = 0; j < g->n_planes; j++) {
+        double dx = (double)g->plane_hi[j][0] - g->plane_lo[j][0], dy = (double)g->plane_hi[j][1] - g->plane_lo[j][1], dz = (double)g->plane_hi[j][2] - g->plane_lo[j][2];
+        g->plane_r[j] = (float)(0.5 * sqrt(dx * dx + dy * dy + dz * dz) * 1.0001);
     }
     g->tau_safe = (float)(tau_safe * 1.0001);
 }
 
-/* 1: the ray must be traced by the reference-order walk */
+/* 1: the ray must be traced by the reference-order walk (same arithmetic as guardFlagsRay in csrc/traverse.cuh) */
 static int guard_flags_ray(const pto_guard *g, const ray *r) {
     if(!g->enabled) return 1;
     for(int j = 0; j < g->n_planes; j++) {
-        float hd = (g->plane_n[j][0] * r->o.x + g->plane_n[j][1] * r->o.y + g->plane_n[j][2] * r->o.z) - g->plane_h[j];
-        float cd = g->plane_n[j][0] * r->d.x + g->plane_n[j][1] * r->d.y + g->plane_n[j][2] * r->d.z;
-        if(fabsf(cd) < g->plane_cone[j]) return 1;
+        float hd = ((g->plane_n[j][0] * r->o.x + g->plane_n[j][1] * r->o.y) + g->plane_n[j][2] * r->o.z) - g->plane_h[j];
+        float cd = (g->plane_n[j][0] * r->d.x + g->plane_n[j][1] * r->d.y) + g->plane_n[j][2] * r->d.z;
         float ahd = fabsf(hd);
-        if(ahd <= g->plane_w[j]) return 1;
-        if(hd * cd < 0.0F) {
-            float dx = r->o.x - g->plane_c[j][0], dy = r->o.y - g->plane_c[j][1], dz = r->o.z - g->plane_c[j][2];
-            float rho = sqrtf(dx * dx + dy * dy + dz * dz) + g->plane_r[j];
-            if(ahd < g->plane_w[j] + g->plane_k[j] * rho) return 1;
+        float dx = r->o.x - 0.5F * (g->plane_lo[j][0] + g->plane_hi[j][0]);
+        float dy = r->o.y - 0.5F * (g->plane_lo[j][1] + g->plane_hi[j][1]);
+        float dz = r->o.z - 0.5F * (g->plane_lo[j][2] + g->plane_hi[j][2]);
+        float band = g->plane_k[j] * (sqrtf((dx * dx + dy * dy) + dz * dz) + g->plane_r[j]);
+        if(fabsf(cd) < g->plane_cone[j] || ahd <= g->plane_w[j] + band) {
+            float entry = box_hit(g->plane_lo[j], g->plane_hi[j], r);
+            if(entry >= 0.0F && (fabsf(cd) < g->plane_cone[j] || entry * fabsf(cd) < band)) return 1;
         }
     }
     for(int j = 0; j < g->n_spheres; j++) {
         float cx = r->o.x - g->sphere[j][0], cy = r->o.y - g->sphere[j][1], cz = r->o.z - g->sphere[j][2];
-        float r2 = g->sphere[j][3] * g->sphere[j][3];
-        float co2 = cx * cx + cy * cy + cz * cz;
-        if(co2 < 3.24F * r2) return 1;
-        if(co2 < 9.0F * r2) {
-            float dd = r->d.x * cx + r->d.y * cy + r->d.z * cz;
-            float disc = dd * dd - co2 + r2;
-            if(fabsf(disc) < r2 * 0.0625F) return 1;
+        float radius = g->sphere[j][3];
+        float r2 = radius * radius;
+        float reach = fmaxf(fmaxf(fabsf(cx), fabsf(cy)), fabsf(cz));
+        if(reach > radius) { /* inside the sphere's box the leaf is always reached (entry 0) and tested exactly */
+            if(reach <= 1.01F * radius) return 1;
+            float co2 = (cx * cx + cy * cy) + cz * cz;
+            if(co2 < 9.0F * r2) {
+                float dd = (r->d.x * cx + r->d.y * cy) + r->d.z * cz;
+                float disc = dd * dd - co2 + r2;
+                if(fabsf(disc) < r2 * 0.0625F) return 1;
+            }
         }
     }
     return 0;

@@ -82,6 +82,42 @@ def test_png_round_trip(b200):
     assert np.abs(decoded - clipped).max() <= 0.5 / 255 + 1e-6  # round(255 v), not truncation
 
 
+def test_png_quantisation_matches_the_reference_formula(b200):
+    """reference src/image/image_io.cpp:139-142 quantises round(255.0 * v) in double; values whose float product would
+    round across a .5 boundary (v = 0x1.383838p-1 -> 155, not 156) must come out as the double formula says."""
+    levels = np.arange(0, 255, dtype=np.float64) + 0.5
+    centre = (levels / 255.0).astype(np.float32)
+    near = np.concatenate([np.nextafter(centre, np.float32(0)), centre, np.nextafter(centre, np.float32(1)), np.float32([float.fromhex("0x1.383838p-1")])])
+    rng = np.random.Generator(np.random.PCG64(5))
+    values = np.concatenate([near, rng.uniform(0, 1, 4 * 64 * 64 - len(near)).astype(np.float32)])
+    image = values.reshape(64, 64, 4)
+    decoded, n_bytes = b200.png_roundtrip(image)
+    assert n_bytes > 0
+    want = np.clip(np.round(255.0 * image.astype(np.float64)), 0, 255)
+    assert np.array_equal(np.round(decoded.astype(np.float64) * 255.0), want)
+
+
+def test_png_reader_rejects_hostile_headers_with_logic_error(b200):
+    """A tiny file whose IHDR promises 65535 x 65535 pixels must fail with the documented std::logic_error, not allocate
+    gigabytes or throw std::bad_alloc; so must truncated streams and 16-bit / interlaced files (documented as unsupported)."""
+    import struct
+    import zlib
+
+    def chunk(kind, payload):
+        return struct.pack(">I", len(payload)) + kind + payload + struct.pack(">I", zlib.crc32(kind + payload) & 0xFFFFFFFF)
+
+    def png(width, height, depth=8, colour=6, interlace=0, data=b"\x00" * 16):
+        ihdr = struct.pack(">IIBBBBB", width, height, depth, colour, 0, 0, interlace)
+        return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", zlib.compress(data)) + chunk(b"IEND", b"")
+
+    assert b200.png_decode_status(png(65535, 65535)) == 1
+    assert b200.png_decode_status(png(2, 2, depth=16, data=b"\x00" * 34)) == 1
+    assert b200.png_decode_status(png(2, 2, interlace=1, data=b"\x00" * 18)) == 1
+    assert b200.png_decode_status(png(2, 2, data=b"\x00" * 18)[:-20]) == 1
+    assert b200.png_decode_status(png(2, 2, data=b"\x00" * 18)) == 0
+    assert b200.png_decode_status(b"not a png") == 1
+
+
 def test_tile_sharding_partitions_the_frame():
     for (w, h, world) in [(1920, 1080, 8), (132, 68, 3), (16, 16, 2), (1, 1, 4), (100, 37, 5)]:
         owners = sharding.owner_map(w, h, world)
