@@ -1,6 +1,11 @@
 #!/usr/bin/env python
-"""bench.py — Msamples/s and Mrays/s of the render hot path on BASELINE.json's configs[1]:
-Cornell box + dragon at 1920x1080, 256 spp, on N B200 (one process per GPU).
+"""bench.py — Msamples/s and Mrays/s of the render hot path on BASELINE.json's configs:
+
+  --gpus 1 (default)   configs[1] "C2": Cornell box + dragon at 1920x1080, 256 spp, 1 B200
+  --gpus 2/4/8         configs[3] "C4": the same scene at 1024 spp, max depth 16, image-tile split over the GPUs
+  --config c5          configs[4] "C5": 3840x2160 at 4096 spp (meant for 8 GPUs)
+  --workload soup      configs[2] "C3": random-triangle soup (--tris Mi triangles), 2^24 coherent / incoherent / shadow rays
+                       through ptb_intersect / ptb_occluded (metric: Mrays/s)
 
 The XYZ RGB dragon asset is absent from the reference checkout, so the scene uses the deterministic stand-in mesh of
 SURVEY.md section 8d ("stand-in-1M": 1000 x 500 bumpy torus, 1 M triangles, the demo's glass material and transform).
@@ -44,11 +49,17 @@ def parse_args():
     p.add_argument("--steps", type=int, default=2)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--width", type=int, default=1920)
-    p.add_argument("--height", type=int, default=1080)
-    p.add_argument("--spp", type=int, default=256)
+    p.add_argument("--workload", default="render", choices=["render", "soup"])
+    p.add_argument("--config", default="auto", choices=["auto", "c2", "c4", "c5"],
+                   help="render workload: auto = c2 on one GPU, c4 on several (BASELINE.json configs[1] / configs[3]); --width/--height/--spp/--max-depth override")
+    p.add_argument("--width", type=int, default=None)
+    p.add_argument("--height", type=int, default=None)
+    p.add_argument("--spp", type=int, default=None)
+    p.add_argument("--tris", type=int, default=4, help="soup workload: Mi triangles (1..16)")
+    p.add_argument("--rays", default="incoherent", choices=["coherent", "incoherent", "shadow"], help="soup workload: ray set (2^24 rays)")
+    p.add_argument("--n-rays", type=int, default=1 << 24)
     p.add_argument("--mesh", default="1000x500", help="stand-in mesh grid nu x nv (2 triangles per cell); 'none' = Cornell only")
-    p.add_argument("--max-depth", type=int, default=0, help="0 = unlimited, as the reference")
+    p.add_argument("--max-depth", type=int, default=None, help="0 = unlimited, as the reference (default: the config's)")
     p.add_argument("--reference-closest", action="store_true",
                    help="closest-hit queries walk the reference-topology tree only (default: certified SAH walk + re-trace of uncertified rays)")
     p.add_argument("--reference-shadows", action="store_true",
@@ -57,12 +68,24 @@ def parse_args():
                    help="certified closest hits with the guard table (the exact mode validation uses); default: relaxed, as production renders")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of one reference-arm sample")
-    return p.parse_args()
+    args = p.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", str(max(args.gpus, 1))))
+    name = args.config if args.config != "auto" else ("c2" if world <= 1 else "c4")
+    width, height, spp, depth = {"c2": (1920, 1080, 256, 0), "c4": (1920, 1080, 1024, 16), "c5": (3840, 2160, 4096, 16)}[name]
+    args.config_name = name
+    args.width = args.width if args.width is not None else width
+    args.height = args.height if args.height is not None else height
+    args.spp = args.spp if args.spp is not None else spp
+    args.max_depth = args.max_depth if args.max_depth is not None else depth
+    return args
 
 
 def mesh_arg(args):
+    """--mesh: 'none', a stand-in grid 'NUxNV', or the path of an OBJ file (the real xyzrgb_dragon.obj drops in here)."""
     if args.mesh == "none":
         return None, "cornell-only"
+    if os.path.isfile(args.mesh):
+        return args.mesh, "obj:" + os.path.basename(args.mesh)
     nu, nv = (int(v) for v in args.mesh.lower().split("x"))
     return (nu, nv), f"stand-in-{2 * nu * nv}"
 
@@ -72,7 +95,9 @@ def build_spec(args):
 
     grid, label = mesh_arg(args)
     mesh = None
-    if grid is not None:
+    if isinstance(grid, str):
+        mesh = ("obj", open(grid, "rb").read())  # io::loadMesh with the demo's transform, cull = false, smooth = true
+    elif grid is not None:
         verts, normals = scenes.standin_triangles(grid[0], grid[1], scenes.DEMO_DRAGON_TRANSFORM)
         mesh = ("triangles", verts, normals)
     return scenes.cornell_demo(mesh), label
@@ -80,8 +105,8 @@ def build_spec(args):
 
 def config_dict(args, label, n_gpus):
     return {
-        "workload": f"Cornell box + {label} glass mesh (xyzrgb_dragon.obj is absent from the reference checkout), "
-                    f"{args.width}x{args.height}, {args.spp} spp (min=max), demo camera (thin lens), eps 1e-3",
+        "workload": f"BASELINE configs[{ {'c2': 1, 'c4': 3, 'c5': 4}[args.config_name] }]: Cornell box + {label} glass mesh (xyzrgb_dragon.obj is absent from the reference "
+                    f"checkout), {args.width}x{args.height}, {args.spp} spp (min=max), max depth {args.max_depth or 'unlimited'}, demo camera (thin lens), eps 1e-3",
         "image": [args.width, args.height],
         "spp": args.spp,
         "max_depth": args.max_depth,
@@ -208,7 +233,7 @@ def run_reference_arm(args):
         "warmup": warmup,
         "ms_per_step": base["seconds_per_step"] * 1e3,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
@@ -236,10 +261,14 @@ def run_b200_arm(args):
         raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     os.environ["PTB_DEVICE"] = str(local_rank)
+    control = None
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # host-side barrier for the phases in which only rank 0 works (a NCCL barrier would keep a spinning kernel on every
+        # waiting GPU, and rank 0's in-library multi-GPU render uses those GPUs)
+        control = dist.new_group(backend="gloo")
     else:
         dist = None
 
@@ -362,6 +391,20 @@ def run_b200_arm(args):
         dist.all_gather(gathered, mine)
         per_rank = {"render_ms": [round(float(g[0]), 2) for g in gathered], "reduce_ms_incl_wait": [round(float(g[1]), 2) for g in gathered]}
 
+    # ---- profile pass (untimed): one more frame with CUDA events around EVERY launch for the per-kernel breakdown (the
+    # timed steps time only the closest-hit trace per launch: the ~300 extra event pairs cost 4-5 % of a frame)
+    pstats = capi.RenderStats()
+    po = opts(args.spp, capi.PTB_FLAG_DEVICE_IO | capi.PTB_FLAG_PROFILE_ALL, 98)
+    capi.check(lib.ptb_render(handle, C.byref(camera), C.byref(po), 0, 0, args.width, args.height, C.c_void_p(image.data_ptr()), C.byref(pstats)))
+    breakdown = {
+        "source": "one untimed frame with PTB_FLAG_PROFILE_ALL (events around every launch)",
+        "frame_ms": pstats.device_ms_total,
+        "closest_trace_ms": pstats.device_ms_trace - pstats.device_ms_trace_shadow,
+        "shadow_trace_ms": pstats.device_ms_trace_shadow,
+        "generate_shade_accumulate_resolve_ms": pstats.device_ms_shade,
+        "shadow_mrays_per_s": pstats.shadow_rays / max(pstats.device_ms_trace_shadow, 1e-9) / 1e3,
+    }
+
     # ---- counting pass (untimed, after the timed steps so that a profiler attached to this command meets steady-state
     # launches first): inner / leaf fetches per ray of the same traversal at reduced spp
     count_spp = max(1, min(args.spp, 2))
@@ -393,9 +436,10 @@ def run_b200_arm(args):
     # algorithmic bytes per ray x the rays it traced / its CUDA-event time.  The north star's figure over ALL rays
     # (closest + shadow kernels) is reported next to it as frac_all_rays.
     rank_rays = float(totals["closest"] + totals["shadow"])
-    trace_s = totals["trace_ms"] / 1e3
+    closest_s = totals["trace_ms"] / 1e3  # the timed steps time the closest-hit trace only (class 0 events)
+    # all traversal kernels: the closest-hit time of the timed steps plus the shadow-trace time of the profile pass
+    trace_s = closest_s + breakdown["shadow_trace_ms"] / 1e3 * args.steps
     achieved_all = bytes_per_ray * rank_rays / max(trace_s, 1e-12) / 1e9
-    closest_s = (totals["trace_ms"] - totals["shadow_ms"]) / 1e3
     closest_bytes_per_ray = INNER_BYTES * count_detail["closest_inner_per_ray"] + LEAF_BYTES * count_detail["closest_leaf_per_ray"] + RAY_RECORD_BYTES
     achieved = closest_bytes_per_ray * float(totals["closest"]) / max(closest_s, 1e-12) / 1e9
     closest_launches = max(int(totals["iterations"]), 1)
@@ -418,23 +462,33 @@ def run_b200_arm(args):
         except ValueError:
             traffic = None
 
-    # ---- e2e through the reference-facing API with host buffers
+    # ---- e2e through the reference-facing API with host buffers: processJob (one call -> the whole image in host memory).
+    # On several GPUs rank 0 alone calls it, with ptb::RenderControl::devices = N: the library itself renders on all N GPUs
+    # of the node (ptb_render_multi: a host thread and a scene replica per GPU, NVLink gather of the tiles, one D2H) while
+    # the other ranks wait on the host.
+    def host_barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier(group=control)
+
     e2e_ms = []
+    e2e_devices = 1
+    if rank == 0:
+        e2e_devices = b200.set_devices(world)
+        b200.set_sharding(0, 1, 2999)
+        scene_cpp.process_job(camera_cpp, args.width, args.height, min(args.spp, 8), min(args.spp, 8), 1e-3, 0)  # replicas + workspaces
     for i in range(args.steps):
         flush.zero_()
-        barrier()
-        t0 = time.perf_counter()
-        if world == 1:
+        host_barrier()
+        if rank == 0:
+            t0 = time.perf_counter()
             b200.set_sharding(0, 1, 3000 + i)
             scene_cpp.process_job(camera_cpp, args.width, args.height, args.spp, args.spp, 1e-3, 0)
-        else:
-            device_step(3000 + i)
-            if rank == 0:
-                host_image.copy_(image, non_blocking=False)
-        torch.cuda.synchronize()
-        e2e_ms.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
-        barrier()
-    e2e_value = (job_samples / args.steps) / (np.mean(e2e_ms) / 1e3) / 1e6
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        host_barrier()
+    if rank == 0:
+        b200.set_devices(1)
+    e2e_value = (job_samples / args.steps) / (np.mean(e2e_ms) / 1e3) / 1e6 if rank == 0 else 0.0
 
     if rank != 0:
         if dist is not None:
@@ -455,7 +509,7 @@ def run_b200_arm(args):
         "warmup": args.warmup,
         "ms_per_step": float(np.mean(step_ms)),
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
@@ -468,7 +522,7 @@ def run_b200_arm(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": C.sizeof(capi.Camera) + C.sizeof(capi.RenderOpts),
                 "d2h_bytes_per_step": args.width * args.height * 16, "ms_per_step": float(np.mean(e2e_ms)),
-                "api": "processJob (C++ host API via harness)" if world == 1 else "ptb_render + NCCL reduce + D2H"},
+                "api": "processJob (C++ host API via harness)" + ("" if world == 1 else f", one call on rank 0 rendering on {e2e_devices} GPUs in-library (ptb_render_multi)")},
         "gpu_launches": int(totals["launches"]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "traffic_source": traffic_note, "peak_source": f"{peak_source} HBM copy bandwidth",
@@ -478,11 +532,12 @@ def run_b200_arm(args):
                      "ms_per_launch": closest_s * 1e3 / closest_launches,
                      "frac_all_rays": achieved_all / peak, "achieved_all_rays": achieved_all, "bytes_per_ray_all_rays": bytes_per_ray,
                      "inner_fetches_per_ray": inner_per_ray, "leaf_fetches_per_ray": leaf_per_ray,
-                     "trace_ms_per_step": totals["trace_ms"] / args.steps, "shade_ms_per_step": totals["shade_ms"] / args.steps,
-                     "trace_share_of_step": totals["trace_ms"] / max(sum(step_ms), 1e-9), "mrays_per_s_trace_only": rank_rays / max(trace_s, 1e-12) / 1e6,
-                     "shadow_trace_ms_per_step": totals["shadow_ms"] / args.steps,
-                     "closest_mrays_per_s": totals["closest"] / max(totals["trace_ms"] - totals["shadow_ms"], 1e-9) / 1e3,
-                     "shadow_mrays_per_s": totals["shadow"] / max(totals["shadow_ms"], 1e-9) / 1e3, **count_detail},
+                     "closest_trace_ms_per_step": totals["trace_ms"] / args.steps, "closest_trace_share_of_step": totals["trace_ms"] / max(sum(step_ms), 1e-9),
+                     "trace_ms_per_step": trace_s * 1e3 / args.steps, "shade_ms_per_step": breakdown["generate_shade_accumulate_resolve_ms"],
+                     "shadow_trace_ms_per_step": breakdown["shadow_trace_ms"], "mrays_per_s_trace_only": rank_rays / max(trace_s, 1e-12) / 1e6,
+                     "closest_mrays_per_s": totals["closest"] / max(totals["trace_ms"], 1e-9) / 1e3,
+                     "shadow_mrays_per_s": breakdown["shadow_mrays_per_s"], **count_detail},
+        "breakdown": breakdown,
         "cpu_baseline": cpu_baseline,
         "scene": {"prims": int(info.n_prims), "inner_nodes": int(info.n_inner_nodes), "bvh_depth": int(info.bvh_depth),
                   "device_mb": info.device_bytes / 2**20, "build_s": info.build_seconds, "scene_ctor_s": t_build,
@@ -492,6 +547,284 @@ def run_b200_arm(args):
         "certificate_audit": None if args.reference_closest else certificate_audit,
         "closest_hit": ("reference-topology tree" if args.reference_closest else
                         f"certified SAH walk; {totals['retraced']} of {totals['closest']} closest-hit rays had no certificate and were re-traced on the reference tree"),
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+
+# ------------------------------------------------------------------------------------------------ C3: triangle soup
+
+
+def soup_scene_arrays(args):
+    """BASELINE configs[2] / SURVEY 8d: N random triangles, centres uniform in [-1,1]^3, vertices = centre + uniform[-s,s]^3,
+    s = 0.5 N^(-1/3), no culling; seed 0x5EED0000 + log2 N."""
+    from cpupathtrace_b200 import capi, scenes
+
+    n_tris = args.tris << 20
+    verts = scenes.soup_triangles(n_tris, 0x5EED0000 + int(np.log2(n_tris)))
+    prims = np.zeros(n_tris, capi.PRIM_DTYPE)
+    prims["kind"] = capi.PTB_PRIM_TRIANGLE
+    prims["p"][:, :9] = verts
+    a, b, c = verts[:, 0:3], verts[:, 3:6], verts[:, 6:9]
+    nrm = np.cross(b - a, c - a)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)
+    prims["p"][:, 9:12] = prims["p"][:, 12:15] = prims["p"][:, 15:18] = nrm
+    mats = np.zeros(1, capi.MATERIAL_DTYPE)
+    mats[0] = ((1, 1, 1, 1), (0, 0, 0, 0), 1.0, 0, 0, 0)
+    return prims, mats
+
+
+def soup_rays_host(kind, n, seed=0x7A750001):
+    """coherent: pinhole at (0,0,-3) through a sqrt(n) x sqrt(n) grid over [-1,1]^2 at z = -1; incoherent: uniform
+    origins in [-1,1]^3, uniform directions (normalised like rt_vector::normalize: multiply by the reciprocal length)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if kind == "incoherent":
+        o = rng.uniform(-1, 1, size=(n, 3)).astype(np.float32)
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+    else:
+        side = int(round(n ** 0.5))
+        u = ((np.arange(side, dtype=np.float32) + np.float32(0.5)) / np.float32(side) * 2 - 1).astype(np.float32)
+        tx, ty = np.meshgrid(u, u, indexing="xy")
+        target = np.stack([tx.ravel(), ty.ravel(), np.full(side * side, -1.0, np.float32)], axis=1)
+        o = np.broadcast_to(np.float32([0.0, 0.0, -3.0]), target.shape).copy()
+        d = (target - o).astype(np.float32)
+    l2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    d = d * (np.float32(1.0) / np.sqrt(l2))[:, None]
+    return np.ascontiguousarray(np.concatenate([o, d.astype(np.float32)], axis=1))
+
+
+def soup_shadow_rays(rays, t, eps=1e-3):
+    """worker.cpp:80-86 from every primary hit towards a point light at (0, 0.99, 0): origin pos + dir * eps, limit |to_light| - eps."""
+    hit = t >= 0
+    pos = rays[hit, :3] + rays[hit, 3:] * t[hit, None]
+    to_light = np.float32([0.0, 0.99, 0.0]) - pos
+    dist = np.sqrt((to_light * to_light).sum(axis=1)).astype(np.float32)
+    ldir = (to_light * (np.float32(1.0) / dist)[:, None]).astype(np.float32)
+    return np.ascontiguousarray(np.concatenate([pos + ldir * np.float32(eps), ldir, (dist - np.float32(eps))[:, None]], axis=1).astype(np.float32))
+
+
+def soup_config(args, n_rays):
+    return {"workload": f"BASELINE configs[2]: random-triangle soup, {args.tris} Mi triangles, {n_rays} {args.rays} rays "
+                        + ("(any-hit, towards a point light from the primary hits)" if args.rays == "shadow" else "(closest hit)"),
+            "tris": args.tris << 20, "rays": args.rays, "n_rays": int(n_rays),
+            "l2": f"scene arrays ({(args.tris << 20) * 128 / 2**20:.0f} MiB of nodes + triangles for the query tree) exceed the 126 MB L2 from 1 Mi triangles up; "
+                  "a 512 MB buffer is written between steps"}
+
+
+def soup_reference(args, prims, rays, shadow, seconds):
+    """The reference's own Scene::getIntersection on this host's cores: a bounded sample of the ray set on the same soup
+    (for the shadow set: the closest-hit query + distance compare of worker.cpp:84-86, which is what the reference runs)."""
+    import concurrent.futures
+
+    from cpupathtrace_b200 import pth
+
+    ref = pth.load_reference(fast=True)
+    cores = os.cpu_count() or 1
+    builder = ref.builder()
+    t0 = time.perf_counter()
+    builder.triangles(prims["p"][:, :9], prims["p"][:, 9:18], cull=False)
+    scene = builder.scene()
+    build_s = time.perf_counter() - t0
+    query = rays if shadow is None else np.ascontiguousarray(shadow[:, :6])
+    chunk = 4096
+
+    def trace(lo):
+        scene.intersect(query[lo:lo + chunk])
+        return min(chunk, len(query) - lo)
+
+    done, t0 = 0, time.perf_counter()
+    with concurrent.futures.ThreadPoolExecutor(cores) as pool:
+        starts = list(range(0, len(query), chunk))
+        pending = []
+        for lo in starts:
+            pending.append(pool.submit(trace, lo))
+            if len(pending) >= 4 * cores:
+                done += pending.pop(0).result()
+                if time.perf_counter() - t0 > seconds:
+                    break
+        for f in pending:
+            done += f.result()
+    elapsed = time.perf_counter() - t0
+    return {"value": done / elapsed / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+            "sample": f"{done} of the {len(query)} {args.rays} rays on the same {args.tris} Mi-triangle soup, Scene::getIntersection per ray from {cores} threads "
+                      f"({elapsed:.1f} s; reference -O3 -march=x86-64-v3; its BVH build took {build_s:.1f} s and is not counted)",
+            "seconds_per_step": elapsed}
+
+
+def run_soup_arm(args, reference_only=False):
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if reference_only and rank != 0:
+        return
+    prims, mats = soup_scene_arrays(args)
+    primary = soup_rays_host("incoherent" if args.rays == "incoherent" else "coherent", args.n_rays)
+
+    if reference_only:
+        # the shadow set needs the primary hits: taken from the reference itself on a subset
+        shadow = None
+        if args.rays == "shadow":
+            from cpupathtrace_b200 import pth
+
+            ref = pth.load_reference(fast=True)
+            b = ref.builder()
+            b.triangles(prims["p"][:, :9], prims["p"][:, 9:18], cull=False)
+            sub = primary[:: max(1, len(primary) // 200000)]
+            t_sub, _ = b.scene().intersect(sub)
+            shadow = soup_shadow_rays(sub, t_sub)
+        base = soup_reference(args, prims, primary, shadow, args.cpu_seconds)
+        line = {"metric": "Mrays/s", "value": base["value"], "unit": "Mrays/s", "impl": "reference", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+                "ms_per_step": base["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": soup_config(args, len(primary)), "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": base["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+
+    from cpupathtrace_b200 import capi
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    os.environ["PTB_DEVICE"] = str(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = capi.Context(-1)
+    t0 = time.perf_counter()
+    scene = capi.Scene(ctx, prims, mats)
+    t_scene = time.perf_counter() - t0
+    info = scene.info()
+    lib = capi.load()
+    dev = torch.device("cuda", local_rank)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    # every rank traces its own contiguous share of the ray set (independent rays: no data-path collective)
+    closest_flags = 0 if args.reference_closest else (capi.PTB_FLAG_CERTIFIED_CLOSEST | (0 if args.guarded else capi.PTB_FLAG_CERTIFIED_RELAXED))
+    if args.rays == "shadow":
+        t_primary, _, _ = scene.intersect(primary, closest_flags)
+        rays_host = soup_shadow_rays(primary, t_primary)
+    else:
+        rays_host = primary
+    share = (len(rays_host) + world - 1) // world
+    rays_host = np.ascontiguousarray(rays_host[rank * share:(rank + 1) * share])
+    n = len(rays_host)
+    any_hit = args.rays == "shadow"
+    width = rays_host.shape[1]
+    pinned_in = torch.from_numpy(rays_host).pin_memory()
+    d_rays = pinned_in.to(dev)
+    d_t = torch.empty(n, dtype=torch.float32, device=dev)
+    d_prim = torch.empty(n, dtype=torch.int32, device=dev)
+    d_occ = torch.empty(n, dtype=torch.uint8, device=dev)
+    h_t = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_prim = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_occ = torch.empty(n, dtype=torch.uint8).pin_memory()
+
+    def device_step(extra=0):
+        if any_hit:
+            return scene.occluded_device(d_rays.data_ptr(), n, d_occ.data_ptr(), extra)
+        return scene.intersect_device(d_rays.data_ptr(), n, d_t.data_ptr(), d_prim.data_ptr(), closest_flags | extra)
+
+    def host_step():
+        stats = capi.RenderStats()
+        if any_hit:
+            capi.check(lib.ptb_occluded(scene._h, C.c_void_p(pinned_in.data_ptr()), n, C.c_void_p(h_occ.data_ptr()), 0, C.byref(stats)))
+        else:
+            capi.check(lib.ptb_intersect(scene._h, C.c_void_p(pinned_in.data_ptr()), n, C.c_void_p(h_t.data_ptr()), C.c_void_p(h_prim.data_ptr()), closest_flags, C.byref(stats)))
+        return stats
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def over_ranks(value, op):
+        if dist is None:
+            return value
+        t = torch.tensor([value], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        barrier()
+        device_step()
+    step_ms, trace_ms = [], 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier()
+        stats = device_step()
+        step_ms.append(over_ranks(stats.device_ms_total, torch.distributed.ReduceOp.MAX if dist is not None else None))
+        trace_ms += stats.device_ms_trace
+    clocks = sampler.stop()
+    counted = device_step(capi.PTB_FLAG_COUNT_VISITS)
+    inner, leaf = counted.inner_visits / n, counted.leaf_visits / n
+    ray_bytes = (28 + 1) if any_hit else (24 + 8)
+    bytes_per_ray = INNER_BYTES * inner + LEAF_BYTES * leaf + ray_bytes
+
+    # size-independent parity: the walk the bench times returns what the reference-order walk returns, ray for ray
+    identical = None
+    if not any_hit and not args.reference_closest:
+        t_fast, prim_fast = d_t.clone(), d_prim.clone()
+        scene.intersect_device(d_rays.data_ptr(), n, d_t.data_ptr(), d_prim.data_ptr(), 0)
+        hit = d_t >= 0
+        identical = bool(torch.equal(d_prim, prim_fast) and torch.equal(d_t[hit], t_fast[hit]) and bool((t_fast[~hit] < 0).all()))
+
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        host_step()
+        e2e_ms.append(over_ranks((time.perf_counter() - t0) * 1e3, torch.distributed.ReduceOp.MAX if dist is not None else None))
+    total_rays = over_ranks(float(n), torch.distributed.ReduceOp.SUM if dist is not None else None)
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+
+    value = total_rays / (np.mean(step_ms) / 1e3) / 1e6
+    peak, peak_source = 6650.0, "fallback"
+    peaks_path = os.path.join(REPO_ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        try:
+            peak, peak_source = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+        except (KeyError, ValueError):
+            pass
+    achieved = bytes_per_ray * n * args.steps / max(trace_ms / 1e3, 1e-12) / 1e9
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from cpupathtrace_b200 import pth
+
+        if os.path.exists(pth.REF_FAST):
+            base = soup_reference(args, prims, primary, rays_host if any_hit else None, args.cpu_seconds)
+            cpu_baseline = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    out_bytes = n * (1 if any_hit else 8)
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(np.mean(step_ms)),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": soup_config(args, total_rays),
+        "clocks": clocks,
+        "e2e": {"value": total_rays / (np.mean(e2e_ms) / 1e3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(n * width * 4), "d2h_bytes_per_step": int(out_bytes),
+                "ms_per_step": float(np.mean(e2e_ms)), "api": "ptb_occluded" if any_hit else "ptb_intersect", "note": "pinned host ray buffer in, pinned host results out, per rank"},
+        "gpu_launches": int(args.steps * (3 + (0 if any_hit or args.reference_closest else 1))),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": f"{peak_source} HBM copy bandwidth",
+                     "kernel": "occludedKernel" if any_hit else ("intersectKernel<reference tree>" if args.reference_closest else "intersectKernel<certified SAH walk> + re-trace launch"),
+                     "bytes_per_ray": bytes_per_ray, "inner_fetches_per_ray": inner, "leaf_fetches_per_ray": leaf, "rays_per_launch": n,
+                     "algorithmic_bytes_per_launch": bytes_per_ray * n, "ms_per_launch": trace_ms / args.steps, "sort_ms_per_launch": float(np.mean(step_ms)) - trace_ms / args.steps,
+                     "note": "rays are traced in Morton order of (direction octant, origin); ms_per_launch is the traversal kernel(s), ms_per_step adds the key + radix-sort pass"},
+        "cpu_baseline": cpu_baseline,
+        "scene": {"prims": int(info.n_prims), "bvh_depth": int(info.bvh_depth), "device_mb": info.device_bytes / 2**20, "build_s": info.build_seconds, "scene_ctor_s": t_scene,
+                  "certifiable": int(info.certifiable)},
+        "identical_to_reference_walk": identical, "retraced": int(counted.closest_rays_retraced),
     }
     print(json.dumps(line))
     if dist is not None:
@@ -515,7 +848,9 @@ def main():
         builtin_print(*a, **k)
         real_stdout.flush()
 
-    if args.impl == "reference":
+    if args.workload == "soup":
+        run_soup_arm(args, reference_only=args.impl == "reference")
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_b200_arm(args)

@@ -29,6 +29,7 @@ PTB_FLAG_SKIP_NULL_SHADOWS = 0x4
 PTB_FLAG_COUNT_VISITS = 0x8
 PTB_FLAG_CERTIFIED_CLOSEST = 0x10
 PTB_FLAG_CERTIFIED_RELAXED = 0x20
+PTB_FLAG_PROFILE_ALL = 0x40
 
 # numpy dtypes of the POD records (layout-identical to the C structs)
 PRIM_DTYPE = np.dtype([("kind", "<u4"), ("material", "<u4"), ("cull_backface", "<u4"), ("reserved", "<u4"), ("p", "<f4", (18,))])

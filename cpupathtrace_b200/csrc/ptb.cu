@@ -123,6 +123,10 @@ struct ptb_context {
     Buffer io_b;
     Buffer io_c;
     Buffer io_d;
+    Buffer sort_keys;   // batch queries: ray sort keys (in | out), ray numbers (in | out), cub workspace
+    Buffer sort_ids;
+    Buffer sort_temp;
+    bool sort_rays = true; // PTB_SORT_RAYS=0: trace batches in the caller's order
     Buffer multi_image;   // ptb_render_multi: this replica's share of the frame (its tiles, zeros elsewhere)
     Buffer multi_staging; // ptb_render_multi on the first replica: copies of the other replicas' images when peers cannot map each other
     uint32_t *host_counters = nullptr; // pinned
@@ -133,6 +137,7 @@ struct ptb_context {
     int event_class[kEventPairs];
     int events_used = 0;
     bool events_ready = false;
+    bool profile_all = false; // this call times every launch (PTB_FLAG_PROFILE_ALL), not only the closest-hit trace
     cudaEvent_t call_start = nullptr;
     cudaEvent_t call_stop = nullptr;
 };
@@ -173,7 +178,7 @@ namespace {
         ptb_context *ctx;
         int pair;
         LaunchTimer(ptb_context *c, int klass) : ctx(c), pair(-1) {
-            if(ctx->events_ready && ctx->events_used < kEventPairs) {
+            if(ctx->events_ready && (klass == 0 || ctx->profile_all) && ctx->events_used < kEventPairs) {
                 pair = ctx->events_used++;
                 ctx->event_class[pair] = klass;
                 cudaEventRecord(ctx->events[pair][0], ctx->stream);
@@ -520,7 +525,8 @@ namespace {
         return PTB_OK;
     }
 
-    int beginCall(ptb_context *ctx, ptb_render_stats *stats) {
+    int beginCall(ptb_context *ctx, ptb_render_stats *stats, uint32_t flags = 0U) {
+        ctx->profile_all = (flags & PTB_FLAG_PROFILE_ALL) != 0U;
         int status = useDevice(ctx);
         if(status != PTB_OK) {
             return status;
@@ -652,6 +658,32 @@ namespace {
         return finish(PTB_OK);
     }
 
+    constexpr uint32_t kSortThreshold = 1U << 16; // smaller batches are traced in the caller's order
+
+    // Fills ctx->sort_ids (second half) with the numbers of the chunk's n rays in sort-key order; returns the device pointer
+    // through `order`.  stride_floats: 6 (closest-hit rays) or 7 (rays with a limit).
+    int sortRays(ptb_scene *scene, const float *d_rays, uint32_t stride_floats, uint32_t n, const uint32_t **order) {
+        ptb_context *ctx = scene->ctx;
+        *order = nullptr;
+        size_t temp_bytes = 0;
+        if(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, static_cast<const uint32_t *>(nullptr), static_cast<uint32_t *>(nullptr), static_cast<const uint32_t *>(nullptr),
+                                           static_cast<uint32_t *>(nullptr), static_cast<int>(n), 0, 30, ctx->stream) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(PTB_ERR_CUDA, "sortRays: radix sort sizing failed");
+        }
+        int status;
+        if((status = ctx->sort_keys.reserve(2 * static_cast<size_t>(n) * sizeof(uint32_t))) != PTB_OK || (status = ctx->sort_ids.reserve(2 * static_cast<size_t>(n) * sizeof(uint32_t))) != PTB_OK ||
+           (status = ctx->sort_temp.reserve(std::max<size_t>(temp_bytes, 16))) != PTB_OK) {
+            return status;
+        }
+        uint32_t *keys = ctx->sort_keys.as<uint32_t>();
+        uint32_t *ids = ctx->sort_ids.as<uint32_t>();
+        rayKeyKernel<<<(n + 255U) / 256U, 256, 0, ctx->stream>>>(scene->dev, d_rays, stride_floats, n, keys, ids);
+        PTB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->sort_temp.ptr, temp_bytes, keys, keys + n, ids, ids + n, static_cast<int>(n), 0, 30, ctx->stream));
+        *order = ids + n;
+        return PTB_OK;
+    }
+
     int finishStats(ptb_context *ctx, bool count_visits, ptb_render_stats *stats) {
         if(stats == nullptr) {
             return PTB_OK;
@@ -757,6 +789,7 @@ int ptb_context_create(int device, ptb_context **out) {
     ctx->trace_blocks_per_sm = static_cast<int>(std::max(1L, envLong("PTB_TRACE_BLOCKS_PER_SM", 16)));
     ctx->log_iterations = envLong("PTB_LOG_ITERATIONS", 0) != 0;
     ctx->production_math = envLong("PTB_PRODUCTION_MATH", 1) != 0;
+    ctx->sort_rays = envLong("PTB_SORT_RAYS", 1) != 0;
     ctx->iterations_per_sync = static_cast<int>(std::min<long>(kMaxIterationsPerSync, std::max(1L, envLong("PTB_ITERATIONS_PER_SYNC", 4))));
     *out = ctx;
     return PTB_OK;
@@ -771,7 +804,7 @@ int ptb_context_destroy(ptb_context *ctx) {
         cudaStreamSynchronize(ctx->stream);
     }
     for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->redo_queue, &ctx->counters, &ctx->visits, &ctx->work_cursor, &ctx->samples, &ctx->pixel_list,
-                     &ctx->io_a, &ctx->io_b, &ctx->io_c, &ctx->io_d, &ctx->multi_image, &ctx->multi_staging}) {
+                     &ctx->io_a, &ctx->io_b, &ctx->io_c, &ctx->io_d, &ctx->multi_image, &ctx->multi_staging, &ctx->sort_keys, &ctx->sort_ids, &ctx->sort_temp}) {
         b->release();
     }
     if(ctx->host_counters != nullptr) {
@@ -1093,7 +1126,7 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
     }
     ptb_context *ctx = scene->ctx;
     std::lock_guard<std::mutex> lock(ctx->mutex);
-    int status = beginCall(ctx, stats);
+    int status = beginCall(ctx, stats, flags);
     if(status != PTB_OK) {
         return status;
     }
@@ -1124,7 +1157,7 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
 
     const ClosestMode closest = closestMode(scene, flags);
     const bool certified = closest.certified;
-    constexpr uint64_t kChunk = 1ULL << 28;
+    constexpr uint64_t kChunk = 1ULL << 26;
     if(certified && (status = ctx->redo_queue.reserve(std::min<uint64_t>(kChunk, n_rays) * sizeof(uint32_t))) != PTB_OK) {
         return status;
     }
@@ -1137,16 +1170,20 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
         const int grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 16))));
         PTB_CUDA(cudaMemsetAsync(counters, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
         const float *chunk_rays = d_rays + 6 * first;
+        const uint32_t *order = nullptr; // large batches are traced in sort-key order (rayKeyKernel); results go by ray number
+        if(ctx->sort_rays && n >= kSortThreshold && (status = sortRays(scene, chunk_rays, 6, n, &order)) != PTB_OK) {
+            return status;
+        }
         LaunchTimer timer(ctx, 0);
         if(certified) {
             if(count_visits) {
-                intersectKernel<kTraceCertified, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, nullptr, nullptr, n, d_t + first, d_prim + first,
+                intersectKernel<kTraceCertified, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, order, nullptr, n, d_t + first, d_prim + first,
                                                                                         counters + kCountFetchClosest, redo, counters + kCountRedo, visits, scene->guard, closest.guarded);
                 intersectKernel<kTraceClosest, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, redo, counters + kCountRedo, n, d_t + first, d_prim + first,
                                                                                       counters + kCountFetchRedo, nullptr, nullptr, visits, scene->guard, closest.guarded);
             }
             else {
-                intersectKernel<kTraceCertified, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, nullptr, nullptr, n, d_t + first, d_prim + first,
+                intersectKernel<kTraceCertified, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, order, nullptr, n, d_t + first, d_prim + first,
                                                                                          counters + kCountFetchClosest, redo, counters + kCountRedo, visits, scene->guard, closest.guarded);
                 intersectKernel<kTraceClosest, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, redo, counters + kCountRedo, n, d_t + first, d_prim + first,
                                                                                        counters + kCountFetchRedo, nullptr, nullptr, visits, scene->guard, closest.guarded);
@@ -1158,11 +1195,11 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
             }
         }
         else if(count_visits) {
-            intersectKernel<kTraceClosest, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, nullptr, nullptr, n, d_t + first, d_prim + first,
+            intersectKernel<kTraceClosest, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, order, nullptr, n, d_t + first, d_prim + first,
                                                                                   counters + kCountFetchClosest, nullptr, nullptr, visits, scene->guard, closest.guarded);
         }
         else {
-            intersectKernel<kTraceClosest, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, nullptr, nullptr, n, d_t + first, d_prim + first,
+            intersectKernel<kTraceClosest, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, order, nullptr, n, d_t + first, d_prim + first,
                                                                                    counters + kCountFetchClosest, nullptr, nullptr, visits, scene->guard, closest.guarded);
         }
     }
@@ -1189,7 +1226,7 @@ int ptb_occluded(ptb_scene *scene, const float *rays, uint64_t n_rays, uint8_t *
     }
     ptb_context *ctx = scene->ctx;
     std::lock_guard<std::mutex> lock(ctx->mutex);
-    int status = beginCall(ctx, stats);
+    int status = beginCall(ctx, stats, flags);
     if(status != PTB_OK) {
         return status;
     }
@@ -1215,18 +1252,22 @@ int ptb_occluded(ptb_scene *scene, const float *rays, uint64_t n_rays, uint8_t *
     PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, kCounterSlots * sizeof(uint32_t), ctx->stream));
     PTB_CUDA(cudaMemsetAsync(ctx->visits.ptr, 0, 2 * sizeof(VisitCounters), ctx->stream));
 
-    constexpr uint64_t kChunk = 1ULL << 30;
+    constexpr uint64_t kChunk = 1ULL << 26;
     for(uint64_t first = 0; first < n_rays; first += kChunk) {
         const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(kChunk, n_rays - first));
         const int grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kBlock - 1) / kBlock, static_cast<uint64_t>(gridFor(ctx, 16))));
         PTB_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(uint32_t), ctx->stream));
-        LaunchTimer timer(ctx, 2);
+        const uint32_t *order = nullptr;
+        if(ctx->sort_rays && n >= kSortThreshold && (status = sortRays(scene, d_rays + 7 * first, 7, n, &order)) != PTB_OK) {
+            return status;
+        }
+        LaunchTimer timer(ctx, 0); // the only kernel of this entry: always timed
         if(count_visits) {
-            occludedKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
+            occludedKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, d_rays + 7 * first, order, n, d_out + first, ctx->counters.as<uint32_t>(),
                                                                     ctx->visits.as<VisitCounters>() + 1);
         }
         else {
-            occludedKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, d_rays + 7 * first, n, d_out + first, ctx->counters.as<uint32_t>(),
+            occludedKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, d_rays + 7 * first, order, n, d_out + first, ctx->counters.as<uint32_t>(),
                                                                      ctx->visits.as<VisitCounters>() + 1);
         }
     }
@@ -1257,7 +1298,7 @@ int ptb_render_samples(ptb_scene *scene, const ptb_camera *camera, const ptb_ren
     }
     ptb_context *ctx = scene->ctx;
     std::lock_guard<std::mutex> lock(ctx->mutex);
-    int status = beginCall(ctx, stats);
+    int status = beginCall(ctx, stats, opts->flags);
     if(status != PTB_OK) {
         return status;
     }
@@ -1329,7 +1370,7 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
     }
     ptb_context *ctx = scene->ctx;
     std::lock_guard<std::mutex> lock(ctx->mutex);
-    int status = beginCall(ctx, stats);
+    int status = beginCall(ctx, stats, opts->flags);
     if(status != PTB_OK) {
         return status;
     }

@@ -187,6 +187,10 @@ typedef enum ptb_rng_mode {
                                      /* Guarded by default: rays for which fp32 rounding in a LARGE triangle's or a nearby  */
                                      /* sphere's own intersection routine could matter are sent to the reference walk up    */
                                      /* front (csrc/cert_guard.h); scenes the guard table cannot cover are not certified.   */
+#define PTB_FLAG_PROFILE_ALL 0x40u   /* CUDA events around EVERY launch (device_ms_shade / device_ms_trace_shadow are filled);  */
+                                     /* without it only the dominant kernel, the closest-hit trace, is timed per launch     */
+                                     /* (device_ms_trace = closest-hit trace only): the extra ~300 event pairs per frame    */
+                                     /* cost 4-5 % of a frame                                                                */
 #define PTB_FLAG_CERTIFIED_RELAXED 0x20u /* with PTB_FLAG_CERTIFIED_CLOSEST: no guard.  Identical results except where the  */
                                      /* reference's own answer is rounding noise of a grazing hit on a large triangle       */
                                      /* (tests/stress_cases.py); meant for production renders (PTB_RNG_COUNTER)             */
@@ -222,9 +226,9 @@ typedef struct ptb_render_stats {
     uint64_t bounce_iterations;
     uint64_t kernel_launches;
     double device_ms_total;  /* CUDA-event time of the whole call on the context's stream */
-    double device_ms_trace;  /* closest + shadow traversal kernels                         */
-    double device_ms_shade;  /* generate + shade + accumulate + resolve                    */
-    double device_ms_trace_shadow;  /* the shadow-ray share of device_ms_trace            */
+    double device_ms_trace;  /* closest-hit traversal kernels (+ shadow traversal with PTB_FLAG_PROFILE_ALL) */
+    double device_ms_shade;  /* generate + shade + accumulate + resolve (PTB_FLAG_PROFILE_ALL only)           */
+    double device_ms_trace_shadow;  /* the shadow-ray share of device_ms_trace (PTB_FLAG_PROFILE_ALL only)    */
     uint64_t shadow_inner_visits;   /* the shadow-ray share of inner_visits               */
     uint64_t shadow_leaf_visits;    /* the shadow-ray share of leaf_visits                */
     uint64_t closest_rays_retraced; /* PTB_FLAG_CERTIFIED_CLOSEST: queries without a certificate, re-traced on the reference tree */

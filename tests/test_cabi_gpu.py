@@ -449,3 +449,50 @@ def test_certified_walk_on_adversarial_geometry(ctx):
     print(f"fine scene: guarded re-traces {stats_g.closest_rays_retraced / len(rays):.1%}, relaxed {stats_r.closest_rays_retraced / len(rays):.1%}; "
           f"relaxed differs from the reference walk on {int((prim_r != prim).sum())} rays")
     scene.close()
+
+
+def test_soup_hits_match_the_oracle(ctx):
+    """BASELINE configs[2] at its smallest size: a 1 Mi-triangle random soup (SURVEY 8d recipe).  Coherent (pinhole grid)
+    and incoherent rays against the plain-C oracle on a subset, bit for bit; on the full 2^20-ray sets the certified walk
+    (guarded and relaxed), with and without the Morton ray sort, must equal the reference-order walk; the shadow set's
+    any-hit answers must equal what the closest hits imply (worker.cpp:84-86)."""
+    import argparse
+    import os
+
+    import bench
+
+    args = argparse.Namespace(tris=1)
+    prims, mats = bench.soup_scene_arrays(args)
+    scene = capi.Scene(ctx, prims, mats)
+    oracle = pto.OracleScene(prims, mats, np.zeros(0, capi.LIGHT_DTYPE))
+    n = 1 << 20
+    for kind in ("coherent", "incoherent"):
+        rays = bench.soup_rays_host(kind, n)
+        t, prim, stats = scene.intersect(rays, flags=capi.PTB_FLAG_COUNT_VISITS)
+        hit = t >= 0
+        assert 0.2 < hit.mean() < 1.0 and stats.inner_visits > stats.leaf_visits > 0
+        sub = np.random.Generator(np.random.PCG64(3)).permutation(n)[:30_000]
+        t_o, prim_o = oracle.intersect(rays[sub])
+        assert np.array_equal(prim[sub], prim_o) and np.array_equal(t[sub][t_o >= 0], t_o[t_o >= 0])
+        for flags in (capi.PTB_FLAG_CERTIFIED_CLOSEST, capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_CERTIFIED_RELAXED):
+            t_c, prim_c, stats_c = scene.intersect(rays, flags=flags | capi.PTB_FLAG_COUNT_VISITS)
+            assert np.array_equal(prim_c, prim) and np.array_equal(t_c[hit], t[hit]) and (t_c[~hit] < 0).all()
+            assert stats_c.inner_visits < stats.inner_visits
+        if kind == "coherent":
+            shadow = bench.soup_shadow_rays(rays, t)
+            occluded, _ = scene.occluded(shadow)
+            t_s, _, _ = scene.intersect(shadow[:, :6])
+            assert np.array_equal(occluded.astype(bool), (t_s >= 0) & (t_s < shadow[:, 6]))
+    # the ray sort is a pure reordering
+    os.environ["PTB_SORT_RAYS"] = "0"
+    try:
+        unsorted_ctx = capi.Context(-1)
+        plain = capi.Scene(unsorted_ctx, prims, mats)
+        t_u, prim_u, _ = plain.intersect(rays)
+        assert np.array_equal(prim_u, prim) and np.array_equal(t_u[hit], t[hit])
+        plain.close()
+        unsorted_ctx.close()
+    finally:
+        os.environ.pop("PTB_SORT_RAYS", None)
+    assert scene.info().certifiable == 1
+    scene.close()
