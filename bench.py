@@ -67,6 +67,7 @@ def parse_args():
     p.add_argument("--guarded", action="store_true",
                    help="certified closest hits with the guard table (the exact mode validation uses); default: relaxed, as production renders")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-adaptive-line", action="store_true", help="skip the untimed adaptive-sampling frame (min = spp / 8)")
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of one reference-arm sample")
     args = p.parse_args()
     world = int(os.environ.get("WORLD_SIZE", str(max(args.gpus, 1))))
@@ -419,6 +420,17 @@ def run_b200_arm(args):
     }
     certificate_audit = {"primitive_tests": int(cstats.leaf_visits - cstats.shadow_leaf_visits), "suspect_hits": int(cstats.certified_suspect_hits),
                          "closest_rays": int(cstats.closest_rays), "retraced": int(cstats.closest_rays_retraced)}
+    # ---- adaptive sampling (untimed, reported next to the headline): the same frame with min = spp / 8 < max = spp.  The
+    # per-pixel loops of processItem end early where the acceptance test fires (worker.cpp:236-260); the device traces
+    # rounds of samples for the pixels still sampling, so a frame whose loops end early costs less.
+    adaptive = None
+    if args.spp >= 16 and not args.no_adaptive_line:
+        astats = capi.RenderStats()
+        ao = capi.render_opts(args.width, args.height, max(args.spp // 8, 1), args.spp, 1e-3, args.max_depth, capi.PTB_RNG_COUNTER, flags | capi.PTB_FLAG_DEVICE_IO, 97, 0, rank, world)
+        capi.check(lib.ptb_render(handle, C.byref(camera), C.byref(ao), 0, 0, args.width, args.height, C.c_void_p(image.data_ptr()), C.byref(astats)))
+        adaptive = {"min_spp": max(args.spp // 8, 1), "max_spp": args.spp, "samples_max": int(sharding.owned_pixels(args.width, args.height, rank, world).sum()) * args.spp, "samples_traced": int(astats.samples),
+                    "samples_the_reference_loops_consume": int(astats.samples_used), "rounds": int(astats.adaptive_rounds), "frame_ms": astats.device_ms_total,
+                    "note": "this rank's tiles; one untimed frame"}
     count_rays = sum_over_ranks(float(cstats.closest_rays + cstats.shadow_rays))
     inner_per_ray = sum_over_ranks(float(cstats.inner_visits)) / max(count_rays, 1.0)
     leaf_per_ray = sum_over_ranks(float(cstats.leaf_visits)) / max(count_rays, 1.0)
@@ -544,6 +556,7 @@ def run_b200_arm(args):
                   "query_tree": "device LBVH" if info.query_tree_on_device else "host binned SAH", "query_tree_device_ms": info.query_tree_device_ms},
         "bounce_iterations_per_step": totals["iterations"] / args.steps,
         "per_rank": per_rank,
+        "adaptive": adaptive,
         "certificate_audit": None if args.reference_closest else certificate_audit,
         "closest_hit": ("reference-topology tree" if args.reference_closest else
                         f"certified SAH walk; {totals['retraced']} of {totals['closest']} closest-hit rays had no certificate and were re-traced on the reference tree"),

@@ -122,6 +122,8 @@ class RenderStats(C.Structure):
         ("shadow_leaf_visits", C.c_uint64),
         ("closest_rays_retraced", C.c_uint64),
         ("certified_suspect_hits", C.c_uint64),
+        ("samples_used", C.c_uint64),
+        ("adaptive_rounds", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -167,10 +167,12 @@ namespace ptb {
     // and its result goes to samples[g].
     struct PathSource {
         const uint32_t *pixel_list;
+        const uint32_t *active; // adaptive rounds: work item g renders pixel pixel_list[active[g % n_pixels]] (n_pixels = active pixels); else null
         const int32_t *pixels;
         const uint64_t *seeds;
         uint32_t n_pixels;
         uint32_t explicit_samples;
+        uint32_t sample_base; // index of the first sample of this round
         unsigned long long total;
     };
 
@@ -186,8 +188,9 @@ namespace ptb {
             key = src.seeds[g];
         }
         else {
-            const uint32_t sample = static_cast<uint32_t>(g / src.n_pixels);
-            const uint32_t packed = src.pixel_list[static_cast<uint32_t>(g % src.n_pixels)];
+            const uint32_t sample = src.sample_base + static_cast<uint32_t>(g / src.n_pixels);
+            const uint32_t slot = static_cast<uint32_t>(g % src.n_pixels);
+            const uint32_t packed = src.pixel_list[src.active != nullptr ? src.active[slot] : slot];
             px = static_cast<int>(packed & 0xFFFFU);
             py = static_cast<int>(packed >> 16);
             key = counterKey(params.seed, static_cast<uint32_t>(px), static_cast<uint32_t>(py), sample);
@@ -551,135 +554,176 @@ namespace ptb {
         int32_t rect_w;
     };
 
-    constexpr int kMaxCandidates = 8;
+    constexpr int kMaxCandidates = 8; // processItem opens a candidate every candidate_batch_count batches: at most 6 for any legal option set
+                                      // (candidate_batch_count >= max(min, max / 4) / stats, i.e. at most ~4 candidates + remainder); the host asserts it
 
     PTB_DEV V4 sub4(V4 a, V4 b) {
         return V4{a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w};
     }
 
-    // processItem's per-pixel loop (worker.cpp:172-319) over the already-computed samples of one pixel.
-    __global__ void __launch_bounds__(kBlock) resolveKernel(ResolveParams rp, const float4 *__restrict__ samples, const uint32_t *__restrict__ pixel_list,
-                                                            float4 *__restrict__ out) {
-        const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-        if(q >= rp.n_pixels) {
-            return;
-        }
+    // The constants processItem derives from RenderOptions (worker.cpp:158-164)
+    struct ResolveConsts {
+        int min_samples;
+        int max_samples;
+        int stats_sample_count;
+        int candidate_batch_count;
+        int check_sample_count;
+    };
 
-        const int min_samples = rp.min_sample_count;
-        const int max_samples = rp.max_sample_count;
-        const int stats_sample_count = min(max(min_samples / 4, 1), 64);
-        const int candidate_batch_count = max(max(min_samples, max_samples / 4) / stats_sample_count, 2);
-        const int check_sample_count = min(max(max(min_samples / 2, (max_samples - min_samples) / 8), max(8, stats_sample_count)), 1024) / stats_sample_count;
+    __host__ __device__ inline ResolveConsts resolveConsts(int min_samples, int max_samples) {
+        ResolveConsts c;
+        c.min_samples = min_samples;
+        c.max_samples = max_samples;
+        const int quarter = min_samples / 4;
+        c.stats_sample_count = quarter < 1 ? 1 : (quarter > 64 ? 64 : quarter);
+        const int a = max_samples / 4;
+        const int b = (min_samples > a ? min_samples : a) / c.stats_sample_count;
+        c.candidate_batch_count = b > 2 ? b : 2;
+        const int half = min_samples / 2;
+        const int eighth = (max_samples - min_samples) / 8;
+        const int lo = half > eighth ? half : eighth;
+        const int floor8 = c.stats_sample_count > 8 ? c.stats_sample_count : 8;
+        int checks = lo > floor8 ? lo : floor8;
+        checks = checks < 1024 ? checks : 1024;
+        c.check_sample_count = checks / c.stats_sample_count;
+        return c;
+    }
 
-        const V4 zero = V4{0.0F, 0.0F, 0.0F, 0.0F};
-        V4 pixel_value = zero;
-        int collected_sample_count = 0;
-        V4 contribution_mean = zero;
-        V4 contribution_m2 = zero;
-        int contribution_count = 0;
-        int stats_sample_index = 0;
-        V4 sample_aggregate = zero;
-
+    // The per-pixel state of processItem's sampling loop (worker.cpp:172-260), resumable: the one-shot resolve keeps it
+    // in registers / local memory, the adaptive path parks it in HBM between rounds of samples.
+    struct PixelStats {
+        V4 pixel_value;
+        V4 contribution_mean;
+        V4 contribution_m2;
+        V4 sample_aggregate;
+        V4 candidate_mean;
+        V4 candidate_m2;
         V4 candidate_means[kMaxCandidates];
         V4 candidate_m2s[kMaxCandidates];
         int candidate_counts[kMaxCandidates];
-        int n_candidates = 0;
+        int collected_sample_count;
+        int contribution_count;
+        int stats_sample_index;
+        int candidate_count;
+        int n_candidates;
+        int remaining_checks;
+        int accepted_candidate;
+        int next_sample; // pixel_sample of the reference's loop: samples consumed so far
+    };
 
-        V4 candidate_mean = zero;
-        V4 candidate_m2 = zero;
-        int candidate_count = 0;
+    PTB_DEV void pixelBegin(PixelStats &st, const ResolveConsts &c) {
+        const V4 zero = V4{0.0F, 0.0F, 0.0F, 0.0F};
+        st.pixel_value = zero;
+        st.contribution_mean = zero;
+        st.contribution_m2 = zero;
+        st.sample_aggregate = zero;
+        st.candidate_mean = zero;
+        st.candidate_m2 = zero;
+        st.collected_sample_count = 0;
+        st.contribution_count = 0;
+        st.stats_sample_index = 0;
+        st.candidate_count = 0;
+        st.n_candidates = 0;
+        st.remaining_checks = c.check_sample_count;
+        st.accepted_candidate = 0;
+        st.next_sample = 0;
+    }
 
-        int remaining_checks = check_sample_count;
-        bool accepted_candidate = false;
+    // One iteration of the reference's per-pixel loop with the sample `raw` (rgb, collected flag).  Returns true when the
+    // loop ends with this sample (the adaptive acceptance test fired: `break` at worker.cpp:251).
+    PTB_DEV bool pixelAdd(PixelStats &st, const ResolveConsts &c, float4 raw) {
+        const V4 zero = V4{0.0F, 0.0F, 0.0F, 0.0F};
+        st.next_sample++;
+        if(raw.w == 0.0F) {
+            return false; // sample not collected: the primary ray missed everything
+        }
+        const V4 color = V4{raw.x, raw.y, raw.z, 1.0F};
 
-        for(int pixel_sample = 0; pixel_sample < max_samples; pixel_sample++) {
-            const float4 raw = samples[static_cast<size_t>(pixel_sample) * rp.n_pixels + q];
-            if(raw.w == 0.0F) {
-                continue; // sample not collected: the primary ray missed everything
+        st.contribution_count++;
+        st.stats_sample_index++;
+        st.sample_aggregate = st.sample_aggregate + color;
+
+        if(st.stats_sample_index == c.stats_sample_count) {
+            st.sample_aggregate = st.sample_aggregate / static_cast<float>(c.stats_sample_count);
+
+            const V4 delta = sub4(st.sample_aggregate, st.contribution_mean);
+            st.contribution_mean = st.contribution_mean + delta / static_cast<float>(st.contribution_count / c.stats_sample_count);
+            const V4 delta2 = sub4(st.sample_aggregate, st.contribution_mean);
+            st.contribution_m2 = st.contribution_m2 + delta * delta2;
+
+            if(st.candidate_count == c.candidate_batch_count) {
+                if(st.n_candidates < kMaxCandidates) {
+                    st.candidate_means[st.n_candidates] = st.candidate_mean;
+                    st.candidate_m2s[st.n_candidates] = st.candidate_m2;
+                    st.candidate_counts[st.n_candidates] = st.candidate_count;
+                    st.n_candidates++;
+                }
+                st.candidate_mean = zero;
+                st.candidate_m2 = zero;
+                st.candidate_count = 0;
             }
-            const V4 color = V4{raw.x, raw.y, raw.z, 1.0F};
 
-            contribution_count++;
-            stats_sample_index++;
-            sample_aggregate = sample_aggregate + color;
+            st.candidate_count++;
+            const V4 candidate_delta = sub4(st.sample_aggregate, st.candidate_mean);
+            st.candidate_mean = st.candidate_mean + candidate_delta / static_cast<float>(st.candidate_count);
+            const V4 candidate_delta2 = sub4(st.sample_aggregate, st.candidate_mean);
+            st.candidate_m2 = st.candidate_m2 + candidate_delta * candidate_delta2;
 
-            if(stats_sample_index == stats_sample_count) {
-                sample_aggregate = sample_aggregate / static_cast<float>(stats_sample_count);
+            st.stats_sample_index = 0;
+            st.sample_aggregate = zero;
+        }
 
-                const V4 delta = sub4(sample_aggregate, contribution_mean);
-                contribution_mean = contribution_mean + delta / static_cast<float>(contribution_count / stats_sample_count);
-                const V4 delta2 = sub4(sample_aggregate, contribution_mean);
-                contribution_m2 = contribution_m2 + delta * delta2;
+        st.pixel_value = st.pixel_value + color;
+        st.collected_sample_count++;
 
-                if(candidate_count == candidate_batch_count) {
-                    if(n_candidates < kMaxCandidates) {
-                        candidate_means[n_candidates] = candidate_mean;
-                        candidate_m2s[n_candidates] = candidate_m2;
-                        candidate_counts[n_candidates] = candidate_count;
-                        n_candidates++;
+        if(st.stats_sample_index == 0 && st.collected_sample_count >= max(c.min_samples, 2)) {
+            bool passed_check = false;
+            if(st.contribution_count / c.stats_sample_count >= 2) {
+                const V4 m2_weighted = st.contribution_m2 / static_cast<float>(st.contribution_count / c.stats_sample_count - 1);
+                const float stddev = sqrtf((m2_weighted.x + m2_weighted.y) + m2_weighted.z);
+                const float mean_contribution = ((st.contribution_mean.x + st.contribution_mean.y) + st.contribution_mean.z) / 3.0F;
+                // `stddev / (3 * 3 * getContribution(mean) + 1E-5) < 0.2F` is evaluated in double (worker.cpp:243)
+                const double relative = static_cast<double>(stddev) / (static_cast<double>(9.0F * mean_contribution) + 1E-5);
+                if(stddev < 1E-4F || relative < static_cast<double>(0.2F)) {
+                    passed_check = true;
+                    st.remaining_checks--;
+                    if(st.remaining_checks <= 0) {
+                        st.accepted_candidate = 1;
+                        return true;
                     }
-                    candidate_mean = zero;
-                    candidate_m2 = zero;
-                    candidate_count = 0;
-                }
-
-                candidate_count++;
-                const V4 candidate_delta = sub4(sample_aggregate, candidate_mean);
-                candidate_mean = candidate_mean + candidate_delta / static_cast<float>(candidate_count);
-                const V4 candidate_delta2 = sub4(sample_aggregate, candidate_mean);
-                candidate_m2 = candidate_m2 + candidate_delta * candidate_delta2;
-
-                stats_sample_index = 0;
-                sample_aggregate = zero;
-            }
-
-            pixel_value = pixel_value + color;
-            collected_sample_count++;
-
-            if(stats_sample_index == 0 && collected_sample_count >= max(min_samples, 2)) {
-                bool passed_check = false;
-                if(contribution_count / stats_sample_count >= 2) {
-                    const V4 m2_weighted = contribution_m2 / static_cast<float>(contribution_count / stats_sample_count - 1);
-                    const float stddev = sqrtf((m2_weighted.x + m2_weighted.y) + m2_weighted.z);
-                    const float mean_contribution = ((contribution_mean.x + contribution_mean.y) + contribution_mean.z) / 3.0F;
-                    // `stddev / (3 * 3 * getContribution(mean) + 1E-5) < 0.2F` is evaluated in double (worker.cpp:243)
-                    const double relative = static_cast<double>(stddev) / (static_cast<double>(9.0F * mean_contribution) + 1E-5);
-                    if(stddev < 1E-4F || relative < static_cast<double>(0.2F)) {
-                        passed_check = true;
-                        remaining_checks--;
-                        if(remaining_checks <= 0) {
-                            accepted_candidate = true;
-                            break;
-                        }
-                    }
-                }
-                if(!passed_check) {
-                    remaining_checks = check_sample_count;
                 }
             }
+            if(!passed_check) {
+                st.remaining_checks = c.check_sample_count;
+            }
+        }
+        return false;
+    }
+
+    // What processItem writes for the pixel once its loop has ended (worker.cpp:262-317)
+    PTB_DEV V4 pixelFinish(PixelStats &st, const ResolveConsts &c) {
+        V4 pixel_value = st.pixel_value;
+        if(st.collected_sample_count > 0) {
+            pixel_value = pixel_value * (1.0F / static_cast<float>(st.collected_sample_count));
         }
 
-        if(collected_sample_count > 0) {
-            pixel_value = pixel_value * (1.0F / static_cast<float>(collected_sample_count));
+        if(st.candidate_count > 0 && st.n_candidates < kMaxCandidates) {
+            st.candidate_means[st.n_candidates] = st.candidate_mean;
+            st.candidate_m2s[st.n_candidates] = st.candidate_m2;
+            st.candidate_counts[st.n_candidates] = st.candidate_count;
+            st.n_candidates++;
         }
 
-        if(candidate_count > 0 && n_candidates < kMaxCandidates) {
-            candidate_means[n_candidates] = candidate_mean;
-            candidate_m2s[n_candidates] = candidate_m2;
-            candidate_counts[n_candidates] = candidate_count;
-            n_candidates++;
-        }
-
-        if(!accepted_candidate) {
+        if(st.accepted_candidate == 0) {
             V4 colors[kMaxCandidates];
             float stddevs[kMaxCandidates];
             int n = 0;
-            const int needed = max((candidate_batch_count * 3) / 4, 2);
-            for(int c = 0; c < n_candidates; c++) {
-                if(candidate_counts[c] < needed) {
+            const int needed = max((c.candidate_batch_count * 3) / 4, 2);
+            for(int k = 0; k < st.n_candidates; k++) {
+                if(st.candidate_counts[k] < needed) {
                     continue;
                 }
-                const V4 m2_weighted = candidate_m2s[c] / static_cast<float>(candidate_counts[c]);
+                const V4 m2_weighted = st.candidate_m2s[k] / static_cast<float>(st.candidate_counts[k]);
                 const float stddev = sqrtf((m2_weighted.x + m2_weighted.y) + m2_weighted.z);
                 // stable insertion (std::sort on fewer than 16 elements is a stable insertion sort in libstdc++)
                 int at = n;
@@ -689,16 +733,16 @@ namespace ptb {
                     at--;
                 }
                 stddevs[at] = stddev;
-                colors[at] = candidate_means[c];
+                colors[at] = st.candidate_means[k];
                 n++;
             }
             if(n > 0) {
                 pixel_value = colors[0];
                 float stddev = stddevs[0];
-                for(int c = 1; c < n; c++) {
-                    const float other = stddevs[c];
+                for(int k = 1; k < n; k++) {
+                    const float other = stddevs[k];
                     if(other < stdmax(stddev + 0.005F, stddev * 1.01F)) {
-                        pixel_value = pixel_value + sub4(colors[c], pixel_value) / static_cast<float>(c + 1);
+                        pixel_value = pixel_value + sub4(colors[k], pixel_value) / static_cast<float>(k + 1);
                         stddev = other;
                     }
                     else {
@@ -707,11 +751,90 @@ namespace ptb {
                 }
             }
         }
+        return pixel_value;
+    }
 
+    PTB_DEV void storePixel(const ResolveParams &rp, const uint32_t *pixel_list, uint32_t q, V4 value, float4 *out) {
         const uint32_t packed = pixel_list[q];
         const int px = static_cast<int>(packed & 0xFFFFU) - rp.rect_x0;
         const int py = static_cast<int>(packed >> 16) - rp.rect_y0;
-        out[static_cast<size_t>(py) * rp.rect_w + px] = f4(pixel_value);
+        out[static_cast<size_t>(py) * rp.rect_w + px] = f4(value);
+    }
+
+    // processItem's per-pixel loop (worker.cpp:172-319) over the already-computed samples of one pixel: all max_sample_count
+    // samples exist (the fixed-spp path, min == max, where the loop cannot end early).
+    __global__ void __launch_bounds__(kBlock) resolveKernel(ResolveParams rp, const float4 *__restrict__ samples, const uint32_t *__restrict__ pixel_list,
+                                                            float4 *__restrict__ out) {
+        const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+        if(q >= rp.n_pixels) {
+            return;
+        }
+        const ResolveConsts c = resolveConsts(rp.min_sample_count, rp.max_sample_count);
+        PixelStats st;
+        pixelBegin(st, c);
+        for(int pixel_sample = 0; pixel_sample < c.max_samples; pixel_sample++) {
+            if(pixelAdd(st, c, samples[static_cast<size_t>(pixel_sample) * rp.n_pixels + q])) {
+                break;
+            }
+        }
+        storePixel(rp, pixel_list, q, pixelFinish(st, c), out);
+    }
+
+    // ---- adaptive sampling (min != max) in rounds: only the pixels whose loop has not ended get more samples.
+    //
+    // Round r traces samples [first, first + count) of every pixel still active and stores them as
+    // samples[(s - first) * n_active + a] for the a-th active pixel; this kernel feeds them to the pixel's parked state in
+    // sample order -- exactly the sequence the reference's loop sees -- and keeps the pixel active iff the loop neither
+    // ended (acceptance) nor ran out of samples.  Samples of a round traced beyond the end of a pixel's loop are ignored,
+    // as the reference never draws them.
+    __global__ void __launch_bounds__(kBlock) adaptiveInitKernel(ResolveConsts c, uint32_t n_pixels, PixelStats *__restrict__ states, uint32_t *__restrict__ active) {
+        const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+        if(q >= n_pixels) {
+            return;
+        }
+        PixelStats st;
+        pixelBegin(st, c);
+        for(int k = 0; k < kMaxCandidates; k++) {
+            st.candidate_means[k] = V4{0.0F, 0.0F, 0.0F, 0.0F};
+            st.candidate_m2s[k] = V4{0.0F, 0.0F, 0.0F, 0.0F};
+            st.candidate_counts[k] = 0;
+        }
+        states[q] = st;
+        active[q] = q;
+    }
+
+    __global__ void __launch_bounds__(kBlock) adaptiveAdvanceKernel(ResolveConsts c, const float4 *__restrict__ samples, const uint32_t *__restrict__ active, uint32_t n_active,
+                                                                    int round_count, PixelStats *__restrict__ states, uint32_t *__restrict__ next_active,
+                                                                    uint32_t *__restrict__ next_count) {
+        const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+        if(a >= n_active) {
+            return;
+        }
+        const uint32_t q = active[a];
+        PixelStats st = states[q];
+        bool ended = false;
+        for(int s = 0; s < round_count && !ended; s++) {
+            ended = pixelAdd(st, c, samples[static_cast<size_t>(s) * n_active + a]);
+        }
+        states[q] = st;
+        if(!ended && st.next_sample < c.max_samples) {
+            next_active[atomicAdd(next_count, 1U)] = q;
+        }
+    }
+
+    __global__ void __launch_bounds__(kBlock) adaptiveFinishKernel(ResolveParams rp, PixelStats *__restrict__ states, const uint32_t *__restrict__ pixel_list,
+                                                                   float4 *__restrict__ out, unsigned long long *__restrict__ samples_used) {
+        const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+        if(q >= rp.n_pixels) {
+            return;
+        }
+        const ResolveConsts c = resolveConsts(rp.min_sample_count, rp.max_sample_count);
+        PixelStats st = states[q];
+        storePixel(rp, pixel_list, q, pixelFinish(st, c), out);
+        const unsigned long long used = __reduce_add_sync(__activemask(), static_cast<uint32_t>(st.next_sample));
+        if(laneId() == static_cast<uint32_t>(__ffs(static_cast<int>(__activemask()))) - 1U) {
+            atomicAdd(samples_used, used);
+        }
     }
 
     // ------------------------------------------------------------------------------------------------ unit kernels

@@ -118,6 +118,10 @@ struct ptb_context {
     Buffer work_cursor;
     Buffer samples;
     Buffer pixel_list;
+    Buffer pixel_states;  // adaptive sampling (min != max): parked processItem loop state per pixel, the two active-pixel lists and their counters
+    Buffer active_lists;
+    Buffer adaptive_counters;
+    bool adaptive_rounds = true; // PTB_ADAPTIVE_ROUNDS=0: trace all max_sample_count samples of every pixel and let the resolve discard the surplus
     long long pixel_list_key[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1}; // what the device-side pixel list currently holds
     Buffer io_a; // staging for host<->device bulk arrays
     Buffer io_b;
@@ -525,6 +529,91 @@ namespace {
         return PTB_OK;
     }
 
+    // One pixel group of an adaptive (min < max) render: rounds of samples for the pixels still sampling (kernels.cuh,
+    // "adaptive sampling in rounds").  ctx->pixel_list holds the group's rp.n_pixels pixels, ctx->samples has room for the
+    // longest round.  A round's `samples` entries a pixel's loop does not consume (it ended inside the round) are the only
+    // work traced beyond what the reference draws.
+    int renderAdaptiveGroup(ptb_scene *scene, const RenderParams &params, const ResolveParams &rp, const ResolveConsts &rc, int first_round, int later_round,
+                            uint64_t pool_limit, bool count_visits, ClosestMode closest, float4 *d_out, ptb_render_stats *stats, ProgressSink *sink) {
+        ptb_context *ctx = scene->ctx;
+        const uint32_t n_pixels = rp.n_pixels;
+        int status;
+        if((status = ctx->pixel_states.reserve(static_cast<size_t>(n_pixels) * sizeof(PixelStats))) != PTB_OK ||
+           (status = ctx->active_lists.reserve(2 * static_cast<size_t>(n_pixels) * sizeof(uint32_t))) != PTB_OK ||
+           (status = ctx->adaptive_counters.reserve(4 * sizeof(unsigned long long))) != PTB_OK) {
+            return status;
+        }
+        PixelStats *states = ctx->pixel_states.as<PixelStats>();
+        uint32_t *lists[2] = {ctx->active_lists.as<uint32_t>(), ctx->active_lists.as<uint32_t>() + n_pixels};
+        unsigned long long *used = ctx->adaptive_counters.as<unsigned long long>();   // samples the pixels' loops consumed
+        uint32_t *next_count = reinterpret_cast<uint32_t *>(used + 1);                // length of the list being written
+        PTB_CUDA(cudaMemsetAsync(used, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        const unsigned pixel_grid = (n_pixels + kBlock - 1) / kBlock;
+        {
+            LaunchTimer timer(ctx, 1);
+            adaptiveInitKernel<<<pixel_grid, kBlock, 0, ctx->stream>>>(rc, n_pixels, states, lists[0]);
+        }
+        PTB_CUDA(cudaGetLastError());
+
+        uint32_t n_active = n_pixels;
+        int cur = 0;
+        int sample_base = 0;
+        const uint64_t done_at_entry = sink != nullptr ? sink->done_before : 0;
+        while(n_active > 0U && sample_base < rc.max_samples) {
+            const int count = std::min(sample_base == 0 ? first_round : later_round, rc.max_samples - sample_base);
+            const uint64_t total = static_cast<uint64_t>(n_active) * static_cast<uint64_t>(count);
+            PathPool pool{};
+            if((status = carvePool(ctx, poolCapacity(total, pool_limit), scene->shadow_stride, pool)) != PTB_OK) {
+                return status;
+            }
+            PathSource src{};
+            src.pixel_list = ctx->pixel_list.as<uint32_t>();
+            src.active = lists[cur];
+            src.n_pixels = n_active;
+            src.sample_base = static_cast<uint32_t>(sample_base);
+            src.total = total;
+            if((status = runBounces(scene, pool, params, src, ctx->samples.as<float4>(), count_visits, closest, stats, sink)) != PTB_OK) {
+                return status;
+            }
+            if(sink != nullptr) {
+                sink->done_before += total;
+            }
+            PTB_CUDA(cudaMemsetAsync(next_count, 0, sizeof(uint32_t), ctx->stream));
+            {
+                LaunchTimer timer(ctx, 1);
+                adaptiveAdvanceKernel<<<(n_active + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(rc, ctx->samples.as<float4>(), lists[cur], n_active, count, states, lists[cur ^ 1],
+                                                                                                 next_count);
+            }
+            PTB_CUDA(cudaGetLastError());
+            uint32_t n_next = 0;
+            PTB_CUDA(cudaMemcpyAsync(&n_next, next_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+            if(stats != nullptr) {
+                stats->kernel_launches += 1;
+                stats->adaptive_rounds += 1;
+            }
+            n_active = n_next;
+            cur ^= 1;
+            sample_base += count;
+        }
+        {
+            LaunchTimer timer(ctx, 1);
+            adaptiveFinishKernel<<<pixel_grid, kBlock, 0, ctx->stream>>>(rp, states, ctx->pixel_list.as<uint32_t>(), d_out, used);
+        }
+        PTB_CUDA(cudaGetLastError());
+        unsigned long long used_host = 0;
+        PTB_CUDA(cudaMemcpyAsync(&used_host, used, sizeof(used_host), cudaMemcpyDeviceToHost, ctx->stream));
+        PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if(stats != nullptr) {
+            stats->kernel_launches += 2;
+            stats->samples_used += used_host;
+        }
+        if(sink != nullptr) {
+            sink->done_before = done_at_entry; // the caller advances it by the group's nominal size
+        }
+        return PTB_OK;
+    }
+
     int beginCall(ptb_context *ctx, ptb_render_stats *stats, uint32_t flags = 0U) {
         ctx->profile_all = (flags & PTB_FLAG_PROFILE_ALL) != 0U;
         int status = useDevice(ctx);
@@ -790,6 +879,7 @@ int ptb_context_create(int device, ptb_context **out) {
     ctx->log_iterations = envLong("PTB_LOG_ITERATIONS", 0) != 0;
     ctx->production_math = envLong("PTB_PRODUCTION_MATH", 1) != 0;
     ctx->sort_rays = envLong("PTB_SORT_RAYS", 1) != 0;
+    ctx->adaptive_rounds = envLong("PTB_ADAPTIVE_ROUNDS", 1) != 0;
     ctx->iterations_per_sync = static_cast<int>(std::min<long>(kMaxIterationsPerSync, std::max(1L, envLong("PTB_ITERATIONS_PER_SYNC", 4))));
     *out = ctx;
     return PTB_OK;
@@ -803,7 +893,7 @@ int ptb_context_destroy(ptb_context *ctx) {
     if(ctx->stream != nullptr) {
         cudaStreamSynchronize(ctx->stream);
     }
-    for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->redo_queue, &ctx->counters, &ctx->visits, &ctx->work_cursor, &ctx->samples, &ctx->pixel_list,
+    for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->redo_queue, &ctx->counters, &ctx->visits, &ctx->work_cursor, &ctx->samples, &ctx->pixel_list, &ctx->pixel_states, &ctx->active_lists, &ctx->adaptive_counters,
                      &ctx->io_a, &ctx->io_b, &ctx->io_c, &ctx->io_d, &ctx->multi_image, &ctx->multi_staging, &ctx->sort_keys, &ctx->sort_ids, &ctx->sort_temp}) {
         b->release();
     }
@@ -1426,7 +1516,24 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
     }
     const uint64_t n_owned_pixels = tile_first.back();
     const uint64_t max_group_samples = std::min<uint64_t>(std::max<uint64_t>(budget_bytes / sizeof(float4), 1), 0xFFFFFFFFULL);
-    const uint64_t max_group_pixels = std::max<uint64_t>(1, max_group_samples / static_cast<uint64_t>(std::max(spp, 1)));
+
+    // Adaptive sampling (min < max, worker.cpp:236-260): samples are traced in rounds and only for the pixels whose loop
+    // has not ended.  The first round is as long as the shortest loop the reference can run (the acceptance test needs
+    // check_sample_count consecutive passes, the first one no earlier than two full batches and min samples), later rounds
+    // cover an eighth of the remaining range, at least one run of checks.
+    const ResolveConsts rc = resolveConsts(opts->min_sample_count, spp);
+    const bool adaptive = ctx->adaptive_rounds && spp > 0 && opts->min_sample_count < spp;
+    int first_round = spp;
+    int later_round = spp;
+    if(adaptive) {
+        const int batch = rc.stats_sample_count;
+        const int first_check = ((std::max(std::max(rc.min_samples, 2), 2 * batch) + batch - 1) / batch) * batch;
+        first_round = std::min(spp, first_check + (std::max(rc.check_sample_count, 1) - 1) * batch);
+        const int eighth = (((spp - first_round) / 8 + batch - 1) / batch) * batch;
+        later_round = std::max(std::max(eighth, std::max(rc.check_sample_count, 1) * batch), 1);
+    }
+    const int longest_round = adaptive ? std::max(first_round, std::min(later_round, std::max(spp - first_round, 1))) : std::max(spp, 1);
+    const uint64_t max_group_pixels = std::max<uint64_t>(1, max_group_samples / static_cast<uint64_t>(longest_round));
     if(static_cast<uint64_t>(std::max(spp, 1)) > 0xFFFFFFFFULL) {
         return fail(PTB_ERR_UNSUPPORTED, "ptb_render: more than 2^32 - 1 samples per pixel");
     }
@@ -1446,7 +1553,7 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
         const long long key[9] = {x0, y0, w, h, tile, shard_index, shard_count, static_cast<long long>(group_begin), static_cast<long long>(group_end)};
         const bool list_cached = std::equal(key, key + 9, ctx->pixel_list_key);
         const uint32_t n_pixels = static_cast<uint32_t>(group_end - group_begin);
-        const uint64_t total = static_cast<uint64_t>(n_pixels) * spp;
+        const uint64_t total = static_cast<uint64_t>(n_pixels) * (adaptive ? longest_round : spp);
         if((status = ctx->pixel_list.reserve(n_pixels * sizeof(uint32_t))) != PTB_OK || (status = ctx->samples.reserve(total * sizeof(float4))) != PTB_OK) {
             return status;
         }
@@ -1474,6 +1581,25 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
             std::copy(key, key + 9, ctx->pixel_list_key);
         }
 
+        ResolveParams rp{};
+        rp.min_sample_count = opts->min_sample_count;
+        rp.max_sample_count = spp;
+        rp.n_pixels = n_pixels;
+        rp.rect_x0 = x0;
+        rp.rect_y0 = y0;
+        rp.rect_w = w;
+
+        if(adaptive) {
+            if((status = renderAdaptiveGroup(scene, params, rp, rc, first_round, later_round, pool_limit, count_visits, closestMode(scene, opts->flags), d_out, stats, &sink)) != PTB_OK) {
+                return status;
+            }
+            sink.done_before = group_end * static_cast<uint64_t>(spp);
+            if(progress != nullptr && group_end < n_owned_pixels) {
+                progress(user, sink.done_before, sink.total);
+            }
+            continue;
+        }
+
         const uint32_t capacity = poolCapacity(total, pool_limit);
         PathPool pool{};
         if((status = carvePool(ctx, capacity, scene->shadow_stride, pool)) != PTB_OK) {
@@ -1489,14 +1615,9 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
             return status;
         }
         sink.done_before += total;
-
-        ResolveParams rp{};
-        rp.min_sample_count = opts->min_sample_count;
-        rp.max_sample_count = spp;
-        rp.n_pixels = n_pixels;
-        rp.rect_x0 = x0;
-        rp.rect_y0 = y0;
-        rp.rect_w = w;
+        if(stats != nullptr) {
+            stats->samples_used += total; // refined below for min != max without rounds: unknown, reported as traced
+        }
         {
             LaunchTimer timer(ctx, 1);
             resolveKernel<<<(n_pixels + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(rp, ctx->samples.as<float4>(), ctx->pixel_list.as<uint32_t>(), d_out);

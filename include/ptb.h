@@ -235,6 +235,10 @@ typedef struct ptb_render_stats {
     uint64_t certified_suspect_hits; /* with PTB_FLAG_COUNT_VISITS: primitive tests of the certified walk that reported a hit */
                                      /* more than 2^-8 in front of the primitive's own bounding box -- the only situation in */
                                      /* which a primitive the walk never reaches could change the reference's answer         */
+    uint64_t samples_used;    /* ptb_render: pixel-samples the per-pixel loops of processItem consumed (worker.cpp:172-260).   */
+                              /* min == max: equals `samples`.  min < max: the loop of a pixel ends early once the acceptance */
+                              /* test fires; samples - samples_used were traced ahead of a loop that had already ended        */
+    uint64_t adaptive_rounds; /* min < max: rounds of samples traced (only pixels still sampling take part in a round)        */
 } ptb_render_stats;
 
 /* ------------------------------------------------------------------------------------------------ entry points */

@@ -1432,19 +1432,27 @@ void pto_process_item(const pto_scene *s, const ptb_camera *cam, int width, int 
 
 /* processItem's per-pixel statistics over precomputed samples: samples[k * n_pixels + q], alpha = collected flag.
  * Used to check the device's resolve kernel on identical per-sample inputs. */
-void pto_resolve(int min_samples, int max_samples, uint32_t n_pixels, const float *samples, float *out_rgba) {
+/* consumed_out (may be NULL): how many samples the loop of worker.cpp:172-260 drew for the pixel before it ended */
+void pto_resolve_counts(int min_samples, int max_samples, uint32_t n_pixels, const float *samples, float *out_rgba, int32_t *consumed_out) {
     for(uint32_t q = 0; q < n_pixels; q++) {
         pixel_state p;
         pixel_begin(&p, min_samples, max_samples);
-        for(int k = 0; k < max_samples; k++) {
+        int k = 0;
+        while(k < max_samples) {
             const float *sm = samples + 4 * ((size_t)k * n_pixels + q);
+            k++;
             if(sm[3] == 0.0F) continue;
             rgba c = {{sm[0], sm[1], sm[2], 1.0F}};
             if(pixel_add(&p, c)) break;
         }
         rgba v = pixel_finish(&p);
         memcpy(out_rgba + 4 * (size_t)q, v.c, sizeof(float) * 4);
+        if(consumed_out != NULL) consumed_out[q] = k;
     }
+}
+
+void pto_resolve(int min_samples, int max_samples, uint32_t n_pixels, const float *samples, float *out_rgba) {
+    pto_resolve_counts(min_samples, max_samples, n_pixels, samples, out_rgba, NULL);
 }
 
 /* ------------------------------------------------------------------------------------------------ unit entries

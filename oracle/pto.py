@@ -27,6 +27,7 @@ def load():
         lib.pto_render_samples.argtypes = [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_uint64, _P, _P, _P, _P]
         lib.pto_process_item.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P]
         lib.pto_resolve.argtypes = [C.c_int, C.c_int, C.c_uint32, _P, _P]
+        lib.pto_resolve_counts.argtypes = [C.c_int, C.c_int, C.c_uint32, _P, _P, _P]
         lib.pto_set_guard.argtypes = [C.c_int]
         lib.pto_scene_certifiable.argtypes = [_P]
         lib.pto_prim_normal.argtypes = [_P, C.c_uint64, _P, _P]
@@ -131,6 +132,16 @@ def resolve(min_spp, max_spp, samples):
     out = np.zeros((n_pixels, 4), np.float32)
     load().pto_resolve(min_spp, max_spp, n_pixels, _ptr(samples), _ptr(out))
     return out
+
+
+def resolve_counts(min_spp, max_spp, samples):
+    """resolve() plus the number of samples each pixel's loop drew before it ended (worker.cpp:236-260)."""
+    samples = np.ascontiguousarray(samples, np.float32)
+    n_pixels = samples.shape[1]
+    out = np.zeros((n_pixels, 4), np.float32)
+    consumed = np.zeros(n_pixels, np.int32)
+    load().pto_resolve_counts(min_spp, max_spp, n_pixels, _ptr(samples), _ptr(out), _ptr(consumed))
+    return out, consumed
 
 
 def _pod(value, dtype):

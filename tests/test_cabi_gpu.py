@@ -82,9 +82,18 @@ def test_render_equals_oracle_per_sample_plus_resolve(ctx, name, spp):
     for s in range(hi):
         seeds = counter_key(seed, xs, ys, np.full(len(xs), s))
         samples[s], _ = oracle.render_samples(camera, w, h, float(g["epsilon"]), np.stack([xs, ys], axis=1).astype(np.int32), seeds)
-    want = pto.resolve(lo, hi, samples).reshape(rh, rw, 4)
-    assert np.array_equal(image, want)
-    assert stats.samples == rw * rh * hi
+    want, consumed = pto.resolve_counts(lo, hi, samples)
+    assert np.array_equal(image, want.reshape(rh, rw, 4))
+    # adaptive sampling is adaptive on the device too: the samples the reference's loops consume are all there, what
+    # was traced beyond them is bounded by the round a pixel's loop ended in, and fixed-spp renders trace exactly max
+    assert stats.samples_used == int(consumed.sum())
+    assert stats.samples_used <= stats.samples <= rw * rh * hi
+    if lo == hi:
+        assert stats.samples == rw * rh * hi and stats.adaptive_rounds == 0
+    else:
+        assert stats.adaptive_rounds >= 1
+        if consumed.sum() < 0.9 * rw * rh * hi:
+            assert stats.samples < rw * rh * hi
 
 
 def test_fresh_inputs_against_oracle(ctx):
@@ -321,6 +330,51 @@ def test_sharded_renders_sum_to_the_full_frame(ctx):
             total += part
         assert covered.all() and np.array_equal(total, full)
     scene.close()
+
+
+def test_adaptive_rounds_trace_fewer_samples_for_the_same_image(ctx, monkeypatch):
+    """min < max (worker.cpp:236-260: the per-pixel loop ends once the acceptance test has fired): rendering in rounds for
+    the pixels still sampling gives bit for bit the image of tracing all max samples of every pixel and resolving
+    afterwards, with fewer samples traced; also across pixel groups (small per-sample buffer) and tile shards."""
+    g = load_golden("samples", "cornell_mesh")
+    w, h = 112, 96
+    kw = camera_kwargs(g["camera"])
+    kw["aspect_ratio"] = -w / h
+    camera = pod_camera(kw)
+    lo, hi = 8, 192
+
+    monkeypatch.setenv("PTB_ADAPTIVE_ROUNDS", "0")
+    plain_ctx = capi.Context(-1)
+    plain_scene = _scene(plain_ctx, g)
+    want, stats_all = plain_scene.render(camera, capi.render_opts(w, h, lo, hi, 1e-3, seed=5))
+    plain_scene.close()
+    plain_ctx.close()
+    assert stats_all.samples == w * h * hi and stats_all.adaptive_rounds == 0
+
+    monkeypatch.setenv("PTB_ADAPTIVE_ROUNDS", "1")
+    scene = _scene(ctx, g)
+    got, stats = scene.render(camera, capi.render_opts(w, h, lo, hi, 1e-3, seed=5))
+    assert np.array_equal(got, want)
+    assert stats.adaptive_rounds > 1 and stats.samples_used <= stats.samples < stats_all.samples
+    print(f"adaptive {lo}..{hi} spp: the loops consume {stats.samples_used / (w * h):.1f} samples per pixel, traced {stats.samples / (w * h):.1f} "
+          f"in {stats.adaptive_rounds} rounds (instead of {hi})")
+    # a frame whose loops end early must get cheaper: at most 10 % more traced than consumed + one round per pixel
+    assert stats.samples <= 1.1 * stats.samples_used + w * h * max(hi // 8, 16)
+
+    total = np.zeros_like(want)
+    for rank in range(3):
+        part, _ = scene.render(camera, capi.render_opts(w, h, lo, hi, 1e-3, seed=5, shard_index=rank, shard_count=3))
+        total += part
+    assert np.array_equal(total, want)
+    scene.close()
+
+    monkeypatch.setenv("PTB_SAMPLE_BUFFER_MB", "1")  # 65536 sample slots: several pixel groups
+    small_ctx = capi.Context(-1)
+    small_scene = _scene(small_ctx, g)
+    grouped, stats_g = small_scene.render(camera, capi.render_opts(w, h, lo, hi, 1e-3, seed=5))
+    small_scene.close()
+    small_ctx.close()
+    assert np.array_equal(grouped, want) and stats_g.samples_used == stats.samples_used
 
 
 def test_full_size_scene_properties(ctx, ref):

@@ -236,13 +236,15 @@ def test_progress_callbacks_fire_while_the_frame_renders(b200):
     scene = spec.build(b200)
     w, h, spp = 640, 360, 64
     camera = scenes.demo_camera(b200, w, h)
-    scene.process_job(camera, w, h, 4, 4, 1e-3)  # warm-up: workspace allocation
+    scene.process_job(camera, w, h, spp, spp, 1e-3)  # warm-up at the same size: the workspace (pool, per-sample buffer) is allocated here, not in the timed call
     for budget_mb in ("0", "64"):  # one pixel group / several pixel groups
         os.environ["PTB_SAMPLE_BUFFER_MB"] = budget_mb
+        os.environ["PTB_POOL_PATHS"] = str(1 << 21)  # a pool much smaller than the frame: many batches of bounce iterations, as in a long render
         try:
             image, info = scene.process_job(camera, w, h, spp, spp, 1e-3)
         finally:
             os.environ.pop("PTB_SAMPLE_BUFFER_MB", None)
+            os.environ.pop("PTB_POOL_PATHS", None)
         assert info["callbacks"] == info["total_tiles"] == 20 * 12 and info["monotonic"]
         assert 0 <= info["first_callback_s"] < 0.6 * info["seconds"], info
         assert info["half_callbacks_s"] < 0.9 * info["seconds"], info

@@ -3,6 +3,9 @@
 
   python tools/ncu_summary.py launches gpurun_out/launches.csv profiles/r01_launches_<tag>.md
   python tools/ncu_summary.py full gpurun_out/prof.ncu-rep profiles/r01_ncu_<tag>.md
+  python tools/ncu_summary.py traffic gpurun_out/prof.ncu-rep profiles/traffic.json "<how the capture was made>"
+      DRAM bytes per launch of the captured kernels (what bench.py quotes as roofline.traffic): written from the SAME
+      report as the full summary, so the two cannot drift apart
 """
 import collections
 import csv
@@ -79,5 +82,39 @@ def full(src, dst):
             f.write(f"| {m} | {units[idx[m]]} | " + " | ".join(r[idx[m]] for r in rows[2:]) + " |\n")
 
 
+def traffic(src, dst, how):
+    import json
+
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    time_scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+
+    def val(row, metric, table):
+        return float(row[idx[metric]].replace(",", "")) * table[units[idx[metric]]]
+
+    launches_out = []
+    for r in rows[2:]:
+        launches_out.append({
+            "kernel": r[idx["Kernel Name"]].split("(")[0].replace("void ", ""),
+            "dram_read_bytes": val(r, "dram__bytes_read.sum", scale),
+            "dram_write_bytes": val(r, "dram__bytes_write.sum", scale),
+            "duration_ms": val(r, "gpu__time_duration.sum", time_scale),
+            "issue_active_pct": float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
+            "threads_per_instruction": float(r[idx["smsp__thread_inst_executed_per_inst_executed.ratio"]]),
+            "dram_throughput_pct": float(r[idx["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]),
+        })
+    top = next((k for k in launches_out if "traceClosestKernel<2" in k["kernel"]), launches_out[0])
+    out = {
+        "source": f"{src} -> this file and the matching profiles/*.md summary come from the same report; {how}",
+        "kernel": top["kernel"],
+        "dram_bytes_per_launch": top["dram_read_bytes"] + top["dram_write_bytes"],
+        "launches": launches_out,
+    }
+    json.dump(out, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
