@@ -68,6 +68,9 @@ class SceneInfo(C.Structure):
         ("query_tree_on_device", C.c_uint32),
         ("certifiable", C.c_uint32),
         ("query_tree_device_ms", C.c_double),
+        ("built_on_device", C.c_uint32),
+        ("query_tree_kind", C.c_uint32),
+        ("reference_tree_device_ms", C.c_double),
     ]
 
 
@@ -143,6 +146,7 @@ PROTOTYPES = {
     "ptb_scene_create": (C.c_int, [_P, C.POINTER(SceneDesc), C.POINTER(_P)]),
     "ptb_scene_destroy": (C.c_int, [_P]),
     "ptb_scene_get_info": (C.c_int, [_P, C.POINTER(SceneInfo)]),
+    "ptb_scene_read": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64]),
     "ptb_intersect": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint32, C.POINTER(RenderStats)]),
     "ptb_occluded": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint32, C.POINTER(RenderStats)]),
     "ptb_render": (C.c_int, [_P, C.POINTER(Camera), C.POINTER(RenderOpts), C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(RenderStats)]),
@@ -338,6 +342,33 @@ class Scene:
         info = SceneInfo()
         check(load().ptb_scene_get_info(self._h, C.byref(info)))
         return info
+
+    NODE_DTYPE = np.dtype([("left_lo", np.float32, 3), ("left_hi", np.float32, 3), ("right_lo", np.float32, 3), ("right_hi", np.float32, 3),
+                           ("left", np.int32), ("right", np.int32), ("leaf_count", np.int32), ("parent", np.int32)])
+
+    def read_nodes(self, query_tree=False):
+        """The 64-byte inner records of the reference-topology tree (or the query tree) as a structured array."""
+        n = max(len(self.prims) - 1, 0)
+        if query_tree and self.info().query_tree_kind == 0:
+            n = 0
+        out = np.zeros(n, self.NODE_DTYPE)
+        check(load().ptb_scene_read(self._h, 1 if query_tree else 0, _ptr(out) if n else None, out.nbytes))
+        return out
+
+    def read_slot_to_prim(self):
+        out = np.zeros(len(self.prims), np.uint32)
+        check(load().ptb_scene_read(self._h, 4, _ptr(out) if len(out) else None, out.nbytes))
+        return out
+
+    def read_geom(self):
+        out = np.zeros((len(self.prims), 16), np.float32)
+        check(load().ptb_scene_read(self._h, 2, _ptr(out) if len(out) else None, out.nbytes))
+        return out
+
+    def read_shade(self):
+        out = np.zeros((len(self.prims), 12), np.float32)
+        check(load().ptb_scene_read(self._h, 3, _ptr(out) if len(out) else None, out.nbytes))
+        return out
 
     def intersect(self, rays, flags=0):
         rays = _f32(rays, (-1, 6))

@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 namespace ptb_guard {
 
@@ -37,8 +39,68 @@ namespace ptb_guard {
         g.certifiable = 1;
         const double slack = kGuardSlack;
         double tau_safe = 0.0;
-        for(uint64_t i = 0; i < n_prims && g.certifiable != 0U; i++) {
-            const ptb_prim &p = prims[i];
+
+        // Pass 1 (parallel for large scenes): almost every triangle of a mesh is "small" -- its worst relative distance
+        // error is far below the slack -- and contributes nothing but a candidate for tau_safe, a maximum.  Everything else
+        // (spheres, large triangles, degenerate ones) is collected and goes through the sequential pass 2 in index order,
+        // where planes are merged.
+        std::vector<uint64_t> special;
+        {
+            const unsigned workers = n_prims >= (1U << 16) ? std::min(16U, std::max(1U, std::thread::hardware_concurrency())) : 1U;
+            std::vector<std::vector<uint64_t>> found(workers);
+            std::vector<double> tau(workers, 0.0);
+            auto scan = [&](unsigned w) {
+                const uint64_t begin = n_prims * w / workers;
+                const uint64_t end = n_prims * (w + 1) / workers;
+                for(uint64_t i = begin; i < end; i++) {
+                    const ptb_prim &p = prims[i];
+                    if(p.kind != PTB_PRIM_TRIANGLE) {
+                        if(p.kind == PTB_PRIM_SPHERE) {
+                            found[w].push_back(i);
+                        }
+                        continue;
+                    }
+                    const Vec a{p.p[0], p.p[1], p.p[2]};
+                    const Vec b{p.p[3], p.p[4], p.p[5]};
+                    const Vec c{p.p[6], p.p[7], p.p[8]};
+                    const Vec ab = sub(b, a);
+                    const Vec ac = sub(c, a);
+                    const Vec n{ab.y * ac.z - ab.z * ac.y, ab.z * ac.x - ab.x * ac.z, ab.x * ac.y - ab.y * ac.x};
+                    const double area2 = norm(n);
+                    const double m = norm(ab) * norm(ac);
+                    if(!(area2 > 0.0) || !(m > 0.0)) {
+                        continue; // degenerate: never hit
+                    }
+                    const double worst_relative = 9.0 * kEps * kSafety * m / 1e-6;
+                    if(worst_relative <= slack / 12.0) {
+                        const double diameter = std::max(norm(ab), std::max(norm(ac), norm(sub(c, b))));
+                        tau[w] = std::max(tau[w], worst_relative * diameter / (slack / 4.0));
+                    }
+                    else {
+                        found[w].push_back(i);
+                    }
+                }
+            };
+            if(workers > 1U) {
+                std::vector<std::thread> pool;
+                for(unsigned w = 0; w < workers; w++) {
+                    pool.emplace_back(scan, w);
+                }
+                for(std::thread &t : pool) {
+                    t.join();
+                }
+            }
+            else {
+                scan(0U);
+            }
+            for(unsigned w = 0; w < workers; w++) {
+                tau_safe = std::max(tau_safe, tau[w]);
+                special.insert(special.end(), found[w].begin(), found[w].end());
+            }
+        }
+
+        for(size_t at = 0; at < special.size() && g.certifiable != 0U; at++) {
+            const ptb_prim &p = prims[special[at]];
             if(p.kind == PTB_PRIM_SPHERE) {
                 if(g.n_spheres == static_cast<uint32_t>(kGuardSpheres)) {
                     g.certifiable = 0;

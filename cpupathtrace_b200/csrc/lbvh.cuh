@@ -29,7 +29,8 @@ namespace ptb {
     struct LbvhWorkspace {
         const float *boxes;        // 6 floats per slot: lo.xyz, hi.xyz
         uint64_t *keys;            // sorted Morton codes
-        uint32_t *slots;           // sorted position -> slot
+        uint32_t *slots;           // sorted position -> slot (null: the position is the slot)
+        const uint32_t *box_ids;   // sorted position -> index of the primitive's box in `boxes` (null: the slot)
         int32_t *leaf_parent;      // sorted position -> inner node
         int32_t *node_parent;      // inner node -> inner node, -1 for the root
         int2 *children;            // inner node -> (left ref, right ref); ref >= 0 inner node, < 0 ~sorted position
@@ -193,8 +194,8 @@ namespace ptb {
                 l_ref = ch.x;
             }
             else {
-                const uint32_t slot = w.slots[~ch.x];
-                lb = loadBox(w.boxes + 6 * static_cast<size_t>(slot));
+                const uint32_t slot = w.slots != nullptr ? w.slots[~ch.x] : static_cast<uint32_t>(~ch.x);
+                lb = loadBox(w.boxes + 6 * static_cast<size_t>(w.box_ids != nullptr ? w.box_ids[~ch.x] : slot));
                 l_ref = ~static_cast<int32_t>(slot);
             }
             if(ch.y >= 0) {
@@ -204,14 +205,16 @@ namespace ptb {
                 r_ref = ch.y;
             }
             else {
-                const uint32_t slot = w.slots[~ch.y];
-                rb = loadBox(w.boxes + 6 * static_cast<size_t>(slot));
+                const uint32_t slot = w.slots != nullptr ? w.slots[~ch.y] : static_cast<uint32_t>(~ch.y);
+                rb = loadBox(w.boxes + 6 * static_cast<size_t>(w.box_ids != nullptr ? w.box_ids[~ch.y] : slot));
                 r_ref = ~static_cast<int32_t>(slot);
             }
             float *nb = w.node_box + 6 * static_cast<size_t>(node);
             for(int c = 0; c < 3; c++) {
-                nb[c] = fminf(lb.lo[c], rb.lo[c]);
-                nb[3 + c] = fmaxf(lb.hi[c], rb.hi[c]);
+                // impl::combineAreas (bounding_box.cpp:8-12, 21-27) with std::min / std::max's choice between equal values,
+                // like the host builder: the parity tree's records come out bit for bit the same from either builder
+                nb[c] = rb.lo[c] < lb.lo[c] ? rb.lo[c] : lb.lo[c];
+                nb[3 + c] = lb.hi[c] < rb.hi[c] ? rb.hi[c] : lb.hi[c];
             }
             const uint32_t height = 1U + max(l_height, r_height);
             w.node_height[node] = height;

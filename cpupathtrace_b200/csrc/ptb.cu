@@ -8,6 +8,7 @@
 #include "host_math.h"
 #include "kernels.cuh"
 #include "lbvh.cuh"
+#include "gpu_build.cuh"
 #include "post_process.cuh"
 
 #include <cub/cub.cuh>
@@ -131,6 +132,7 @@ struct ptb_context {
     Buffer sort_ids;
     Buffer sort_temp;
     bool sort_rays = true; // PTB_SORT_RAYS=0: trace batches in the caller's order
+    Buffer build_arena;   // scene setup on the device: every temporary of a tree build is carved from this one allocation
     Buffer multi_image;   // ptb_render_multi: this replica's share of the frame (its tiles, zeros elsewhere)
     Buffer multi_staging; // ptb_render_multi on the first replica: copies of the other replicas' images when peers cannot map each other
     uint32_t *host_counters = nullptr; // pinned
@@ -620,6 +622,9 @@ namespace {
         if(status != PTB_OK) {
             return status;
         }
+        // the arena of the last scene build (kept so that building several scenes in a row does not go through the
+        // allocator each time) is handed back before a query or render sizes its workspace from the free memory
+        ctx->build_arena.release();
         if(stats != nullptr) {
             std::memset(stats, 0, sizeof(*stats));
         }
@@ -644,16 +649,16 @@ namespace {
     // Builds the query hierarchy on the device (lbvh.cuh).  `boxes` holds 6 floats per slot in the reference tree's leaf
     // order.  On success `records` holds n - 1 inner records, the root is record 0 and `height` the number of inner
     // levels (what the traversal stack must hold).
-    int buildQueryBvhOnDevice(ptb_context *ctx, const std::vector<float> &boxes, uint32_t n, const float root_lo[3], const float root_hi[3], Buffer &records,
+    int buildQueryBvhOnDevice(ptb_context *ctx, const float *boxes_on_device, uint32_t n, const float root_lo[3], const float root_hi[3], Buffer &records,
                               uint32_t &height, double &device_ms) {
         height = 0;
         device_ms = 0.0;
         if(n < 2) {
             return PTB_OK;
         }
-        Buffer d_boxes, keys_a, keys_b, slots_a, slots_b, leaf_parent, node_parent, children, arrivals, node_box, node_height, node_count, sort_temp, d_height;
+        Buffer keys_a, keys_b, slots_a, slots_b, leaf_parent, node_parent, children, arrivals, node_box, node_height, node_count, sort_temp, d_height;
         auto release_all = [&]() {
-            for(Buffer *b : {&d_boxes, &keys_a, &keys_b, &slots_a, &slots_b, &leaf_parent, &node_parent, &children, &arrivals, &node_box, &node_height, &node_count, &sort_temp,
+            for(Buffer *b : {&keys_a, &keys_b, &slots_a, &slots_b, &leaf_parent, &node_parent, &children, &arrivals, &node_box, &node_height, &node_count, &sort_temp,
                              &d_height}) {
                 b->release();
             }
@@ -665,7 +670,6 @@ namespace {
                 status = b.reserve(std::max<size_t>(bytes, 16));
             }
         };
-        reserve(d_boxes, boxes.size() * sizeof(float));
         reserve(keys_a, n * sizeof(uint64_t));
         reserve(keys_b, n * sizeof(uint64_t));
         reserve(slots_a, n * sizeof(uint32_t));
@@ -702,14 +706,10 @@ namespace {
             release_all();
             return st;
         };
-        if(cudaMemcpyAsync(d_boxes.ptr, boxes.data(), boxes.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
-            cudaGetLastError();
-            return finish(fail(PTB_ERR_CUDA, "buildQueryBvhOnDevice: box upload failed"));
-        }
         cudaEventRecord(start, ctx->stream);
 
         LbvhWorkspace w{};
-        w.boxes = d_boxes.as<float>();
+        w.boxes = boxes_on_device;
         w.keys = keys_b.as<uint64_t>();
         w.slots = slots_b.as<uint32_t>();
         w.leaf_parent = leaf_parent.as<int32_t>();
@@ -744,6 +744,256 @@ namespace {
         cudaEventElapsedTime(&ms, start, stop);
         device_ms = ms;
         height = h;
+        return finish(PTB_OK);
+    }
+
+    // a piece of a larger device allocation
+    struct Carved {
+        void *ptr = nullptr;
+        size_t bytes = 0;
+        template<typename T>
+        T *as() const {
+            return static_cast<T *>(ptr);
+        }
+    };
+
+    // ---- scene setup on the device (gpu_build.cuh)
+    //
+    // Builds one hierarchy over `n` boxes (6 floats per id, on the device) level by level.
+    //   reference_split: impl::constructBVH's topology (ids = the caller's primitive numbers); `order_out` receives the
+    //                    leaf order (slot -> primitive), leaf refs of the records are ~slot.
+    //   otherwise:       full-sweep SAH query tree (ids = leaf slots); leaf refs are ~id.
+    // `depth` = deepest leaf with the root at 1; 0 when the tree came out deeper than `max_depth` (caller falls back).
+    int buildTreeOnDevice(ptb_context *ctx, const float *d_boxes, uint32_t n, bool reference_split, uint32_t max_depth, Buffer &records, Buffer *order_out, uint32_t &depth,
+                          float root_box[6], double &device_ms, size_t *arena_bytes_only = nullptr) {
+        depth = 0;
+        device_ms = 0.0;
+        if(n < 2U) {
+            return fail(PTB_ERR_INVALID_ARGUMENT, "buildTreeOnDevice: fewer than two primitives");
+        }
+        const size_t inner = static_cast<size_t>(n) - 1;
+        const int n_lists = reference_split ? 4 : 3;
+        // all temporaries of a build are carved from one arena (ctx->build_arena): thirty cudaMalloc / cudaFree pairs cost
+        // ten times the build itself
+        Carved lists_a, lists_b, keys, keys_sorted, ids, node_pos_a, node_pos_b, seg_begin, seg_count, children, node_parent, leaf_parent, side, flags, ranks, any_active, cut,
+            group_keys, best_cost, best_key, seq_a, seq_b, costs, temp, arrivals, node_box, node_height, node_count, d_height;
+        std::vector<Carved *> carved;
+        auto release_all = [&]() {};
+        int status = PTB_OK;
+        auto carve = [&](Carved &c, size_t bytes) {
+            c.bytes = (std::max<size_t>(bytes, 16) + 255) & ~static_cast<size_t>(255);
+            carved.push_back(&c);
+        };
+        auto reserve = [&](Buffer &b, size_t bytes) {
+            if(status == PTB_OK) {
+                status = b.reserve(std::max<size_t>(bytes, 16));
+            }
+        };
+        carve(lists_a, static_cast<size_t>(n_lists) * n * sizeof(uint32_t));
+        carve(lists_b, static_cast<size_t>(n_lists) * n * sizeof(uint32_t));
+        carve(keys, 3 * static_cast<size_t>(n) * sizeof(float));
+        carve(keys_sorted, static_cast<size_t>(n) * sizeof(float));
+        carve(ids, static_cast<size_t>(n) * sizeof(uint32_t));
+        carve(node_pos_a, static_cast<size_t>(n) * sizeof(int32_t));
+        carve(node_pos_b, static_cast<size_t>(n) * sizeof(int32_t));
+        carve(seg_begin, inner * sizeof(uint32_t));
+        carve(seg_count, inner * sizeof(uint32_t));
+        carve(children, inner * sizeof(int2));
+        carve(node_parent, inner * sizeof(int32_t));
+        carve(leaf_parent, static_cast<size_t>(n) * sizeof(int32_t));
+        carve(side, static_cast<size_t>(n) * sizeof(uint32_t));
+        carve(flags, 3 * (static_cast<size_t>(n) + 1) * sizeof(uint32_t));
+        carve(ranks, 3 * (static_cast<size_t>(n) + 1) * sizeof(uint32_t));
+        carve(any_active, sizeof(uint32_t));
+        if(reference_split) {
+            carve(cut, 3 * inner * sizeof(float));
+            carve(group_keys, 36 * inner * sizeof(uint32_t));
+        }
+        else {
+            carve(best_cost, inner * sizeof(uint32_t));
+            carve(best_key, inner * sizeof(unsigned long long));
+            carve(seq_a, 6 * static_cast<size_t>(n) * sizeof(SweepBox));
+            carve(seq_b, 6 * static_cast<size_t>(n) * sizeof(SweepBox));
+            carve(costs, 3 * static_cast<size_t>(n) * sizeof(float));
+        }
+        carve(arrivals, inner * sizeof(uint32_t));
+        carve(node_box, inner * 6 * sizeof(float));
+        carve(node_height, inner * sizeof(uint32_t));
+        carve(node_count, inner * sizeof(uint32_t));
+        carve(d_height, sizeof(uint32_t));
+        if(arena_bytes_only == nullptr) {
+            reserve(records, inner * sizeof(NodeRecord));
+            if(order_out != nullptr) {
+                reserve(*order_out, static_cast<size_t>(n) * sizeof(uint32_t));
+            }
+        }
+
+        size_t sort_bytes = 0;
+        size_t sum_bytes = 0;
+        size_t sweep_bytes = 0;
+        const int scan_items = static_cast<int>(3 * (static_cast<size_t>(n) + 1));
+        if(status == PTB_OK) {
+            cudaError_t e1 = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys.as<float>(), keys_sorted.as<float>(), ids.as<uint32_t>(), lists_a.as<uint32_t>(),
+                                                             static_cast<int>(n), 0, 32, ctx->stream);
+            cudaError_t e2 = cub::DeviceScan::ExclusiveSum(nullptr, sum_bytes, flags.as<uint32_t>(), ranks.as<uint32_t>(), scan_items, ctx->stream);
+            cudaError_t e3 = cudaSuccess;
+            if(!reference_split) {
+                e3 = cub::DeviceScan::InclusiveScan(nullptr, sweep_bytes, seq_a.as<SweepBox>(), seq_b.as<SweepBox>(), SweepMerge{}, static_cast<int>(6 * static_cast<size_t>(n)),
+                                                    ctx->stream);
+            }
+            if(e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+                cudaGetLastError();
+                status = fail(PTB_ERR_CUDA, "buildTreeOnDevice: cub workspace sizing failed");
+            }
+        }
+        size_t temp_bytes = std::max(sort_bytes, std::max(sum_bytes, sweep_bytes));
+        carve(temp, temp_bytes);
+        size_t arena_bytes = 0;
+        for(const Carved *c : carved) {
+            arena_bytes += c->bytes;
+        }
+        if(arena_bytes_only != nullptr) {
+            *arena_bytes_only = arena_bytes; // dry run: the caller sizes one arena for several builds
+            return status;
+        }
+        reserve(ctx->build_arena, arena_bytes);
+        if(status == PTB_OK) {
+            char *at = ctx->build_arena.as<char>();
+            for(Carved *c : carved) {
+                c->ptr = at;
+                at += c->bytes;
+            }
+        }
+        if(status != PTB_OK) {
+            release_all();
+            return status;
+        }
+        if(static_cast<size_t>(n) * 6 > static_cast<size_t>(std::numeric_limits<int>::max()) - 8) {
+            release_all();
+            return fail(PTB_ERR_UNSUPPORTED, "buildTreeOnDevice: too many primitives for the device builder");
+        }
+
+        cudaEvent_t start = nullptr;
+        cudaEvent_t stop = nullptr;
+        cudaEventCreate(&start);
+        cudaEventCreate(&stop);
+        auto finish = [&](int st) {
+            cudaEventDestroy(start);
+            cudaEventDestroy(stop);
+            release_all();
+            return st;
+        };
+        cudaEventRecord(start, ctx->stream);
+
+        BuildState st{};
+        st.n = n;
+        st.boxes = d_boxes;
+        for(int a = 0; a < n_lists; a++) {
+            st.list[a] = lists_a.as<uint32_t>() + static_cast<size_t>(a) * n;
+            st.list_next[a] = lists_b.as<uint32_t>() + static_cast<size_t>(a) * n;
+        }
+        st.node_of_pos = node_pos_a.as<int32_t>();
+        st.node_of_pos_next = node_pos_b.as<int32_t>();
+        st.seg_begin = seg_begin.as<uint32_t>();
+        st.seg_count = seg_count.as<uint32_t>();
+        st.children = children.as<int2>();
+        st.node_parent = node_parent.as<int32_t>();
+        st.leaf_parent = leaf_parent.as<int32_t>();
+        st.side = side.as<uint32_t>();
+        st.flags = flags.as<uint32_t>();
+        st.ranks = ranks.as<uint32_t>();
+        st.any_active = any_active.as<uint32_t>();
+        st.cut = cut.as<float>();
+        st.group_keys = group_keys.as<uint32_t>();
+        st.best_cost = best_cost.as<uint32_t>();
+        st.best_key = best_key.as<unsigned long long>();
+
+        const unsigned grid = (n + kBuildBlock - 1U) / kBuildBlock;
+        const unsigned grid_plus = (n + 1U + kBuildBlock - 1U) / kBuildBlock; // kernels that also write the sentinel at position n
+        const dim3 grid3(grid, 3);
+        const dim3 grid3_plus(grid_plus, 3);
+        axisKeysKernel<<<grid, kBuildBlock, 0, ctx->stream>>>(d_boxes, n, reference_split ? 0 : 1, keys.as<float>(), ids.as<uint32_t>());
+        for(int a = 0; a < 3; a++) {
+            cub::DeviceRadixSort::SortPairs(temp.ptr, sort_bytes, keys.as<float>() + static_cast<size_t>(a) * n, keys_sorted.as<float>(), ids.as<uint32_t>(), st.list[a],
+                                            static_cast<int>(n), 0, 32, ctx->stream);
+        }
+        if(reference_split) {
+            iotaKernel<<<grid, kBuildBlock, 0, ctx->stream>>>(st.list[3], n);
+        }
+        buildInitKernel<<<grid, kBuildBlock, 0, ctx->stream>>>(st);
+
+        uint32_t levels = 0;
+        for(;;) {
+            if(levels >= max_depth) {
+                cudaStreamSynchronize(ctx->stream);
+                cudaGetLastError();
+                return finish(PTB_OK); // depth stays 0: deeper than the traversal stack allows
+            }
+            cudaMemsetAsync(any_active.ptr, 0, sizeof(uint32_t), ctx->stream);
+            if(reference_split) {
+                refCutKernel<<<grid, kBuildBlock, 0, ctx->stream>>>(st);
+                refGroupKernel<<<grid, kBuildBlock, 0, ctx->stream>>>(st);
+                refChooseKernel<<<grid_plus, kBuildBlock, 0, ctx->stream>>>(st);
+                cub::DeviceScan::ExclusiveSum(temp.ptr, sum_bytes, st.flags, st.ranks, static_cast<int>(n + 1U), ctx->stream);
+                refPartitionKernel<<<grid, kBuildBlock, 0, ctx->stream>>>(st);
+            }
+            else {
+                sweepFillKernel<<<grid3, kBuildBlock, 0, ctx->stream>>>(st, seq_a.as<SweepBox>());
+                cub::DeviceScan::InclusiveScan(temp.ptr, sweep_bytes, seq_a.as<SweepBox>(), seq_b.as<SweepBox>(), SweepMerge{}, static_cast<int>(6 * static_cast<size_t>(n)), ctx->stream);
+                sweepCostKernel<<<grid3, kBuildBlock, 0, ctx->stream>>>(st, seq_b.as<SweepBox>(), costs.as<float>());
+                sweepPickKernel<<<grid3, kBuildBlock, 0, ctx->stream>>>(st, costs.as<float>());
+                sweepSideKernel<<<grid3, kBuildBlock, 0, ctx->stream>>>(st);
+            }
+            sideFlagsKernel<<<grid3_plus, kBuildBlock, 0, ctx->stream>>>(st);
+            cub::DeviceScan::ExclusiveSum(temp.ptr, sum_bytes, st.flags, st.ranks, scan_items, ctx->stream);
+            listPartitionKernel<<<grid3, kBuildBlock, 0, ctx->stream>>>(st, reference_split ? 0 : 1);
+            uint32_t more = 0;
+            if(cudaMemcpyAsync(&more, any_active.ptr, sizeof(more), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+               cudaGetLastError() != cudaSuccess) {
+                cudaGetLastError();
+                return finish(fail(PTB_ERR_CUDA, "buildTreeOnDevice: a level of the build failed"));
+            }
+            for(int a = 0; a < n_lists; a++) {
+                std::swap(st.list[a], st.list_next[a]);
+            }
+            std::swap(st.node_of_pos, st.node_of_pos_next);
+            levels++;
+            if(more == 0U) {
+                break;
+            }
+        }
+
+        LbvhWorkspace w{};
+        w.boxes = d_boxes;
+        w.slots = reference_split ? nullptr : st.list[0];
+        w.box_ids = reference_split ? st.list[3] : nullptr;
+        w.leaf_parent = st.leaf_parent;
+        w.node_parent = st.node_parent;
+        w.children = st.children;
+        w.arrivals = arrivals.as<uint32_t>();
+        w.node_box = node_box.as<float>();
+        w.node_height = node_height.as<uint32_t>();
+        w.node_count = node_count.as<uint32_t>();
+        w.records = records.as<float4>();
+        w.n = n;
+        cudaMemsetAsync(arrivals.ptr, 0, inner * sizeof(uint32_t), ctx->stream);
+        cudaMemsetAsync(d_height.ptr, 0, sizeof(uint32_t), ctx->stream);
+        fitKernel<<<grid, kBuildBlock, 0, ctx->stream>>>(w, d_height.as<uint32_t>());
+        if(order_out != nullptr) {
+            cudaMemcpyAsync(order_out->ptr, st.list[3], static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
+        }
+        cudaEventRecord(stop, ctx->stream);
+        uint32_t height = 0;
+        if(cudaMemcpyAsync(&height, d_height.ptr, sizeof(height), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+           cudaMemcpyAsync(root_box, node_box.ptr, 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+           cudaGetLastError() != cudaSuccess) {
+            cudaGetLastError();
+            return finish(fail(PTB_ERR_CUDA, "buildTreeOnDevice: box fit failed"));
+        }
+        float ms = 0.0F;
+        cudaEventElapsedTime(&ms, start, stop);
+        device_ms = ms;
+        depth = height + 1U;
         return finish(PTB_OK);
     }
 
@@ -893,7 +1143,7 @@ int ptb_context_destroy(ptb_context *ctx) {
     if(ctx->stream != nullptr) {
         cudaStreamSynchronize(ctx->stream);
     }
-    for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->redo_queue, &ctx->counters, &ctx->visits, &ctx->work_cursor, &ctx->samples, &ctx->pixel_list, &ctx->pixel_states, &ctx->active_lists, &ctx->adaptive_counters,
+    for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->redo_queue, &ctx->counters, &ctx->visits, &ctx->work_cursor, &ctx->samples, &ctx->pixel_list, &ctx->pixel_states, &ctx->active_lists, &ctx->adaptive_counters, &ctx->build_arena,
                      &ctx->io_a, &ctx->io_b, &ctx->io_c, &ctx->io_d, &ctx->multi_image, &ctx->multi_staging, &ctx->sort_keys, &ctx->sort_ids, &ctx->sort_temp}) {
         b->release();
     }
@@ -986,45 +1236,232 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
 
     const double t0 = nowSeconds();
     const int threads = static_cast<int>(envLong("PTB_BUILD_THREADS", 0));
-    FlatBvh bvh = buildReferenceBvh(desc->prims, desc->n_prims, threads);
-    if(bvh.depth > static_cast<uint32_t>(kStackCapacity)) {
-        return fail(PTB_ERR_UNSUPPORTED, "ptb_scene_create: BVH deeper than the traversal stack (" + std::to_string(bvh.depth) + ")");
+    const uint64_t n = desc->n_prims;
+    // Scene setup runs on the device (gpu_build.cuh): bounding boxes, the reference-topology tree, the leaf-order geometry
+    // and shading records, and the query tree.  PTB_DEVICE_BUILD=0 (and scenes of fewer than two primitives) take the
+    // host builders of bvh_build.cpp, which produce the same parity tree bit for bit.
+    const bool device_build = n >= 2 && envLong("PTB_DEVICE_BUILD", 1) != 0;
+    const bool want_query_tree = n > 1 && envLong("PTB_OCCLUSION_BVH", 1) != 0;
+    // query tree: "sweep" full-sweep SAH on the device (default with the device build), "lbvh" Morton-order linear BVH on
+    // the device, "host" binned SAH on the host (default with the host build)
+    const char *query_env = std::getenv("PTB_QUERY_TREE");
+    std::string query_kind = query_env != nullptr ? query_env : "";
+    if(desc->bvh_mode == PTB_BVH_REFERENCE_GPU_QUERY_TREE || envLong("PTB_GPU_BVH", 0) != 0) {
+        query_kind = "lbvh";
+    }
+    if(query_kind != "sweep" && query_kind != "lbvh" && query_kind != "host") {
+        query_kind = device_build ? "sweep" : "host";
     }
 
-    const uint64_t n = desc->n_prims;
-    std::vector<float4> geom(kGeomLanes * n, make_float4(0.0F, 0.0F, 0.0F, 0.0F));
-    std::vector<float4> shade(3 * n);
-    for(uint64_t slot = 0; slot < n; slot++) {
-        const ptb_prim &prim = desc->prims[bvh.slot_to_prim[slot]];
-        const float *p = prim.p;
-        uint32_t flags = prim.kind & kKindMask;
-        if(prim.kind == PTB_PRIM_TRIANGLE && prim.cull_backface != 0U) {
-            flags |= kCullBit;
+    auto *scene = new(std::nothrow) ptb_scene();
+    if(scene == nullptr) {
+        return fail(PTB_ERR_OUT_OF_MEMORY, "ptb_scene_create: host allocation failed");
+    }
+    scene->ctx = ctx;
+    auto abandon = [&](int st) {
+        ptb_scene_destroy(scene);
+        return st;
+    };
+    auto upload = [&](Buffer &buffer, const void *src, size_t bytes) -> int {
+        int st = buffer.reserve(std::max<size_t>(bytes, 16));
+        if(st != PTB_OK) {
+            return st;
         }
-        float4 *g = &geom[kGeomLanes * slot];
-        float4 *s = &shade[3 * slot];
-        if(prim.kind == PTB_PRIM_TRIANGLE) {
-            // edges are differenced on the host exactly as Triangle::getIntersection does per call (object.cpp:149-150)
-            g[0] = make_float4(p[0], p[1], p[2], 0.0F);
-            g[1] = make_float4(p[3] - p[0], p[4] - p[1], p[5] - p[2], 0.0F);
-            g[2] = make_float4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0F);
-            s[0] = make_float4(p[9], p[10], p[11], 0.0F);
-            s[1] = make_float4(p[12], p[13], p[14], 0.0F);
-            s[2] = make_float4(p[15], p[16], p[17], 0.0F);
+        if(bytes > 0) {
+            PTB_CUDA(cudaMemcpyAsync(buffer.ptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            PTB_CUDA(cudaStreamSynchronize(ctx->stream));
         }
-        else if(prim.kind == PTB_PRIM_SPHERE) {
-            g[0] = make_float4(p[0], p[1], p[2], 0.0F);
-            g[1] = make_float4(p[3], p[3] * p[3], 0.0F, 0.0F);
-            g[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
-            s[0] = s[1] = s[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+        return PTB_OK;
+    };
+
+    const bool log_build = envLong("PTB_LOG_BUILD", 0) != 0;
+    double t_mark = t0;
+    auto mark = [&](const char *what) {
+        if(log_build) {
+            const double now = nowSeconds();
+            std::fprintf(stderr, "[ptb] scene setup: %-34s %8.2f ms\n", what, (now - t_mark) * 1e3);
+            t_mark = now;
+        }
+    };
+    FlatBvh bvh; // host path: the whole tree; device path: slot_to_prim, root, depth (the records stay on the device)
+    size_t n_inner_nodes = 0;
+    Buffer boxes_by_slot; // 6 floats per leaf slot, on the device: input of the device-side query-tree builders
+    bool query_tree_on_device = false;
+    int32_t query_root_ref = -1;
+    double query_tree_device_ms = 0.0;
+    double reference_tree_device_ms = 0.0;
+    double upload_seconds = 0.0;
+
+    if(device_build) {
+        Buffer d_prims, boxes_by_prim;
+        auto cleanup = [&](int st) {
+            d_prims.release();
+            boxes_by_prim.release();
+            boxes_by_slot.release();
+            return st != PTB_OK ? abandon(st) : st;
+        };
+        const double tu = nowSeconds();
+        if((status = upload(d_prims, desc->prims, n * sizeof(ptb_prim))) != PTB_OK) {
+            return cleanup(status);
+        }
+        upload_seconds += nowSeconds() - tu;
+        mark("upload of the primitives");
+        const uint32_t n32 = static_cast<uint32_t>(n);
+        const unsigned grid = (n32 + kBuildBlock - 1U) / kBuildBlock;
+        if((status = boxes_by_prim.reserve(6 * n * sizeof(float))) != PTB_OK || (status = boxes_by_slot.reserve(6 * n * sizeof(float))) != PTB_OK ||
+           (status = scene->geom.reserve(kGeomLanes * n * sizeof(float4))) != PTB_OK || (status = scene->shade.reserve(3 * n * sizeof(float4))) != PTB_OK) {
+            return cleanup(status);
+        }
+        {
+            // one arena for both tree builds (growing it between them would free and re-allocate a few hundred MB)
+            size_t for_reference = 0;
+            size_t for_query = 0;
+            uint32_t unused_depth = 0;
+            double unused_ms = 0.0;
+            float unused_box[6];
+            Buffer unused;
+            buildTreeOnDevice(ctx, nullptr, n32, true, 0U, unused, nullptr, unused_depth, unused_box, unused_ms, &for_reference);
+            if(want_query_tree && query_kind == "sweep") {
+                buildTreeOnDevice(ctx, nullptr, n32, false, 0U, unused, nullptr, unused_depth, unused_box, unused_ms, &for_query);
+            }
+            if((status = ctx->build_arena.reserve(std::max(for_reference, for_query))) != PTB_OK) {
+                return cleanup(status);
+            }
+        }
+        primBoundsKernel<<<grid, kBuildBlock, 0, ctx->stream>>>(d_prims.as<ptb_prim>(), n32, boxes_by_prim.as<float>());
+        float root_box[6] = {};
+        // depth limit: the traversal stack holds one deferred sibling per level
+        status = buildTreeOnDevice(ctx, boxes_by_prim.as<float>(), n32, true, static_cast<uint32_t>(kStackCapacity), scene->nodes, &scene->slot_to_prim, bvh.depth, root_box,
+                                   reference_tree_device_ms);
+        if(status != PTB_OK) {
+            return cleanup(status);
+        }
+        if(bvh.depth == 0U) {
+            return cleanup(fail(PTB_ERR_UNSUPPORTED, "ptb_scene_create: BVH deeper than the traversal stack"));
+        }
+        mark("boxes + reference-topology tree");
+        packSlotsKernel<<<grid, kBuildBlock, 0, ctx->stream>>>(d_prims.as<ptb_prim>(), scene->slot_to_prim.as<uint32_t>(), boxes_by_prim.as<float>(), n32, scene->geom.as<float4>(),
+                                                              scene->shade.as<float4>(), boxes_by_slot.as<float>());
+        bvh.slot_to_prim.resize(n);
+        if(cudaMemcpyAsync(bvh.slot_to_prim.data(), scene->slot_to_prim.ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+           cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            cudaGetLastError();
+            return cleanup(fail(PTB_ERR_CUDA, "ptb_scene_create: packing the leaf records failed"));
+        }
+        bvh.root_ref = 0;
+        for(int c = 0; c < 3; c++) {
+            bvh.root_low[c] = root_box[c];
+            bvh.root_high[c] = root_box[3 + c];
+        }
+        n_inner_nodes = n - 1;
+        d_prims.release();
+        boxes_by_prim.release();
+        mark("leaf records + slot table");
+    }
+    else {
+        bvh = buildReferenceBvh(desc->prims, desc->n_prims, threads);
+        if(bvh.depth > static_cast<uint32_t>(kStackCapacity)) {
+            return abandon(fail(PTB_ERR_UNSUPPORTED, "ptb_scene_create: BVH deeper than the traversal stack (" + std::to_string(bvh.depth) + ")"));
+        }
+        n_inner_nodes = bvh.nodes.size();
+
+        std::vector<float4> geom(kGeomLanes * n, make_float4(0.0F, 0.0F, 0.0F, 0.0F));
+        std::vector<float4> shade(3 * n);
+        for(uint64_t slot = 0; slot < n; slot++) {
+            const ptb_prim &prim = desc->prims[bvh.slot_to_prim[slot]];
+            const float *p = prim.p;
+            uint32_t flags = prim.kind & kKindMask;
+            if(prim.kind == PTB_PRIM_TRIANGLE && prim.cull_backface != 0U) {
+                flags |= kCullBit;
+            }
+            float4 *g = &geom[kGeomLanes * slot];
+            float4 *s = &shade[3 * slot];
+            if(prim.kind == PTB_PRIM_TRIANGLE) {
+                // edges are differenced on the host exactly as Triangle::getIntersection does per call (object.cpp:149-150)
+                g[0] = make_float4(p[0], p[1], p[2], 0.0F);
+                g[1] = make_float4(p[3] - p[0], p[4] - p[1], p[5] - p[2], 0.0F);
+                g[2] = make_float4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0F);
+                s[0] = make_float4(p[9], p[10], p[11], 0.0F);
+                s[1] = make_float4(p[12], p[13], p[14], 0.0F);
+                s[2] = make_float4(p[15], p[16], p[17], 0.0F);
+            }
+            else if(prim.kind == PTB_PRIM_SPHERE) {
+                g[0] = make_float4(p[0], p[1], p[2], 0.0F);
+                g[1] = make_float4(p[3], p[3] * p[3], 0.0F, 0.0F);
+                g[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+                s[0] = s[1] = s[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+            }
+            else {
+                g[0] = g[1] = g[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+                s[0] = s[1] = s[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+            }
+            std::memcpy(&g[0].w, &flags, sizeof(flags));
+            std::memcpy(&s[0].w, &prim.material, sizeof(uint32_t));
+        }
+        const double tu = nowSeconds();
+        status = upload(scene->nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(NodeRecord));
+        status = status != PTB_OK ? status : upload(scene->geom, geom.data(), geom.size() * sizeof(float4));
+        status = status != PTB_OK ? status : upload(scene->shade, shade.data(), shade.size() * sizeof(float4));
+        status = status != PTB_OK ? status : upload(scene->slot_to_prim, bvh.slot_to_prim.data(), bvh.slot_to_prim.size() * sizeof(uint32_t));
+        if(status == PTB_OK && want_query_tree && query_kind != "host") {
+            std::vector<float> boxes(6 * n);
+            for(uint64_t slot = 0; slot < n; slot++) {
+                primBounds(desc->prims[bvh.slot_to_prim[slot]], &boxes[6 * slot], &boxes[6 * slot + 3]);
+            }
+            status = upload(boxes_by_slot, boxes.data(), boxes.size() * sizeof(float));
+        }
+        upload_seconds += nowSeconds() - tu;
+        if(status != PTB_OK) {
+            boxes_by_slot.release();
+            return abandon(status);
+        }
+    }
+
+    // query hierarchy for any-hit and certified closest-hit queries over the same primitives, leaf refs in reference slots
+    if(want_query_tree && query_kind != "host") {
+        uint32_t levels = 0;
+        if(query_kind == "lbvh") {
+            status = buildQueryBvhOnDevice(ctx, boxes_by_slot.as<float>(), static_cast<uint32_t>(n), bvh.root_low, bvh.root_high, scene->occ_nodes, levels, query_tree_device_ms);
         }
         else {
-            g[0] = g[1] = g[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
-            s[0] = s[1] = s[2] = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+            float unused_root[6];
+            uint32_t depth = 0;
+            status = buildTreeOnDevice(ctx, boxes_by_slot.as<float>(), static_cast<uint32_t>(n), false, static_cast<uint32_t>(kStackCapacity), scene->occ_nodes, nullptr, depth,
+                                       unused_root, query_tree_device_ms);
+            levels = depth > 0U ? depth - 1U : 0U;
         }
-        std::memcpy(&g[0].w, &flags, sizeof(flags));
-        std::memcpy(&s[0].w, &prim.material, sizeof(uint32_t));
+        if(status != PTB_OK) {
+            boxes_by_slot.release();
+            return abandon(status);
+        }
+        // many coincident centres can chain into a tree deeper than the traversal stack: then the host builder takes over
+        query_tree_on_device = levels >= 1U && levels <= static_cast<uint32_t>(kStackCapacity);
+        if(query_tree_on_device) {
+            query_root_ref = 0;
+        }
+        else {
+            scene->occ_nodes.release();
+        }
     }
+    boxes_by_slot.release();
+    mark("query tree (device)");
+    if(want_query_tree && !query_tree_on_device) {
+        std::vector<uint32_t> prim_to_slot(n);
+        for(uint64_t slot = 0; slot < n; slot++) {
+            prim_to_slot[bvh.slot_to_prim[slot]] = static_cast<uint32_t>(slot);
+        }
+        FlatBvh occlusion = buildOcclusionBvh(desc->prims, n, prim_to_slot.data(), threads);
+        if(occlusion.depth <= static_cast<uint32_t>(kStackCapacity) && !occlusion.nodes.empty()) { // else (pathological input) keep using the reference tree
+            const double tu = nowSeconds();
+            if((status = upload(scene->occ_nodes, occlusion.nodes.data(), occlusion.nodes.size() * sizeof(NodeRecord))) != PTB_OK) {
+                return abandon(status);
+            }
+            upload_seconds += nowSeconds() - tu;
+            query_root_ref = occlusion.root_ref;
+        }
+    }
+    const bool have_query_tree = scene->occ_nodes.ptr != nullptr && (query_tree_on_device || query_root_ref != -1);
+    mark("query tree (host)");
 
     std::vector<float4> mats(3 * static_cast<size_t>(desc->n_materials));
     for(uint32_t i = 0; i < desc->n_materials; i++) {
@@ -1070,78 +1507,22 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
         emis[3 * i + 1] = e1;
         emis[3 * i + 2] = e2;
     }
-    // query hierarchy for any-hit and certified closest-hit queries over the same primitives, leaf refs in reference
-    // slots: linear BVH built on the device, or (default) binned SAH built on the host
-    const bool want_query_tree = n > 1 && envLong("PTB_OCCLUSION_BVH", 1) != 0;
-    const bool gpu_query_tree = want_query_tree && (desc->bvh_mode == PTB_BVH_REFERENCE_GPU_QUERY_TREE || envLong("PTB_GPU_BVH", 0) != 0);
-    auto *scene = new(std::nothrow) ptb_scene();
-    if(scene == nullptr) {
-        return fail(PTB_ERR_OUT_OF_MEMORY, "ptb_scene_create: host allocation failed");
-    }
-    scene->ctx = ctx;
-    bool query_tree_on_device = false;
-    double query_tree_device_ms = 0.0;
-    if(gpu_query_tree) {
-        std::vector<float> boxes(6 * n);
-        for(uint64_t slot = 0; slot < n; slot++) {
-            primBounds(desc->prims[bvh.slot_to_prim[slot]], &boxes[6 * slot], &boxes[6 * slot + 3]);
-        }
-        uint32_t height = 0;
-        status = buildQueryBvhOnDevice(ctx, boxes, static_cast<uint32_t>(n), bvh.root_low, bvh.root_high, scene->occ_nodes, height, query_tree_device_ms);
-        if(status != PTB_OK) {
-            ptb_scene_destroy(scene);
-            return status;
-        }
-        // Morton ties can chain into a very deep tree (many coincident centres): then the host builder takes over
-        query_tree_on_device = height >= 1 && height <= static_cast<uint32_t>(kStackCapacity);
-        if(!query_tree_on_device) {
-            scene->occ_nodes.release();
-        }
-    }
-    FlatBvh occlusion;
-    if(want_query_tree && !query_tree_on_device) {
-        std::vector<uint32_t> prim_to_slot(n);
-        for(uint64_t slot = 0; slot < n; slot++) {
-            prim_to_slot[bvh.slot_to_prim[slot]] = static_cast<uint32_t>(slot);
-        }
-        occlusion = buildOcclusionBvh(desc->prims, n, prim_to_slot.data(), threads);
-        if(occlusion.depth > static_cast<uint32_t>(kStackCapacity)) {
-            occlusion = FlatBvh{}; // pathological input: keep using the reference tree
-        }
-    }
     const double t1 = nowSeconds();
+    mark("materials, lights, emissive table");
 
-    auto upload = [&](Buffer &buffer, const void *src, size_t bytes) -> int {
-        int st = buffer.reserve(std::max<size_t>(bytes, 16));
-        if(st != PTB_OK) {
-            return st;
-        }
-        if(bytes > 0) {
-            PTB_CUDA(cudaMemcpy(buffer.ptr, src, bytes, cudaMemcpyHostToDevice));
-        }
-        return PTB_OK;
-    };
-    status = upload(scene->nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(NodeRecord));
-    if(status == PTB_OK && !occlusion.nodes.empty()) {
-        status = upload(scene->occ_nodes, occlusion.nodes.data(), occlusion.nodes.size() * sizeof(NodeRecord));
-    }
-    status = status != PTB_OK ? status : upload(scene->geom, geom.data(), geom.size() * sizeof(float4));
-    status = status != PTB_OK ? status : upload(scene->shade, shade.data(), shade.size() * sizeof(float4));
-    status = status != PTB_OK ? status : upload(scene->mats, mats.data(), mats.size() * sizeof(float4));
+    status = upload(scene->mats, mats.data(), mats.size() * sizeof(float4));
     status = status != PTB_OK ? status : upload(scene->lights, lights.data(), lights.size() * sizeof(float4));
     status = status != PTB_OK ? status : upload(scene->emis, emis.data(), emis.size() * sizeof(float4));
     status = status != PTB_OK ? status : upload(scene->cdf, emissive.cdf.data(), emissive.cdf.size() * sizeof(float));
-    status = status != PTB_OK ? status : upload(scene->slot_to_prim, bvh.slot_to_prim.data(), bvh.slot_to_prim.size() * sizeof(uint32_t));
     if(status != PTB_OK) {
-        ptb_scene_destroy(scene);
-        return status;
+        return abandon(status);
     }
     const double t2 = nowSeconds();
 
     DeviceScene &d = scene->dev;
     d.nodes = scene->nodes.as<float4>();
-    d.occ_nodes = (query_tree_on_device || !occlusion.nodes.empty()) ? scene->occ_nodes.as<float4>() : nullptr;
-    d.occ_root_ref = query_tree_on_device ? 0 : occlusion.root_ref;
+    d.occ_nodes = have_query_tree ? scene->occ_nodes.as<float4>() : nullptr;
+    d.occ_root_ref = query_root_ref;
     d.geom = scene->geom.as<float4>();
     d.shade = scene->shade.as<float4>();
     d.mats = scene->mats.as<float4>();
@@ -1160,22 +1541,27 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
     }
 
     scene->shadow_stride = std::max<uint32_t>(1U, desc->n_lights + emissive.object_sample_count);
+    mark("upload of the small tables");
     ptb_guard::buildCertGuard(desc->prims, desc->n_prims, &scene->guard);
+    mark("guard table of the certified walk");
 
     ptb_scene_info &info = scene->info;
     info.n_prims = n;
-    info.n_inner_nodes = bvh.nodes.size();
+    info.n_inner_nodes = n_inner_nodes;
     info.bvh_depth = bvh.depth;
     info.n_emissive = d.n_emissive;
     info.object_sample_count = d.object_sample_count;
     info.n_lights = desc->n_lights;
     info.device_bytes = scene->nodes.bytes + scene->occ_nodes.bytes + scene->geom.bytes + scene->shade.bytes + scene->mats.bytes + scene->lights.bytes + scene->emis.bytes +
                         scene->cdf.bytes + scene->slot_to_prim.bytes;
-    info.build_seconds = t1 - t0;
+    info.build_seconds = (t1 - t0) - upload_seconds;
     info.query_tree_on_device = query_tree_on_device ? 1U : 0U;
     info.certifiable = scene->guard.certifiable;
     info.query_tree_device_ms = query_tree_device_ms;
-    info.upload_seconds = t2 - t1;
+    info.upload_seconds = (t2 - t1) + upload_seconds;
+    info.built_on_device = device_build ? 1U : 0U;
+    info.query_tree_kind = !have_query_tree ? 0U : (!query_tree_on_device ? 1U : (query_kind == "lbvh" ? 2U : 3U));
+    info.reference_tree_device_ms = reference_tree_device_ms;
     for(int c = 0; c < 3; c++) {
         info.root_low[c] = bvh.root_low[c];
         info.root_high[c] = bvh.root_high[c];
@@ -1197,6 +1583,39 @@ int ptb_scene_destroy(ptb_scene *scene) {
         b->release();
     }
     delete scene;
+    return PTB_OK;
+}
+
+int ptb_scene_read(const ptb_scene *scene, uint32_t array, void *out, uint64_t bytes) {
+    if(scene == nullptr || (bytes > 0 && out == nullptr)) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_scene_read: null argument");
+    }
+    const Buffer *source = nullptr;
+    size_t valid = 0; // buffers may be larger than the array they hold
+    const size_t n = scene->dev.n_prims;
+    const size_t inner = n > 0 ? n - 1 : 0;
+    switch(array) {
+        case PTB_SCENE_NODES: source = &scene->nodes; valid = inner * sizeof(NodeRecord); break;
+        case PTB_SCENE_QUERY_NODES: source = &scene->occ_nodes; valid = scene->dev.occ_nodes != nullptr ? inner * sizeof(NodeRecord) : 0; break;
+        case PTB_SCENE_GEOM: source = &scene->geom; valid = kGeomLanes * n * sizeof(float4); break;
+        case PTB_SCENE_SHADE: source = &scene->shade; valid = 3 * n * sizeof(float4); break;
+        case PTB_SCENE_SLOT_TO_PRIM: source = &scene->slot_to_prim; valid = n * sizeof(uint32_t); break;
+        default: return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_scene_read: unknown array");
+    }
+    if(bytes > valid) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_scene_read: more bytes requested than the array holds");
+    }
+    if(bytes == 0) {
+        return PTB_OK;
+    }
+    ptb_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mutex);
+    int status = useDevice(ctx);
+    if(status != PTB_OK) {
+        return status;
+    }
+    PTB_CUDA(cudaMemcpyAsync(out, source->ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(cudaStreamSynchronize(ctx->stream));
     return PTB_OK;
 }
 

@@ -133,6 +133,10 @@ typedef struct ptb_scene_info {
     uint32_t certifiable;          /* 1: the guard table of the certified walk covers every large triangle / sphere of the  */
                                    /* scene (csrc/cert_guard.h); 0: guarded certified queries walk the reference tree        */
     double query_tree_device_ms;   /* CUDA-event time of that build (Morton codes, sort, hierarchy, box fit) */
+    uint32_t built_on_device;      /* 1: boxes, the reference-topology tree (impl::constructBVH, scene.cpp:12-102) and the leaf  */
+                                   /* records were built by the GPU (csrc/gpu_build.cuh); 0: by the host builders                 */
+    uint32_t query_tree_kind;      /* 0 none, 1 host binned SAH, 2 device linear BVH, 3 device full-sweep SAH (default)          */
+    double reference_tree_device_ms; /* CUDA-event time of the device build of the reference-topology tree                       */
 } ptb_scene_info;
 
 /* ------------------------------------------------------------------------------------------------ camera POD */
@@ -256,6 +260,19 @@ int ptb_context_synchronize(ptb_context *ctx);
 int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **out);
 int ptb_scene_destroy(ptb_scene *scene);
 int ptb_scene_get_info(const ptb_scene *scene, ptb_scene_info *out);
+
+/* Copies one of the scene's device arrays to the host (inspection, tests, serialisation): `bytes` must not exceed the
+ * array's size.  PTB_SCENE_NODES / PTB_SCENE_QUERY_NODES: 64-byte inner records (csrc/bvh_build.h: left box, right box,
+ * left ref, right ref, leaf count, parent; ref >= 0 inner record, < 0 ~leaf slot); PTB_SCENE_GEOM: 64 bytes per leaf slot;
+ * PTB_SCENE_SHADE: 48 bytes per leaf slot; PTB_SCENE_SLOT_TO_PRIM: uint32 per leaf slot (index into ptb_scene_desc.prims). */
+typedef enum ptb_scene_array {
+    PTB_SCENE_NODES = 0,
+    PTB_SCENE_QUERY_NODES = 1,
+    PTB_SCENE_GEOM = 2,
+    PTB_SCENE_SHADE = 3,
+    PTB_SCENE_SLOT_TO_PRIM = 4
+} ptb_scene_array;
+int ptb_scene_read(const ptb_scene *scene, uint32_t array, void *out, uint64_t bytes);
 
 /* Scene::getIntersection (src/scene/scene.cpp:210-220) for a batch.
  * rays: 6 floats each (origin xyz, unit direction xyz).  t_out[i] < 0 = miss (prim_out[i] = -1), else the

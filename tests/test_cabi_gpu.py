@@ -256,16 +256,19 @@ def test_unit_entries_match_oracle(ctx):
     scene.close()
 
 
-def test_device_built_query_tree_changes_nothing(ctx):
+def test_device_built_query_tree_changes_nothing(ctx, monkeypatch):
     """with PTB_BVH_REFERENCE_GPU_QUERY_TREE the hierarchy walked by any-hit and certified closest-hit
     queries is built on the GPU (Morton sort + Karras hierarchy, csrc/lbvh.cuh).  Results cannot depend on that tree's
     shape: closest hits (a third aimed at shared vertices / edges), visibility and validation-mode samples must be
     bit-identical to the scene with the host-built tree and to the golden vectors of the unmodified reference."""
     for name in ("cornell_mesh", "mixed"):
         g = load_golden("hits", name)
+        monkeypatch.setenv("PTB_QUERY_TREE", "host")
         host = _scene(ctx, g)
+        monkeypatch.delenv("PTB_QUERY_TREE")
         dev = capi.Scene(ctx, g["prims"], g["materials"], g["lights"], bvh_mode=capi.PTB_BVH_REFERENCE_GPU_QUERY_TREE)
         assert dev.info().query_tree_on_device == 1 and host.info().query_tree_on_device == 0
+        assert dev.info().query_tree_kind == 2 and host.info().query_tree_kind == 1
         assert dev.info().query_tree_device_ms > 0
         hit = g["t"] >= 0
         for flags in (0, capi.PTB_FLAG_CERTIFIED_CLOSEST):
@@ -301,6 +304,158 @@ def test_device_built_query_tree_changes_nothing(ctx):
     assert np.array_equal(prim_d, prim) and np.array_equal(t_d[t >= 0], t[t >= 0])
     host.close()
     dev.close()
+
+
+def _build_cases():
+    """Primitive sets for builder parity: the golden scenes, many coincident boxes, ties in every coordinate (a regular
+    grid), a random soup and degenerate sizes."""
+    cases = []
+    for name in GOLDEN_SCENES:
+        g = load_golden("samples", name)
+        cases.append((name, g["prims"], g["materials"], g["lights"]))
+    g = load_golden("samples", "cornell_mesh")
+    cases.append(("300 copies", np.repeat(g["prims"][:1], 300), g["materials"], g["lights"]))
+    cases.append(("two", g["prims"][:2], g["materials"], g["lights"]))
+    cases.append(("three", g["prims"][:3], g["materials"], g["lights"]))
+    verts, normals = scenes.standin_triangles(64, 40, scenes.DEMO_DRAGON_TRANSFORM)
+    mesh = np.zeros(len(verts), capi.PRIM_DTYPE)
+    mesh["kind"] = capi.PTB_PRIM_TRIANGLE
+    mesh["p"][:, :9] = verts
+    mesh["p"][:, 9:18] = normals
+    cases.append(("5120-triangle mesh + golden scene", np.concatenate([g["prims"], mesh]), g["materials"], g["lights"]))
+    soup = np.zeros(60000, capi.PRIM_DTYPE)
+    soup["kind"] = capi.PTB_PRIM_TRIANGLE
+    soup["p"][:, :9] = scenes.soup_triangles(60000, 5)
+    soup["p"][:, 11] = soup["p"][:, 14] = soup["p"][:, 17] = 1.0
+    cases.append(("soup 60k", soup, g["materials"], g["lights"]))
+    # a regular grid of equal triangles: every lower corner repeats many times in each axis (the `<=` partition sends
+    # all ties left and the rebalancing moves the tail back)
+    grid = np.zeros(12 * 12 * 12, capi.PRIM_DTYPE)
+    at = 0
+    for ix in range(12):
+        for iy in range(12):
+            for iz in range(12):
+                o = np.array([ix, iy, iz], np.float32) * 0.25
+                grid[at]["kind"] = capi.PTB_PRIM_TRIANGLE
+                grid[at]["p"][:9] = np.concatenate([o, o + np.float32([0.2, 0, 0]), o + np.float32([0, 0.2, 0.1])])
+                grid[at]["p"][9:18] = np.tile(np.float32([0, 0, 1]), 3)
+                at += 1
+    cases.append(("tie grid", grid, g["materials"], g["lights"]))
+    return cases
+
+
+def test_device_built_scene_equals_the_host_built_scene(ctx, monkeypatch):
+    """Scene setup on the GPU (csrc/gpu_build.cuh: level-synchronous restatement of impl::constructBVH, scene.cpp:12-102)
+    produces the parity tree of the host builder bit for bit: the same leaf order, the same 64-byte records, the same
+    geometry and shading records."""
+    for name, prims, mats, lights in _build_cases():
+        monkeypatch.setenv("PTB_DEVICE_BUILD", "0")
+        host = capi.Scene(ctx, prims, mats, lights)
+        monkeypatch.setenv("PTB_DEVICE_BUILD", "1")
+        dev = capi.Scene(ctx, prims, mats, lights)
+        assert host.info().built_on_device == 0 and dev.info().built_on_device == 1, name
+        assert np.array_equal(dev.read_slot_to_prim(), host.read_slot_to_prim()), name
+        a, b = dev.read_nodes(), host.read_nodes()
+        for field in ("left", "right", "leaf_count", "parent"):
+            assert np.array_equal(a[field], b[field]), (name, field)
+        for field in ("left_lo", "left_hi", "right_lo", "right_hi"):
+            assert np.array_equal(a[field].view(np.uint32), b[field].view(np.uint32)), (name, field)
+        assert np.array_equal(dev.read_geom().view(np.uint32), host.read_geom().view(np.uint32)), name
+        assert np.array_equal(dev.read_shade().view(np.uint32), host.read_shade().view(np.uint32)), name
+        hi, di = host.info(), dev.info()
+        assert (hi.bvh_depth, hi.n_inner_nodes, list(hi.root_low), list(hi.root_high)) == (di.bvh_depth, di.n_inner_nodes, list(di.root_low), list(di.root_high)), name
+        host.close()
+        dev.close()
+
+
+def _prim_boxes(prims):
+    """Object::getBoundingVolume in float32 (object.cpp:60-62, 90-93, 184-186): [n, 6] = lo xyz, hi xyz."""
+    p = prims["p"]
+    tri = p[:, :9].reshape(-1, 3, 3)
+    boxes = np.concatenate([tri.min(axis=1), tri.max(axis=1)], axis=1).astype(np.float32)
+    sphere = prims["kind"] == capi.PTB_PRIM_SPHERE
+    boxes[sphere, :3] = p[sphere, :3] - p[sphere, 3:4]
+    boxes[sphere, 3:] = p[sphere, :3] + p[sphere, 3:4]
+    boxes[prims["kind"] == capi.PTB_PRIM_NULL] = 0.0
+    return boxes
+
+
+def _check_query_tree(nodes, slot_lo, slot_hi):
+    """Structural validity of a query tree: a binary tree over all leaf slots, every box the exact union of its children."""
+    n = len(slot_lo)
+    assert len(nodes) == n - 1
+    seen_leaf = np.zeros(n, bool)
+    seen_inner = np.zeros(n - 1, bool)
+    seen_inner[0] = True
+    lo = np.zeros((n - 1, 3), np.float32)
+    hi = np.zeros((n - 1, 3), np.float32)
+    count = np.zeros(n - 1, np.int64)
+    # children come after... not necessarily in index order for every builder: iterate by an explicit stack, post-order
+    order = []
+    stack = [0]
+    while stack:
+        i = stack.pop()
+        order.append(i)
+        for side in ("left", "right"):
+            ref = int(nodes[side][i])
+            if ref >= 0:
+                assert not seen_inner[ref]
+                seen_inner[ref] = True
+                assert nodes["parent"][ref] == i
+                stack.append(ref)
+            else:
+                assert not seen_leaf[~ref]
+                seen_leaf[~ref] = True
+    assert seen_leaf.all() and seen_inner.all()
+    depth = np.zeros(n - 1, np.int64)
+    for i in reversed(order):
+        boxes = []
+        total = 0
+        below = 0
+        for side in ("left", "right"):
+            ref = int(nodes[side][i])
+            if ref >= 0:
+                boxes.append((lo[ref], hi[ref]))
+                total += count[ref]
+                below = max(below, depth[ref])
+            else:
+                boxes.append((slot_lo[~ref], slot_hi[~ref]))
+                total += 1
+        assert np.array_equal(nodes["left_lo"][i], boxes[0][0]) and np.array_equal(nodes["left_hi"][i], boxes[0][1])
+        assert np.array_equal(nodes["right_lo"][i], boxes[1][0]) and np.array_equal(nodes["right_hi"][i], boxes[1][1])
+        lo[i] = np.minimum(boxes[0][0], boxes[1][0])
+        hi[i] = np.maximum(boxes[0][1], boxes[1][1])
+        count[i] = total
+        depth[i] = below + 1
+        assert nodes["leaf_count"][i] == total
+    return int(depth[0])
+
+
+def test_device_built_query_trees_are_valid_and_change_nothing(ctx, monkeypatch):
+    """The query tree (any-hit and certified closest-hit walks) built on the device by full-sweep SAH is a valid hierarchy
+    over all leaf slots with exact boxes, and -- like every query tree -- cannot change a result."""
+    for name, prims, mats, lights in _build_cases():
+        monkeypatch.setenv("PTB_QUERY_TREE", "host")
+        host = capi.Scene(ctx, prims, mats, lights)
+        rays = random_rays(20000, seed=101, box=2.5)
+        t, prim, _ = host.intersect(rays)
+        for kind, code in (("sweep", 3), ("lbvh", 2)):
+            monkeypatch.setenv("PTB_QUERY_TREE", kind)
+            dev = capi.Scene(ctx, prims, mats, lights)
+            assert dev.info().query_tree_kind == code, (name, kind, dev.info().query_tree_kind)
+            nodes = dev.read_nodes(query_tree=True)
+            geom = dev.read_geom()
+            slot_to_prim = dev.read_slot_to_prim()
+            boxes = _prim_boxes(prims[slot_to_prim])
+            depth = _check_query_tree(nodes, boxes[:, :3], boxes[:, 3:])
+            assert depth <= 64
+            if kind == "sweep" and name == "300 copies":
+                assert depth <= 12  # equal costs everywhere: ties go to the most balanced split
+            t_d, prim_d, _ = dev.intersect(rays, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_CERTIFIED_RELAXED)
+            assert np.array_equal(prim_d, prim) and np.array_equal(t_d[t >= 0], t[t >= 0]), (name, kind)
+            del geom
+            dev.close()
+        host.close()
 
 
 def test_sharded_renders_sum_to_the_full_frame(ctx):
