@@ -435,10 +435,11 @@ def run_b200_arm(args):
     if args.spp >= 16 and not args.no_adaptive_line:
         astats = capi.RenderStats()
         ao = capi.render_opts(args.width, args.height, max(args.spp // 8, 1), args.spp, 1e-3, args.max_depth, capi.PTB_RNG_COUNTER, flags | capi.PTB_FLAG_DEVICE_IO, 97, 0, rank, world)
-        capi.check(lib.ptb_render(handle, C.byref(camera), C.byref(ao), 0, 0, args.width, args.height, C.c_void_p(image.data_ptr()), C.byref(astats)))
+        for _ in range(2):  # the first adaptive frame allocates the parked per-pixel state; the second one is reported
+            capi.check(lib.ptb_render(handle, C.byref(camera), C.byref(ao), 0, 0, args.width, args.height, C.c_void_p(image.data_ptr()), C.byref(astats)))
         adaptive = {"min_spp": max(args.spp // 8, 1), "max_spp": args.spp, "samples_max": int(sharding.owned_pixels(args.width, args.height, rank, world).sum()) * args.spp, "samples_traced": int(astats.samples),
                     "samples_the_reference_loops_consume": int(astats.samples_used), "rounds": int(astats.adaptive_rounds), "frame_ms": astats.device_ms_total,
-                    "note": "this rank's tiles; one untimed frame"}
+                    "fixed_spp_frame_ms": breakdown["frame_ms"], "note": "this rank's tiles; second of two untimed frames; fixed_spp_frame_ms = the profile pass at max_spp"}
     count_rays = sum_over_ranks(float(cstats.closest_rays + cstats.shadow_rays))
     inner_per_ray = sum_over_ranks(float(cstats.inner_visits)) / max(count_rays, 1.0)
     leaf_per_ray = sum_over_ranks(float(cstats.leaf_visits)) / max(count_rays, 1.0)
@@ -496,7 +497,11 @@ def run_b200_arm(args):
     if rank == 0:
         e2e_devices = b200.set_devices(world)
         b200.set_sharding(0, 1, 2999)
-        scene_cpp.process_job(camera_cpp, args.width, args.height, min(args.spp, 8), min(args.spp, 8), 1e-3, 0)  # replicas + workspaces
+        # untimed warm-up of this path: scene replicas on the other GPUs (first call), then one frame at full size so that the
+        # replicas' workspaces (path pool, per-sample buffer) have their final size before the timed steps
+        scene_cpp.process_job(camera_cpp, args.width, args.height, min(args.spp, 8), min(args.spp, 8), 1e-3, 0)
+        if e2e_devices > 1:
+            scene_cpp.process_job(camera_cpp, args.width, args.height, args.spp, args.spp, 1e-3, 0)
     for i in range(args.steps):
         flush.zero_()
         host_barrier()
@@ -541,7 +546,7 @@ def run_b200_arm(args):
         "wall_ms_per_step": float(np.mean(wall_ms)),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": C.sizeof(capi.Camera) + C.sizeof(capi.RenderOpts),
-                "d2h_bytes_per_step": args.width * args.height * 16, "ms_per_step": float(np.mean(e2e_ms)),
+                "d2h_bytes_per_step": args.width * args.height * 16, "ms_per_step": float(np.mean(e2e_ms)), "ms_steps": [round(float(v), 1) for v in e2e_ms],
                 "api": "processJob (C++ host API via harness)" + ("" if world == 1 else f", one call on rank 0 rendering on {e2e_devices} GPUs in-library (ptb_render_multi)")},
         "gpu_launches": int(totals["launches"]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

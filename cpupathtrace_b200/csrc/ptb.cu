@@ -103,6 +103,7 @@ struct ptb_context {
     ptb::VoteParams vote{12, 12, 2, 4};        // closest-hit kernels
     ptb::VoteParams vote_shadow{16, 12, 2, 4}; // any-hit / shadow kernels (shorter rays: refill in larger batches)
     int trace_blocks_per_sm = 16;
+    int shade_blocks_per_sm = PTB_SHADE_MIN_BLOCKS; // grid of the shade kernel = its resident blocks (PTB_SHADE_BLOCKS_PER_SM)
     bool log_iterations = false; // PTB_LOG_ITERATIONS=1: one stderr line per bounce iteration
     bool production_math = true; // PTB_RNG_COUNTER renders use the FMA / SFU build of generate, shade and accumulate (PTB_PRODUCTION_MATH=0: the exact build)
     int iterations_per_sync = 4; // bounce iterations launched between two host synchronisations (PTB_ITERATIONS_PER_SYNC)
@@ -439,6 +440,10 @@ namespace {
                 PTB_CUDA(cudaMemsetAsync(counters + kCountShadow, 0, kPerIterationCounters * sizeof(uint32_t), ctx->stream));
 
                 const int flat_grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_cur) + kFlatBlock - 1) / kFlatBlock, static_cast<uint64_t>(gridFor(ctx, 32 * kBlock / kFlatBlock))));
+                // the shade kernel splits its queue statically between blocks that all run the whole launch: a grid of exactly
+                // the resident blocks (6 per SM at 80 registers) has no last partial wave (32 per SM = 5.33 waves left a third
+                // of the slots empty for the last sixth of every launch)
+                const int shade_grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_cur) + kFlatBlock - 1) / kFlatBlock, static_cast<uint64_t>(gridFor(ctx, ctx->shade_blocks_per_sm))));
                 {
                     LaunchTimer timer(ctx, 0);
                     if(certified) {
@@ -453,13 +458,13 @@ namespace {
                 {
                     LaunchTimer timer(ctx, 1);
                     if(params.rng_xorshift != 0U) {
-                        shadeKernel<ReferenceRng><<<flat_grid, kFlatBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, queue_slot[cur], shadow_queue);
+                        shadeKernel<ReferenceRng><<<shade_grid, kFlatBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, queue_slot[cur], shadow_queue);
                     }
                     else if(ctx->production_math) {
-                        ptb_fast_api::launchShade(&scene->dev, &pool, &params, queues[cur], counters, queue_slot[cur], shadow_queue, flat_grid, ctx->stream);
+                        ptb_fast_api::launchShade(&scene->dev, &pool, &params, queues[cur], counters, queue_slot[cur], shadow_queue, shade_grid, ctx->stream);
                     }
                     else {
-                        shadeKernel<CounterRng><<<flat_grid, kFlatBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, queue_slot[cur], shadow_queue);
+                        shadeKernel<CounterRng><<<shade_grid, kFlatBlock, 0, ctx->stream>>>(scene->dev, pool, params, queues[cur], counters, queue_slot[cur], shadow_queue);
                     }
                 }
                 {
@@ -1126,6 +1131,7 @@ int ptb_context_create(int device, ptb_context **out) {
     ctx->vote_shadow.refill = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_SHADOW_REFILL_VOTE", envLong("PTB_REFILL_VOTE", 16)))));
     ctx->vote_shadow.leaf = static_cast<int>(std::min(32L, std::max(1L, envLong("PTB_SHADOW_LEAF_VOTE", envLong("PTB_LEAF_VOTE", 12)))));
     ctx->trace_blocks_per_sm = static_cast<int>(std::max(1L, envLong("PTB_TRACE_BLOCKS_PER_SM", 16)));
+    ctx->shade_blocks_per_sm = static_cast<int>(std::max(1L, envLong("PTB_SHADE_BLOCKS_PER_SM", PTB_SHADE_MIN_BLOCKS)));
     ctx->log_iterations = envLong("PTB_LOG_ITERATIONS", 0) != 0;
     ctx->production_math = envLong("PTB_PRODUCTION_MATH", 1) != 0;
     ctx->sort_rays = envLong("PTB_SORT_RAYS", 1) != 0;
@@ -1939,7 +1945,8 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
     // Adaptive sampling (min < max, worker.cpp:236-260): samples are traced in rounds and only for the pixels whose loop
     // has not ended.  The first round is as long as the shortest loop the reference can run (the acceptance test needs
     // check_sample_count consecutive passes, the first one no earlier than two full batches and min samples), later rounds
-    // cover an eighth of the remaining range, at least one run of checks.
+    // cover a quarter of the remaining range (PTB_ADAPTIVE_ROUND_DIVISOR; measured on the bench scene, 32..256 / 16..1024 spp:
+    // 2 -> 540 / 3078 ms, 4 -> 562 / 3032, 8 -> 586 / 3182, 16 -> 650 / 3149), at least one run of checks.
     const ResolveConsts rc = resolveConsts(opts->min_sample_count, spp);
     const bool adaptive = ctx->adaptive_rounds && spp > 0 && opts->min_sample_count < spp;
     int first_round = spp;
@@ -1948,7 +1955,8 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
         const int batch = rc.stats_sample_count;
         const int first_check = ((std::max(std::max(rc.min_samples, 2), 2 * batch) + batch - 1) / batch) * batch;
         first_round = std::min(spp, first_check + (std::max(rc.check_sample_count, 1) - 1) * batch);
-        const int eighth = (((spp - first_round) / 8 + batch - 1) / batch) * batch;
+        const int divisor = static_cast<int>(std::min(64L, std::max(1L, envLong("PTB_ADAPTIVE_ROUND_DIVISOR", 4))));
+        const int eighth = (((spp - first_round) / divisor + batch - 1) / batch) * batch;
         later_round = std::max(std::max(eighth, std::max(rc.check_sample_count, 1) * batch), 1);
     }
     const int longest_round = adaptive ? std::max(first_round, std::min(later_round, std::max(spp - first_round, 1))) : std::max(spp, 1);

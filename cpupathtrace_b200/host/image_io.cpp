@@ -126,10 +126,13 @@ namespace io {
         Image<Color<float>> decodePng(std::basic_istream<char> &stream);
     }
 
-    // Reads 8-bit, non-interlaced PNGs of every colour type (what writeRGBImage and common tools produce).  16-bit,
-    // sub-8-bit and Adam7-interlaced files, which the reference reads through libpng's EXPAND | PACKING | STRIP_16
-    // transforms (image_io.cpp:50-107), are rejected with std::logic_error -- like every other failure, including
-    // running out of memory on a hostile header.
+    // Reads every PNG the reference reads through libpng with EXPAND | PACKING | STRIP_16 (image_io.cpp:50-107): all five
+    // colour types, bit depths 1 / 2 / 4 / 8 / 16, non-interlaced and Adam7.  What those transforms leave is an 8-bit image
+    // of 1 (grey), 2 (grey + alpha), 3 (RGB) or 4 (RGBA) channels -- palette entries become RGB(A), a tRNS colour key
+    // becomes an alpha channel, grey samples below 8 bits are scaled to 8, 16-bit samples keep their high byte -- and the
+    // reference then copies 3- and 4-channel rows only (image_io.cpp:63-79): a grey or grey + alpha file yields an image of
+    // zero-initialised pixels.  That behaviour is kept.  Every failure, including running out of memory on a hostile
+    // header, is a std::logic_error.
     Image<Color<float>> readRGBImage(std::basic_istream<char> &stream) noexcept(false) {
         try {
             return decodePng(stream);
@@ -213,92 +216,152 @@ namespace io {
             default:
                 throw std::logic_error("readRGBImage: unsupported colour type");
         }
-        if(width == 0 || height == 0 || width > 65535U || height > 65535U || bit_depth != 8 || interlace != 0) {
-            throw std::logic_error("readRGBImage: only non-interlaced 8-bit images are supported");
+        const bool depth_ok = colour_type == 0   ? (bit_depth == 1 || bit_depth == 2 || bit_depth == 4 || bit_depth == 8 || bit_depth == 16)
+                              : colour_type == 3 ? (bit_depth == 1 || bit_depth == 2 || bit_depth == 4 || bit_depth == 8)
+                                                 : (bit_depth == 8 || bit_depth == 16);
+        if(width == 0 || height == 0 || width > 65535U || height > 65535U || !depth_ok || interlace > 1) {
+            throw std::logic_error("readRGBImage: invalid header");
         }
 
-        const std::size_t stride = static_cast<std::size_t>(width) * channels;
+        // the passes of the image: one for a non-interlaced file, seven for Adam7 (x0, y0, dx, dy per pass)
+        struct Pass {
+            uint32_t x0, y0, dx, dy;
+        };
+        static const Pass kAdam7[7] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+        static const Pass kWhole[1] = {{0, 0, 1, 1}};
+        const Pass *passes = interlace != 0 ? kAdam7 : kWhole;
+        const int n_passes = interlace != 0 ? 7 : 1;
+        const std::size_t bits_per_pixel = static_cast<std::size_t>(channels) * static_cast<std::size_t>(bit_depth);
+        const std::size_t filter_unit = std::max<std::size_t>(bits_per_pixel / 8, 1); // bytes per complete pixel, at least 1
+
+        std::size_t raw_bytes = 0;
+        for(int k = 0; k < n_passes; k++) {
+            const Pass &ps = passes[k];
+            const std::size_t pw = width > ps.x0 ? (width - ps.x0 + ps.dx - 1) / ps.dx : 0;
+            const std::size_t ph = height > ps.y0 ? (height - ps.y0 + ps.dy - 1) / ps.dy : 0;
+            if(pw != 0 && ph != 0) {
+                raw_bytes += ph * (1 + (pw * bits_per_pixel + 7) / 8);
+            }
+        }
         // deflate expands at most ~1032:1: an IHDR that promises more pixels than the IDAT stream can possibly hold is
         // rejected before anything is allocated (a 100-byte file must not trigger a multi-gigabyte allocation)
-        const long double promised = static_cast<long double>(height) * static_cast<long double>(stride + 1);
-        if(promised > 1040.0L * static_cast<long double>(packed.size()) + 1024.0L) {
+        if(static_cast<long double>(raw_bytes) > 1040.0L * static_cast<long double>(packed.size()) + 1024.0L) {
             throw std::logic_error("readRGBImage: image dimensions exceed what the compressed data can hold");
         }
-        std::vector<unsigned char> raw(static_cast<std::size_t>(height) * (stride + 1));
+        std::vector<unsigned char> raw(raw_bytes);
         uLongf raw_size = static_cast<uLongf>(raw.size());
         if(uncompress(raw.data(), &raw_size, packed.data(), static_cast<uLong>(packed.size())) != Z_OK || raw_size != raw.size()) {
             throw std::logic_error("readRGBImage: inflate failed");
         }
 
-        // undo the scanline filters in place
-        std::vector<unsigned char> pixels(static_cast<std::size_t>(height) * stride);
-        for(uint32_t y = 0; y < height; y++) {
-            const unsigned char filter = raw[y * (stride + 1)];
-            const unsigned char *in = &raw[y * (stride + 1) + 1];
-            unsigned char *row = &pixels[y * stride];
-            const unsigned char *above = y > 0 ? &pixels[(y - 1) * stride] : nullptr;
-            for(std::size_t i = 0; i < stride; i++) {
-                const int left = i >= static_cast<std::size_t>(channels) ? row[i - channels] : 0;
-                const int up = above != nullptr ? above[i] : 0;
-                const int up_left = (above != nullptr && i >= static_cast<std::size_t>(channels)) ? above[i - channels] : 0;
-                int predicted = 0;
-                switch(filter) {
-                    case 0:
-                        predicted = 0;
-                        break;
-                    case 1:
-                        predicted = left;
-                        break;
-                    case 2:
-                        predicted = up;
-                        break;
-                    case 3:
-                        predicted = (left + up) / 2;
-                        break;
-                    case 4:
-                        predicted = paeth(left, up, up_left);
-                        break;
-                    default:
-                        throw std::logic_error("readRGBImage: unknown scanline filter");
+        // samples[(y * width + x) * channels + c]: the file's samples, one per element (PACKING: values below 8 bits unscaled)
+        std::vector<uint16_t> samples(static_cast<std::size_t>(width) * height * channels);
+        std::vector<unsigned char> line;
+        std::vector<unsigned char> previous;
+        std::size_t in = 0;
+        for(int k = 0; k < n_passes; k++) {
+            const Pass &ps = passes[k];
+            const std::size_t pw = width > ps.x0 ? (width - ps.x0 + ps.dx - 1) / ps.dx : 0;
+            const std::size_t ph = height > ps.y0 ? (height - ps.y0 + ps.dy - 1) / ps.dy : 0;
+            if(pw == 0 || ph == 0) {
+                continue;
+            }
+            const std::size_t line_bytes = (pw * bits_per_pixel + 7) / 8;
+            line.assign(line_bytes, 0);
+            previous.assign(line_bytes, 0);
+            for(std::size_t row = 0; row < ph; row++) {
+                const unsigned char filter = raw[in++];
+                for(std::size_t i = 0; i < line_bytes; i++) {
+                    const int left = i >= filter_unit ? line[i - filter_unit] : 0;
+                    const int up = previous[i];
+                    const int up_left = i >= filter_unit ? previous[i - filter_unit] : 0;
+                    int predicted = 0;
+                    switch(filter) {
+                        case 0:
+                            predicted = 0;
+                            break;
+                        case 1:
+                            predicted = left;
+                            break;
+                        case 2:
+                            predicted = up;
+                            break;
+                        case 3:
+                            predicted = (left + up) / 2;
+                            break;
+                        case 4:
+                            predicted = paeth(left, up, up_left);
+                            break;
+                        default:
+                            throw std::logic_error("readRGBImage: unknown scanline filter");
+                    }
+                    line[i] = static_cast<unsigned char>(raw[in + i] + predicted);
                 }
-                row[i] = static_cast<unsigned char>(in[i] + predicted);
+                in += line_bytes;
+                const std::size_t y = ps.y0 + row * ps.dy;
+                for(std::size_t col = 0; col < pw; col++) {
+                    const std::size_t x = ps.x0 + col * ps.dx;
+                    uint16_t *out = &samples[(y * width + x) * channels];
+                    for(int c = 0; c < channels; c++) {
+                        const std::size_t sample = col * channels + static_cast<std::size_t>(c);
+                        if(bit_depth == 16) {
+                            out[c] = static_cast<uint16_t>((static_cast<unsigned>(line[2 * sample]) << 8) | line[2 * sample + 1]);
+                        }
+                        else if(bit_depth == 8) {
+                            out[c] = line[sample];
+                        }
+                        else {
+                            const std::size_t bit = sample * static_cast<std::size_t>(bit_depth);
+                            const int shift = 8 - bit_depth - static_cast<int>(bit % 8);
+                            out[c] = static_cast<uint16_t>((line[bit / 8] >> shift) & ((1 << bit_depth) - 1));
+                        }
+                    }
+                }
+                previous.swap(line);
             }
         }
 
+        // EXPAND: palette -> RGB(A); a tRNS colour key -> alpha; grey below 8 bits scaled to 8 (libpng: value * 255 / max)
         Image<Color<float>> image(static_cast<int>(width), static_cast<int>(height));
+        const bool keyed = !transparency.empty() && (colour_type == 0 || colour_type == 2);
+        const int out_channels = colour_type == 3 ? (transparency.empty() ? 3 : 4) : channels + (keyed ? 1 : 0);
+        if(out_channels != 3 && out_channels != 4) {
+            return image; // grey and grey + alpha: the reference copies no rows (image_io.cpp:63-79)
+        }
+        // the colour key is compared with the file's samples at their full depth (libpng expands before it strips), then
+        // STRIP_16 keeps the high byte
+        auto key = [&](int c) -> unsigned {
+            return transparency.size() >= static_cast<std::size_t>(2 * c + 2) ? (static_cast<unsigned>(transparency[2 * c]) << 8) | transparency[2 * c + 1] : 0x10000U;
+        };
+        const int strip = bit_depth == 16 ? 8 : 0;
         for(uint32_t y = 0; y < height; y++) {
             for(uint32_t x = 0; x < width; x++) {
-                const unsigned char *p = &pixels[y * stride + static_cast<std::size_t>(x) * channels];
+                const uint16_t *p = &samples[(static_cast<std::size_t>(y) * width + x) * channels];
                 unsigned char rgba[4] = {0, 0, 0, 255};
-                switch(colour_type) {
-                    case 0:
-                        rgba[0] = rgba[1] = rgba[2] = p[0];
-                        break;
-                    case 2:
-                        rgba[0] = p[0];
-                        rgba[1] = p[1];
-                        rgba[2] = p[2];
-                        break;
-                    case 3: {
-                        const std::size_t entry = p[0];
-                        if(3 * entry + 2 >= palette.size()) {
-                            throw std::logic_error("readRGBImage: palette index out of range");
-                        }
-                        rgba[0] = palette[3 * entry];
-                        rgba[1] = palette[3 * entry + 1];
-                        rgba[2] = palette[3 * entry + 2];
-                        if(entry < transparency.size()) {
-                            rgba[3] = transparency[entry];
-                        }
-                        break;
+                if(colour_type == 3) {
+                    const std::size_t entry = p[0];
+                    if(3 * entry + 2 >= palette.size()) {
+                        throw std::logic_error("readRGBImage: palette index out of range");
                     }
-                    case 4:
-                        rgba[0] = rgba[1] = rgba[2] = p[0];
-                        rgba[3] = p[1];
-                        break;
-                    default:
-                        std::memcpy(rgba, p, 4);
-                        break;
+                    rgba[0] = palette[3 * entry];
+                    rgba[1] = palette[3 * entry + 1];
+                    rgba[2] = palette[3 * entry + 2];
+                    if(entry < transparency.size()) {
+                        rgba[3] = transparency[entry];
+                    }
+                }
+                else if(colour_type == 2) {
+                    rgba[0] = static_cast<unsigned char>(p[0] >> strip);
+                    rgba[1] = static_cast<unsigned char>(p[1] >> strip);
+                    rgba[2] = static_cast<unsigned char>(p[2] >> strip);
+                    if(keyed && p[0] == key(0) && p[1] == key(1) && p[2] == key(2)) {
+                        rgba[3] = 0;
+                    }
+                }
+                else {
+                    for(int c = 0; c < 4; c++) {
+                        rgba[c] = static_cast<unsigned char>(p[c] >> strip);
+                    }
                 }
                 image(static_cast<int>(x), static_cast<int>(y)) =
                   Color<float>(rgba[0] / 255.0F, rgba[1] / 255.0F, rgba[2] / 255.0F, rgba[3] / 255.0F);

@@ -130,6 +130,18 @@ class Pth:
         n = self.lib.pth_png_roundtrip(w, h, _ptr(img), _ptr(out))
         return out, n
 
+    def png_decode(self, data, max_pixels=1 << 22):
+        """b200 build only: io::readRGBImage on raw bytes -> float image [h, w, 4] (raises ValueError on a decode failure)."""
+        import ctypes as C
+
+        out = np.zeros(max_pixels * 4, np.float32)
+        w, h = C.c_int(0), C.c_int(0)
+        self.lib.pth_png_decode.restype = C.c_int
+        status = self.lib.pth_png_decode(bytes(data), C.c_long(len(data)), C.byref(w), C.byref(h), _ptr(out), C.c_long(max_pixels))
+        if status != 0:
+            raise ValueError(f"png decode failed with status {status}")
+        return out[:w.value * h.value * 4].reshape(h.value, w.value, 4)
+
     def png_decode_status(self, data):
         """b200 build only: io::readRGBImage on raw bytes; 0 = decoded, 1 = std::logic_error, 2 = any other exception."""
         return self.lib.pth_png_decode_status(bytes(data), len(data))

@@ -649,6 +649,28 @@ extern "C" long pth_png_roundtrip(int width, int height, const float *pixels_in,
     }
 }
 
+// b200 build only: io::readRGBImage on raw bytes into out[capacity_pixels * 4]; returns 0 and the size on success, 1 for
+// std::logic_error, 2 for anything else, 3 when the image does not fit
+extern "C" int pth_png_decode(const unsigned char *bytes, long length, int *width, int *height, float *out, long capacity_pixels) {
+    try {
+        std::stringstream stream(std::string(reinterpret_cast<const char *>(bytes), static_cast<size_t>(length)), std::ios_base::in | std::ios_base::binary);
+        Image<> decoded = io::readRGBImage(stream);
+        *width = decoded.getWidth();
+        *height = decoded.getHeight();
+        if(static_cast<long>(decoded.size()) > capacity_pixels) {
+            return 3;
+        }
+        std::memcpy(out, decoded.data(), sizeof(float) * 4 * decoded.size());
+        return 0;
+    }
+    catch(const std::logic_error &) {
+        return 1;
+    }
+    catch(...) {
+        return 2;
+    }
+}
+
 // b200 build only: io::readRGBImage on raw bytes; 0 = decoded, 1 = std::logic_error (the documented failure), 2 = anything else
 extern "C" int pth_png_decode_status(const unsigned char *bytes, long length) {
     try {

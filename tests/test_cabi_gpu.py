@@ -368,6 +368,56 @@ def test_device_built_scene_equals_the_host_built_scene(ctx, monkeypatch):
         dev.close()
 
 
+def test_device_build_at_full_size(ctx, monkeypatch):
+    """BASELINE-size scene (1 M-triangle stand-in mesh + the golden Cornell scene's primitives): the device-built parity
+    tree equals the host-built one bit for bit, and the device-built query tree is a valid hierarchy of depth <= 64."""
+    g = load_golden("samples", "cornell_mesh")
+    verts, normals = scenes.standin_triangles(1000, 500, scenes.DEMO_DRAGON_TRANSFORM)
+    mesh = np.zeros(len(verts), capi.PRIM_DTYPE)
+    mesh["kind"] = capi.PTB_PRIM_TRIANGLE
+    mesh["p"][:, :9] = verts
+    mesh["p"][:, 9:18] = normals
+    prims = np.concatenate([g["prims"], mesh])
+    monkeypatch.setenv("PTB_DEVICE_BUILD", "0")
+    monkeypatch.setenv("PTB_QUERY_TREE", "host")
+    host = capi.Scene(ctx, prims, g["materials"], g["lights"])
+    monkeypatch.setenv("PTB_DEVICE_BUILD", "1")
+    monkeypatch.setenv("PTB_QUERY_TREE", "sweep")
+    dev = capi.Scene(ctx, prims, g["materials"], g["lights"])
+    hi, di = host.info(), dev.info()
+    assert di.built_on_device == 1 and di.query_tree_kind == 3 and hi.built_on_device == 0
+    print(f"1 M triangles: parity tree {di.reference_tree_device_ms:.1f} ms, query tree {di.query_tree_device_ms:.1f} ms on the device; "
+          f"ptb_scene_create {di.build_seconds + di.upload_seconds:.3f} s (host builders: {hi.build_seconds + hi.upload_seconds:.3f} s)")
+    assert np.array_equal(dev.read_slot_to_prim(), host.read_slot_to_prim())
+    assert dev.read_nodes().tobytes() == host.read_nodes().tobytes()
+    assert dev.read_geom().tobytes() == host.read_geom().tobytes() and dev.read_shade().tobytes() == host.read_shade().tobytes()
+    assert (hi.bvh_depth, list(hi.root_low), list(hi.root_high)) == (di.bvh_depth, list(di.root_low), list(di.root_high))
+    nodes = dev.read_nodes(query_tree=True)
+    # structure without the per-node Python walk of _check_query_tree: every slot is a leaf exactly once, every inner node
+    # a child exactly once, parents consistent, leaf counts add up
+    refs = np.concatenate([nodes["left"], nodes["right"]])
+    leaves = np.sort(~refs[refs < 0])
+    inner = np.sort(refs[refs >= 0])
+    assert np.array_equal(leaves, np.arange(len(prims))) and np.array_equal(inner, np.arange(1, len(nodes)))
+    for side in ("left", "right"):
+        child = nodes[side]
+        is_inner = child >= 0
+        assert np.array_equal(nodes["parent"][child[is_inner]], np.nonzero(is_inner)[0])
+    counts = np.where(nodes["left"] >= 0, nodes["leaf_count"][np.maximum(nodes["left"], 0)], 1) + np.where(nodes["right"] >= 0, nodes["leaf_count"][np.maximum(nodes["right"], 0)], 1)
+    assert np.array_equal(counts, nodes["leaf_count"]) and nodes["leaf_count"][0] == len(prims)
+    # boxes: a child's box (as stored in its parent) is the union of the two boxes stored in the child
+    for side, lo_name, hi_name in (("left", "left_lo", "left_hi"), ("right", "right_lo", "right_hi")):
+        child = nodes[side]
+        is_inner = child >= 0
+        c = child[is_inner]
+        assert np.array_equal(nodes[lo_name][is_inner], np.minimum(nodes["left_lo"][c], nodes["right_lo"][c]))
+        assert np.array_equal(nodes[hi_name][is_inner], np.maximum(nodes["left_hi"][c], nodes["right_hi"][c]))
+        boxes = _prim_boxes(prims[dev.read_slot_to_prim()[~child[~is_inner]]])
+        assert np.array_equal(nodes[lo_name][~is_inner], boxes[:, :3]) and np.array_equal(nodes[hi_name][~is_inner], boxes[:, 3:])
+    host.close()
+    dev.close()
+
+
 def _prim_boxes(prims):
     """Object::getBoundingVolume in float32 (object.cpp:60-62, 90-93, 184-186): [n, 6] = lo xyz, hi xyz."""
     p = prims["p"]

@@ -99,7 +99,7 @@ def test_png_quantisation_matches_the_reference_formula(b200):
 
 def test_png_reader_rejects_hostile_headers_with_logic_error(b200):
     """A tiny file whose IHDR promises 65535 x 65535 pixels must fail with the documented std::logic_error, not allocate
-    gigabytes or throw std::bad_alloc; so must truncated streams and 16-bit / interlaced files (documented as unsupported)."""
+    gigabytes or throw std::bad_alloc; so must truncated streams and headers with invalid depths or interlace methods."""
     import struct
     import zlib
 
@@ -111,11 +111,124 @@ def test_png_reader_rejects_hostile_headers_with_logic_error(b200):
         return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", zlib.compress(data)) + chunk(b"IEND", b"")
 
     assert b200.png_decode_status(png(65535, 65535)) == 1
-    assert b200.png_decode_status(png(2, 2, depth=16, data=b"\x00" * 34)) == 1
-    assert b200.png_decode_status(png(2, 2, interlace=1, data=b"\x00" * 18)) == 1
+    assert b200.png_decode_status(png(2, 2, depth=16, data=b"\x00" * 34)) == 0  # 16-bit: read since round 2
+    assert b200.png_decode_status(png(2, 2, depth=3, data=b"\x00" * 18)) == 1  # no such bit depth
+    assert b200.png_decode_status(png(2, 2, interlace=2, data=b"\x00" * 18)) == 1  # no such interlace method
+    assert b200.png_decode_status(png(2, 2, interlace=1, data=b"\x00" * 18)) == 1  # Adam7 needs 4 pass rows here, not 2
     assert b200.png_decode_status(png(2, 2, data=b"\x00" * 18)[:-20]) == 1
     assert b200.png_decode_status(png(2, 2, data=b"\x00" * 18)) == 0
     assert b200.png_decode_status(b"not a png") == 1
+
+
+def test_png_reader_reads_what_libpng_reads(b200):
+    """The reference reads PNGs through libpng with EXPAND | PACKING | STRIP_16 and copies 3- and 4-channel rows
+    (src/image/image_io.cpp:50-79).  io::readRGBImage here: every colour type and bit depth, Adam7, palette with tRNS, colour
+    keys, 16-bit samples (high byte); grey and grey + alpha files yield zero pixels, as in the reference.  Expected values
+    come from PIL (an independent decoder) for the files PIL can write, and from the source arrays for hand-assembled
+    16-bit and interlaced files."""
+    import io
+    import struct
+    import zlib
+
+    from PIL import Image
+
+    rng = np.random.Generator(np.random.PCG64(77))
+    w, h = 37, 23  # odd sizes: partial bytes at the end of low-bit rows, ragged Adam7 passes
+
+    def pil_bytes(img, **kw):
+        buf = io.BytesIO()
+        img.save(buf, format="PNG", **kw)
+        return buf.getvalue()
+
+    def expect_rgba(img):
+        return np.asarray(img.convert("RGBA"), np.float32) / np.float32(255.0)
+
+    rgb = Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), "RGB")
+    rgba = Image.fromarray(rng.integers(0, 256, (h, w, 4), dtype=np.uint8), "RGBA")
+    assert np.array_equal(b200.png_decode(pil_bytes(rgb)), expect_rgba(rgb))
+    assert np.array_equal(b200.png_decode(pil_bytes(rgba)), expect_rgba(rgba))
+    for colours in (2, 4, 16, 200):  # palette images of 1, 2, 4 and 8 bits per index
+        pal = Image.fromarray(rng.integers(0, colours, (h, w), dtype=np.uint8), "P")
+        pal.putpalette(rng.integers(0, 256, 3 * colours, dtype=np.uint8).tobytes())
+        data = pil_bytes(pal, bits={2: 1, 4: 2, 16: 4, 200: 8}[colours])
+        assert np.array_equal(b200.png_decode(data), expect_rgba(pal)), colours
+        alpha = bytes(rng.integers(0, 256, colours // 2 + 1, dtype=np.uint8))  # tRNS shorter than the palette
+        data = pil_bytes(pal, bits={2: 1, 4: 2, 16: 4, 200: 8}[colours], transparency=alpha)
+        assert np.array_equal(b200.png_decode(data), expect_rgba(Image.open(io.BytesIO(data)))), colours
+    for mode, array in (("L", rng.integers(0, 256, (h, w), dtype=np.uint8)), ("1", rng.integers(0, 2, (h, w), dtype=np.uint8) * 255),
+                        ("LA", rng.integers(0, 256, (h, w, 2), dtype=np.uint8))):
+        grey = Image.fromarray(array.astype(np.uint8), "L" if mode == "1" else mode).convert(mode)
+        got = b200.png_decode(pil_bytes(grey))
+        assert got.shape == (h, w, 4) and not got.any(), mode  # the reference copies no rows of 1- and 2-channel images
+
+    def chunk(kind, payload):
+        return struct.pack(">I", len(payload)) + kind + payload + struct.pack(">I", zlib.crc32(kind + payload) & 0xFFFFFFFF)
+
+    def assemble(width, height, depth, colour, interlace, raw, extra=b""):
+        ihdr = struct.pack(">IIBBBBB", width, height, depth, colour, 0, 0, interlace)
+        return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + extra + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+
+    def filtered_rows(rows, bpp):
+        """Scanlines with PNG filters 0..4 in turn (rows: [n, bytes] uint8)."""
+        out = bytearray()
+        prev = np.zeros(rows.shape[1], np.int32)
+        for y, row in enumerate(rows.astype(np.int32)):
+            f = y % 5
+            left = np.concatenate([np.zeros(bpp, np.int32), row[:-bpp]]) if rows.shape[1] > bpp else np.zeros_like(row)
+            upleft = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]]) if rows.shape[1] > bpp else np.zeros_like(row)
+            if f == 0:
+                pred = np.zeros_like(row)
+            elif f == 1:
+                pred = left
+            elif f == 2:
+                pred = prev
+            elif f == 3:
+                pred = (left + prev) // 2
+            else:
+                p = left + prev - upleft
+                pa, pb, pc = np.abs(p - left), np.abs(p - prev), np.abs(p - upleft)
+                pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prev, upleft))
+            out.append(f)
+            out += bytes(((row - pred) & 0xFF).astype(np.uint8))
+            prev = row
+        return bytes(out)
+
+    # 16-bit RGB and RGBA: STRIP_16 keeps the high byte; an RGB colour key is compared at 16 bits
+    for channels, colour in ((3, 2), (4, 6)):
+        src = rng.integers(0, 65536, (h, w, channels), dtype=np.uint16)
+        src[3, 5] = src[4, 6] = (0x1234, 0x5678, 0x9ABC, 0xFFFF)[:channels]
+        src[5, 7] = (0x1234, 0x5678, 0x9ABD, 0xFFFF)[:channels]  # differs from the key in a LOW byte only
+        rows = src.astype(">u2").tobytes()
+        rows = np.frombuffer(rows, np.uint8).reshape(h, w * channels * 2)
+        want = np.ones((h, w, 4), np.float32)
+        want[..., :channels] = (src >> 8).astype(np.float32) / np.float32(255.0)
+        assert np.array_equal(b200.png_decode(assemble(w, h, 16, colour, 0, filtered_rows(rows, 2 * channels))), want), colour
+        if channels == 3:
+            key = chunk(b"tRNS", struct.pack(">HHH", 0x1234, 0x5678, 0x9ABC))
+            want[3, 5, 3] = want[4, 6, 3] = 0.0
+            assert np.array_equal(b200.png_decode(assemble(w, h, 16, colour, 0, filtered_rows(rows, 2 * channels), extra=key)), want)
+
+    # Adam7: 8-bit RGBA and 4-bit palette, every pass filtered on its own
+    passes = [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)]
+    src = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    raw = b""
+    for x0, y0, dx, dy in passes:
+        sub = src[y0::dy, x0::dx]
+        if sub.size:
+            raw += filtered_rows(sub.reshape(sub.shape[0], -1), 4)
+    assert np.array_equal(b200.png_decode(assemble(w, h, 8, 6, 1, raw)), src.astype(np.float32) / np.float32(255.0))
+    index = rng.integers(0, 16, (h, w), dtype=np.uint8)
+    palette = rng.integers(0, 256, (16, 3), dtype=np.uint8)
+    raw = b""
+    for x0, y0, dx, dy in passes:
+        sub = index[y0::dy, x0::dx]
+        if sub.size:
+            padded = np.zeros((sub.shape[0], (sub.shape[1] + 1) // 2 * 2), np.uint8)
+            padded[:, :sub.shape[1]] = sub
+            raw += filtered_rows((padded[:, 0::2] << 4) | padded[:, 1::2], 1)
+    want = np.ones((h, w, 4), np.float32)
+    want[..., :3] = palette[index].astype(np.float32) / np.float32(255.0)
+    assert np.array_equal(b200.png_decode(assemble(w, h, 4, 3, 1, raw, extra=chunk(b"PLTE", palette.tobytes()))), want)
 
 
 def test_tile_sharding_partitions_the_frame():
