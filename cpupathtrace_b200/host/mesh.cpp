@@ -11,13 +11,18 @@
 //   * faces with an out-of-range index, two coincident vertices or a zero cross product are dropped.
 #include <PathTrace/scene/mesh.h>
 
+#include <algorithm>
+#include <array>
 #include <cerrno>
+#include <chrono>
+#include <cstdio>
 #include <climits>
 #include <cstdlib>
 #include <fstream>
 #include <iterator>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -27,14 +32,144 @@ namespace {
         ObjReader(const std::string &text, const mat4<float> &transform, bool cull, bool smooth) :
           data(text.data()), size(text.size()), transform(transform), cull(cull), smooth(smooth) {}
 
-        std::vector<Triangle> run() {
-            while(more()) {
-                record();
+        static double nowSeconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+        static void phase(const char *what, double &since) {
+            if(std::getenv("PTB_LOG_MESH") != nullptr) {
+                const double now = nowSeconds();
+                std::fprintf(stderr, "[mesh] %-28s %7.1f ms\n", what, (now - since) * 1e3);
+                since = now;
             }
+        }
+
+        std::vector<Triangle> run() {
+            double since = nowSeconds();
+            unsigned workers = std::min(16U, std::max(1U, std::thread::hardware_concurrency()));
+            if(const char *forced = std::getenv("PTB_MESH_THREADS")) {
+                workers = static_cast<unsigned>(std::min(64L, std::max(1L, std::atol(forced))));
+            }
+            if(workers > 1U && size >= (1U << 20)) {
+                runChunks(workers);
+            }
+            else {
+                while(more()) {
+                    record();
+                }
+            }
+            phase("records -> faces", since);
             if(smooth) {
                 smoothNormals();
             }
+            phase("smooth normals", since);
             return std::move(faces);
+        }
+
+        // Large files are parsed in chunks on several threads.  The grammar above is sequential -- a record may end in the
+        // middle of a line or spill into the next one (a vertex record with two numbers eats the first token of the
+        // following line), and a face is kept only if its indices are below the number of vertices read SO FAR -- so a
+        // chunk (cut after a line break) is parsed as if the stream started there, records where it stopped, and is only
+        // accepted if the chunk before it stopped exactly at its first byte; from the first chunk that does not line up the
+        // rest of the file is parsed sequentially.  Faces are validated afterwards against the vertex count at their position
+        // in the stream, which the chunks' prefix sums give.  Result: identical to the sequential parse, byte for byte.
+        struct PendingFace {
+            int ia, ib, ic;
+            uint32_t vertices_before; // within the chunk
+        };
+
+        void runChunks(unsigned workers) {
+            std::vector<std::size_t> cut(workers + 1, size);
+            cut[0] = 0;
+            for(unsigned k = 1; k < workers; k++) {
+                std::size_t p = std::max(cut[k - 1], size * k / workers);
+                while(p < size && data[p] != '\n') {
+                    p++;
+                }
+                cut[k] = std::min(size, p + 1);
+            }
+            std::vector<ObjReader> parts;
+            parts.reserve(workers);
+            for(unsigned k = 0; k < workers; k++) {
+                parts.emplace_back(*this);
+                parts.back().at = cut[k];
+                parts.back().deferred = true;
+            }
+            {
+                std::vector<std::thread> pool;
+                for(unsigned k = 0; k < workers; k++) {
+                    pool.emplace_back([&parts, &cut, k]() {
+                        ObjReader &part = parts[k];
+                        while(part.at < cut[k + 1] && part.more()) {
+                            part.record();
+                        }
+                    });
+                }
+                for(std::thread &t : pool) {
+                    t.join();
+                }
+            }
+            double since = nowSeconds();
+            phase("  (chunk parse done)", since);
+            // accept the chunks that line up; parse the rest sequentially (in deferred mode as well) from where the last
+            // accepted chunk stopped
+            unsigned accepted = 1;
+            while(accepted < workers && parts[accepted - 1].at == cut[accepted]) {
+                accepted++;
+            }
+            if(parts[accepted - 1].at < size && accepted < workers) {
+                ObjReader &tail = parts[accepted];
+                tail.vertices.clear();
+                tail.pending.clear();
+                tail.at = parts[accepted - 1].at;
+                while(tail.more()) {
+                    tail.record();
+                }
+                accepted++;
+            }
+            parts.erase(parts.begin() + static_cast<std::ptrdiff_t>(accepted), parts.end());
+
+            // vertices: concatenate; faces: validate against the vertex count at their position, in parallel per chunk
+            std::vector<std::size_t> vertex_base(parts.size() + 1, 0);
+            for(std::size_t k = 0; k < parts.size(); k++) {
+                vertex_base[k + 1] = vertex_base[k] + parts[k].vertices.size();
+            }
+            vertices.resize(vertex_base.back());
+            {
+                std::vector<std::thread> pool;
+                for(std::size_t k = 0; k < parts.size(); k++) {
+                    pool.emplace_back([this, &parts, &vertex_base, k]() { std::copy(parts[k].vertices.begin(), parts[k].vertices.end(), vertices.begin() + static_cast<std::ptrdiff_t>(vertex_base[k])); });
+                }
+                for(std::thread &t : pool) {
+                    t.join();
+                }
+            }
+            {
+                std::vector<std::thread> pool;
+                for(std::size_t k = 0; k < parts.size(); k++) {
+                    pool.emplace_back([this, &parts, &vertex_base, k]() {
+                        ObjReader &part = parts[k];
+                        part.faces.reserve(part.pending.size());
+                        part.corner_vertex.reserve(3 * part.pending.size());
+                        for(const PendingFace &f : part.pending) {
+                            part.keepFace(vertices, static_cast<int>(vertex_base[k] + f.vertices_before), f.ia, f.ib, f.ic);
+                        }
+                    });
+                }
+                for(std::thread &t : pool) {
+                    t.join();
+                }
+            }
+            phase("  vertices + face validation", since);
+            std::size_t total = 0;
+            for(const ObjReader &part : parts) {
+                total += part.faces.size();
+            }
+            faces.reserve(total);
+            corner_vertex.reserve(3 * total);
+            for(ObjReader &part : parts) {
+                faces.insert(faces.end(), part.faces.begin(), part.faces.end());
+                corner_vertex.insert(corner_vertex.end(), part.corner_vertex.begin(), part.corner_vertex.end());
+            }
+            at = size;
+            phase("  concatenation", since);
         }
 
       private:
@@ -48,6 +183,8 @@ namespace {
         std::vector<vec3<float>> vertices;
         std::vector<Triangle> faces;
         std::vector<uint32_t> corner_vertex; // 3 per kept face: which vertex each corner refers to
+        bool deferred = false;               // chunk mode: faces are recorded, not validated (runChunks)
+        std::vector<PendingFace> pending;
 
         bool more() const { return at < size; }
         char look() const { return more() ? data[at] : static_cast<char>(-1); }
@@ -132,13 +269,21 @@ namespace {
             const int ia = faceIndex();
             const int ib = faceIndex();
             const int ic = faceIndex();
-            const int count = static_cast<int>(vertices.size());
+            if(deferred) {
+                pending.push_back(PendingFace{ia, ib, ic, static_cast<uint32_t>(vertices.size())});
+                return;
+            }
+            keepFace(vertices, static_cast<int>(vertices.size()), ia, ib, ic);
+        }
+
+        // `count` = vertices read before the face record; `all` may hold more (chunk mode)
+        void keepFace(const std::vector<vec3<float>> &all, int count, int ia, int ib, int ic) {
             if(ia < 0 || ia >= count || ib < 0 || ib >= count || ic < 0 || ic >= count) {
                 return;
             }
-            const vec3<float> &a = vertices[ia];
-            const vec3<float> &b = vertices[ib];
-            const vec3<float> &c = vertices[ic];
+            const vec3<float> &a = all[ia];
+            const vec3<float> &b = all[ib];
+            const vec3<float> &c = all[ic];
             // written so that NaN coordinates fail the test
             const bool distinct = (b - a).getLengthSquared() > 0.0F && (c - a).getLengthSquared() > 0.0F && (c - b).getLengthSquared() > 0.0F;
             if(!distinct) {
@@ -237,7 +382,28 @@ namespace {
 namespace io {
 
     std::vector<Triangle> loadMesh(std::basic_istream<char> &stream, mat4<float> transformation, bool cull_backface, bool smooth) {
-        const std::string text((std::istreambuf_iterator<char>(stream)), std::istreambuf_iterator<char>());
+        const double t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        // the whole stream in blocks (an istreambuf_iterator copy moves one character per virtual call: 0.15 s for 40 MB)
+        std::string text;
+        {
+            std::streambuf *buffer = stream.rdbuf();
+            std::size_t filled = 0;
+            for(;;) {
+                if(text.size() - filled < (1U << 20)) {
+                    text.resize(std::max<std::size_t>(2 * text.size(), 4U << 20));
+                }
+                const std::streamsize got = buffer != nullptr ? buffer->sgetn(&text[filled], static_cast<std::streamsize>(text.size() - filled)) : 0;
+                if(got <= 0) {
+                    break;
+                }
+                filled += static_cast<std::size_t>(got);
+            }
+            text.resize(filled);
+            stream.setstate(std::ios_base::eofbit);
+        }
+        if(std::getenv("PTB_LOG_MESH") != nullptr) {
+            std::fprintf(stderr, "[mesh] %-28s %7.1f ms\n", "stream -> memory", (std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0) * 1e3);
+        }
         return ObjReader(text, transformation, cull_backface, smooth).run();
     }
 

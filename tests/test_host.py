@@ -68,6 +68,57 @@ def test_obj_parser_edge_cases_match_reference(ref, b200):
                 assert ta.shape == tb.shape and np.array_equal(ta, tb, equal_nan=True), (text, smooth, tr)
 
 
+def test_chunked_obj_parse_equals_the_sequential_parse(ref, b200, monkeypatch):
+    """Files above 1 MB are parsed in chunks on several threads (host/mesh.cpp).  The reference's grammar is sequential: a
+    short vertex record eats the first token of the next line, faces are kept only if their indices are below the number
+    of vertices read so far.  A file full of such cases -- also right at the chunk cuts, which move with the thread
+    count -- must give the triangles of the sequential parse and of the reference's own parser."""
+    rng = np.random.Generator(np.random.PCG64(2024))
+    lines = []
+    n_vertices = 0
+    while len(lines) < 70000:
+        kind = rng.integers(0, 100)
+        if kind < 45:
+            lines.append("v %.5f %.5f %.5f" % tuple(rng.uniform(-3, 3, 3)))
+            n_vertices += 1
+        elif kind < 85:
+            hi = max(n_vertices + 40, 3)  # some indices point at vertices that come later (or never): dropped
+            a, b, c = (int(v) for v in rng.integers(1, hi, 3))
+            lines.append(rng.choice(["f %d %d %d", "f %d//7 %d//8 %d//9", "f   %d %d %d 12"]) % (a, b, c))
+        elif kind < 88:
+            lines.append("v %.4f %.4f" % tuple(rng.uniform(-3, 3, 2)))  # short record: spills into the next line
+            n_vertices += 1
+        elif kind < 91:
+            lines.append("f %d %d" % tuple(int(v) for v in rng.integers(1, max(n_vertices, 2), 2)))
+        elif kind < 94:
+            lines.append("# comment v 1 2 3")
+        elif kind < 96:
+            lines.append("vn 0 0 1")
+        elif kind < 98:
+            lines.append("")
+        else:
+            lines.append("  v 1e-2 -2E+0 +3.5 trailing words")
+            n_vertices += 1
+    text = "\n".join(lines) + "\n"
+    crlf = text.replace("\n", "\r\n")
+    for data in (text, crlf):
+        assert len(data) > (1 << 20)
+        spec = scenes.SceneSpec()
+        spec.mesh_obj(data, None, False, True, -1)
+        results = []
+        for threads in ("1", "3", "7", "16"):
+            monkeypatch.setenv("PTB_MESH_THREADS", threads)
+            b = spec.replay(b200)
+            results.append(b.get_triangles())
+            b.close()
+        b = spec.replay(ref)
+        want = b.get_triangles()
+        b.close()
+        assert len(want) > 1000
+        for got in results:
+            assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 def test_png_round_trip(b200):
     """reference test/image/image_io_test.cpp:12-40: encode/decode within 0.004 per channel (seeded random 256x128)."""
     rng = np.random.Generator(np.random.PCG64(1234))
