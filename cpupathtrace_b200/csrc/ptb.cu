@@ -1948,6 +1948,11 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
     // cover a quarter of the remaining range (PTB_ADAPTIVE_ROUND_DIVISOR; measured on the bench scene, 32..256 / 16..1024 spp:
     // 2 -> 540 / 3078 ms, 4 -> 562 / 3032, 8 -> 586 / 3182, 16 -> 650 / 3149), at least one run of checks.
     const ResolveConsts rc = resolveConsts(opts->min_sample_count, spp);
+    // candidates a pixel's loop can open (worker.cpp:208-219): one per candidate_batch_count batches plus the remainder; the
+    // per-pixel state holds kMaxCandidates of them (at most 6 for any option set: candidate_batch_count >= max / 4 batches)
+    if(spp > 0 && (spp / rc.stats_sample_count) / rc.candidate_batch_count + 1 > kMaxCandidates) {
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_render: sample counts that open more than " + std::to_string(kMaxCandidates) + " candidates per pixel");
+    }
     const bool adaptive = ctx->adaptive_rounds && spp > 0 && opts->min_sample_count < spp;
     int first_round = spp;
     int later_round = spp;

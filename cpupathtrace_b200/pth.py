@@ -295,7 +295,7 @@ class PthScene:
         return out
 
     def process_job(self, camera, width, height, min_spp, max_spp, epsilon, workers=0):
-        out = np.zeros((max(height, 0), max(width, 0), 4), np.float32)
+        out = np.empty((max(height, 0), max(width, 0), 4), np.float32)
         total, mono = C.c_int(), C.c_int()
         calls = self.pth.lib.pth_process_job(self.h, camera.h, width, height, min_spp, max_spp, epsilon, workers, _ptr(out), C.byref(total), C.byref(mono))
         timeline = np.zeros(3, np.float64)
