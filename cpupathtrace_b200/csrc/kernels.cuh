@@ -30,9 +30,6 @@ namespace ptb {
     constexpr int kBlock = 128;
     constexpr int kFlatBlock = PTB_FLAT_BLOCK;
     static_assert(kBlock == kTraceBlock, "the traversal's shared-memory stack is laid out for kBlock threads per CTA");
-#ifndef PTB_SHADE_PREFETCH
-#define PTB_SHADE_PREFETCH 0
-#endif
 #ifndef PTB_SHADE_MIN_BLOCKS
 #define PTB_SHADE_MIN_BLOCKS 6 // 80 registers: +4 % shade throughput over the unconstrained 93 (8 CTAs / 64 registers spill and gain nothing)
 #endif
@@ -323,17 +320,6 @@ namespace ptb {
         uint32_t stat_skipped = 0U;
         uint32_t parity = 0U;
         // whole blocks iterate together (the barriers below need every thread of the block in every trip)
-#if PTB_SHADE_PREFETCH
-        // software pipeline over the trips: the queue entry of the NEXT trip is loaded at the top of this one, its hit record
-        // after this trip's vertex has been shaded -- two of the three dependent DRAM round trips (queue -> hit -> geometry)
-        // overlap with the arithmetic of the trip before
-        uint32_t i_ahead = 0U;
-        float2 h_ahead = make_float2(-1.0F, 0.0F);
-        if(blockIdx.x * blockDim.x + threadIdx.x < count) {
-            i_ahead = queue[blockIdx.x * blockDim.x + threadIdx.x];
-            h_ahead = pool.hit[i_ahead];
-        }
-#endif
         for(uint32_t first = blockIdx.x * blockDim.x; first < count; first += stride, parity ^= 1U) {
             const uint32_t k = first + threadIdx.x;
             const bool active = k < count;
@@ -343,20 +329,6 @@ namespace ptb {
             bool hit_surface = false;
             float t = -1.0F;
             uint32_t slot = 0U;
-#if PTB_SHADE_PREFETCH
-            const bool next_active = k + stride < count && k + stride >= k;
-            uint32_t i_next = 0U;
-            if(next_active) {
-                i_next = queue[k + stride];
-            }
-            if(active) {
-                i = i_ahead;
-                loadPath(pool, i, p, flags);
-                t = h_ahead.x;
-                slot = static_cast<uint32_t>(__float_as_int(h_ahead.y));
-                hit_surface = !(t < 0.0F);
-            }
-#else
             if(active) {
                 i = queue[k];
                 loadPath(pool, i, p, flags);
@@ -365,7 +337,6 @@ namespace ptb {
                 slot = static_cast<uint32_t>(__float_as_int(h.y));
                 hit_surface = !(t < 0.0F);
             }
-#endif
 
             uint32_t n_shadow = 0U;
             bool continues = false;
@@ -397,12 +368,6 @@ namespace ptb {
                 storePath(pool, i, p, flags, word);
             }
 
-#if PTB_SHADE_PREFETCH
-            i_ahead = i_next;
-            if(next_active) {
-                h_ahead = pool.hit[i_next];
-            }
-#endif
             // queue the shadow rays: exclusive scan of the per-lane counts over the lanes that arrive together (normally
             // the whole warp; one ballot per bit of the count stays correct for any group of lanes), one SHARED-memory
             // atomic per group, one global atomic per block and trip.

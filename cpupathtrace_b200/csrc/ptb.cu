@@ -136,7 +136,9 @@ struct ptb_context {
     Buffer build_arena;   // scene setup on the device: every temporary of a tree build is carved from this one allocation
     Buffer multi_image;   // ptb_render_multi: this replica's share of the frame (its tiles, zeros elsewhere)
     Buffer multi_staging; // ptb_render_multi on the first replica: copies of the other replicas' images when peers cannot map each other
-    uint32_t *host_counters = nullptr; // pinned
+    uint32_t *host_counters = nullptr; // pinned: two batches of bounce iterations (double-buffered)
+    cudaEvent_t batch_done[2] = {nullptr, nullptr};
+    bool pipelined_batches = true; // PTB_PIPELINED_BATCHES=0: the host waits for every batch before enqueuing the next
     unsigned long long *host_cursor = nullptr; // pinned: the work cursor as of the last batch of bounce iterations
 
     // profiling events: [pair][0 = start, 1 = stop], class 0 = closest-hit trace, 2 = shadow trace, 1 = everything else
@@ -430,8 +432,18 @@ namespace {
             }
         };
 
+        // Batches are double-buffered: batch b + 1 is enqueued BEFORE the host waits for batch b's counters, so the GPU never
+        // idles at a batch boundary while the host thread reads counters, reports progress or is descheduled (measured: up to
+        // 26 ms of a 790 ms frame were such gaps).  Termination is noticed one batch late; the surplus iterations run on empty
+        // queues.
         const int batch = ctx->iterations_per_sync;
-        while(n_cur > 0U) {
+        struct Inflight {
+            int launched;
+            int cur_after; // `cur` after the batch was enqueued
+        };
+        Inflight inflight[2] = {};
+        auto enqueue_batch = [&](int buffer) -> int {
+            uint32_t *host_counters = ctx->host_counters + buffer * kMaxIterationsPerSync * kCounterSlots;
             int launched = 0;
             for(; launched < batch; launched++) {
                 const int nxt = cur ^ 1;
@@ -442,7 +454,7 @@ namespace {
                 const int flat_grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_cur) + kFlatBlock - 1) / kFlatBlock, static_cast<uint64_t>(gridFor(ctx, 32 * kBlock / kFlatBlock))));
                 // the shade kernel splits its queue statically between blocks that all run the whole launch: a grid of exactly
                 // the resident blocks (6 per SM at 80 registers) has no last partial wave (32 per SM = 5.33 waves left a third
-                // of the slots empty for the last sixth of every launch)
+                // of the slots empty for the last sixth of every launch: shade + accumulate 303 -> 291 ms per frame)
                 const int shade_grid = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_cur) + kFlatBlock - 1) / kFlatBlock, static_cast<uint64_t>(gridFor(ctx, ctx->shade_blocks_per_sm))));
                 {
                     LaunchTimer timer(ctx, 0);
@@ -491,20 +503,40 @@ namespace {
                                                                                           queue_slot[nxt], samples, work_cursor);
                     }
                 }
-                PTB_CUDA(cudaMemcpyAsync(ctx->host_counters + launched * kCounterSlots, counters, kCounterSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                PTB_CUDA(cudaMemcpyAsync(host_counters + launched * kCounterSlots, counters, kCounterSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
                 cur = nxt;
             }
             if(progress != nullptr) {
                 PTB_CUDA(cudaMemcpyAsync(ctx->host_cursor, work_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
             }
-            PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+            PTB_CUDA(cudaEventRecord(ctx->batch_done[buffer], ctx->stream));
             PTB_CUDA(cudaGetLastError());
+            inflight[buffer] = Inflight{launched, cur};
+            return PTB_OK;
+        };
 
-            // `cur` is now the queue the last launched iteration wrote; walk the batch in launch order
-            int slot_in = (launched % 2 == 0) ? cur : (cur ^ 1);
+        int status = PTB_OK;
+        int oldest = 0;
+        bool ahead = false; // a batch beyond `oldest` is in flight
+        if(n_cur > 0U && (status = enqueue_batch(0)) != PTB_OK) {
+            return status;
+        }
+        while(n_cur > 0U) {
+            if(!ahead && ctx->pipelined_batches) {
+                if((status = enqueue_batch(oldest ^ 1)) != PTB_OK) {
+                    return status;
+                }
+                ahead = true;
+            }
+            PTB_CUDA(cudaEventSynchronize(ctx->batch_done[oldest]));
+
+            // walk the oldest batch in launch order
+            const Inflight &done = inflight[oldest];
+            const uint32_t *host_counters = ctx->host_counters + oldest * kMaxIterationsPerSync * kCounterSlots;
+            int slot_in = (done.launched % 2 == 0) ? done.cur_after : (done.cur_after ^ 1);
             uint32_t n_in = n_cur;
-            for(int j = 0; j < launched; j++) {
-                const uint32_t *hc = ctx->host_counters + j * kCounterSlots;
+            for(int j = 0; j < done.launched; j++) {
+                const uint32_t *hc = host_counters + j * kCounterSlots;
                 const int slot_out = slot_in ^ 1;
                 if(n_in > 0U) {
                     if(stats != nullptr) {
@@ -524,7 +556,6 @@ namespace {
                 n_in = hc[queue_slot[slot_out]];
                 slot_in = slot_out;
             }
-            collectTimers(ctx, stats);
             n_cur = n_in;
             if(progress != nullptr && progress->fn != nullptr && n_cur > 0U) {
                 // started work items minus the paths still in flight = samples retired into the per-sample buffer
@@ -532,7 +563,21 @@ namespace {
                 const uint64_t retired = started > n_cur ? started - n_cur : 0;
                 progress->fn(progress->user, progress->done_before + retired, progress->total);
             }
+            if(ahead) {
+                oldest ^= 1;
+                ahead = false;
+                if(n_cur == 0U) {
+                    PTB_CUDA(cudaEventSynchronize(ctx->batch_done[oldest])); // the surplus batch: empty queues throughout
+                }
+            }
+            else if(n_cur > 0U) {
+                if((status = enqueue_batch(oldest)) != PTB_OK) {
+                    return status;
+                }
+            }
         }
+        PTB_CUDA(cudaGetLastError());
+        collectTimers(ctx, stats);
         return PTB_OK;
     }
 
@@ -1112,7 +1157,10 @@ int ptb_context_create(int device, ptb_context **out) {
         return fail(PTB_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100-class; the kernels are built for sm_100a only");
     }
     PTB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    PTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->host_counters), kMaxIterationsPerSync * kCounterSlots * sizeof(uint32_t)));
+    PTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->host_counters), 2 * kMaxIterationsPerSync * kCounterSlots * sizeof(uint32_t)));
+    PTB_CUDA(cudaEventCreateWithFlags(&ctx->batch_done[0], cudaEventDisableTiming));
+    PTB_CUDA(cudaEventCreateWithFlags(&ctx->batch_done[1], cudaEventDisableTiming));
+    ctx->pipelined_batches = envLong("PTB_PIPELINED_BATCHES", 1) != 0;
     PTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->host_cursor), sizeof(unsigned long long)));
     for(auto &pair : ctx->events) {
         PTB_CUDA(cudaEventCreate(&pair[0]));
@@ -1152,6 +1200,12 @@ int ptb_context_destroy(ptb_context *ctx) {
     for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->redo_queue, &ctx->counters, &ctx->visits, &ctx->work_cursor, &ctx->samples, &ctx->pixel_list, &ctx->pixel_states, &ctx->active_lists, &ctx->adaptive_counters, &ctx->build_arena,
                      &ctx->io_a, &ctx->io_b, &ctx->io_c, &ctx->io_d, &ctx->multi_image, &ctx->multi_staging, &ctx->sort_keys, &ctx->sort_ids, &ctx->sort_temp}) {
         b->release();
+    }
+    for(cudaEvent_t &e : ctx->batch_done) {
+        if(e != nullptr) {
+            cudaEventDestroy(e);
+            e = nullptr;
+        }
     }
     if(ctx->host_counters != nullptr) {
         cudaFreeHost(ctx->host_counters);
@@ -1432,8 +1486,11 @@ int ptb_scene_create(ptb_context *ctx, const ptb_scene_desc *desc, ptb_scene **o
         else {
             float unused_root[6];
             uint32_t depth = 0;
-            status = buildTreeOnDevice(ctx, boxes_by_slot.as<float>(), static_cast<uint32_t>(n), false, static_cast<uint32_t>(kStackCapacity), scene->occ_nodes, nullptr, depth,
-                                       unused_root, query_tree_device_ms);
+            // (PTB_QUERY_TREE_MAX_LEVELS below 64 exists to exercise the fallback: a sweep tree deeper than the stack needs
+            // surface areas growing a hundredfold per primitive, which float coordinates cannot hold for 64 levels)
+            const uint32_t max_levels = static_cast<uint32_t>(std::min<long>(kStackCapacity, std::max(1L, envLong("PTB_QUERY_TREE_MAX_LEVELS", kStackCapacity))));
+            status = buildTreeOnDevice(ctx, boxes_by_slot.as<float>(), static_cast<uint32_t>(n), false, max_levels, scene->occ_nodes, nullptr, depth, unused_root,
+                                       query_tree_device_ms);
             levels = depth > 0U ? depth - 1U : 0U;
         }
         if(status != PTB_OK) {

@@ -368,40 +368,54 @@ def test_device_built_scene_equals_the_host_built_scene(ctx, monkeypatch):
         dev.close()
 
 
-def test_query_tree_deeper_than_the_stack_falls_back(ctx, monkeypatch):
-    """Triangles whose sizes grow geometrically make the surface-area heuristic peel off one primitive per level: the
-    device-built query tree would be deeper than the 64-entry traversal stack.  The builder must notice and hand over to
-    the host builder (or do without a query tree) -- and results must not change either way."""
+def test_query_tree_fallback_and_wide_dynamic_range(ctx, monkeypatch):
+    """(1) Triangles whose sizes span seven orders of magnitude (the surface-area heuristic peels the large ones off level
+    by level): the device-built query tree stays a valid hierarchy within the traversal stack, any-hit queries on it agree
+    with visibility derived from the reference-order closest hit, guarded certified closest hits are identical.
+    (2) A device tree that comes out deeper than allowed (forced here through PTB_QUERY_TREE_MAX_LEVELS; naturally it
+    would take surface areas growing a hundredfold per primitive over 64 levels) hands over to the host builder, and
+    nothing changes."""
     g = load_golden("samples", "cornell_mesh")
     n = 90
     prims = np.zeros(n, capi.PRIM_DTYPE)
     prims["kind"] = capi.PTB_PRIM_TRIANGLE
     for k in range(n):
-        size = np.float32(1.5) ** k
+        size = np.float32(1.2) ** k
         prims[k]["p"][:9] = np.float32([size, 0, 0, size * 1.4, size * 0.3, 0, size * 1.2, 0, size * 0.3])
         prims[k]["p"][9:18] = np.tile(np.float32([0, 0, 1]), 3)
-    monkeypatch.setenv("PTB_QUERY_TREE", "sweep")
-    scene = capi.Scene(ctx, prims, g["materials"], g["lights"])
-    info = scene.info()
-    assert info.built_on_device == 1 and info.query_tree_kind in (0, 1, 3)
-    if info.query_tree_kind != 0:
-        nodes = scene.read_nodes(query_tree=True)
-        boxes = _prim_boxes(prims[scene.read_slot_to_prim()])
-        assert _check_query_tree(nodes, boxes[:, :3], boxes[:, 3:]) <= 64
     rng = np.random.Generator(np.random.PCG64(3))
-    targets = np.float32(1.5) ** rng.uniform(0, n, 20000).astype(np.float32)
-    origins = np.stack([targets * 1.2, rng.uniform(-5, 5, 20000).astype(np.float32) * targets, targets * 0.1], axis=1).astype(np.float32)
-    d = np.stack([rng.normal(0, 0.05, 20000), -np.sign(origins[:, 1]), rng.normal(0, 0.05, 20000)], axis=1).astype(np.float32)
-    d /= np.linalg.norm(d, axis=1, keepdims=True)
-    rays = np.concatenate([origins, d.astype(np.float32)], axis=1)
-    t, prim, _ = scene.intersect(rays)
-    t_c, prim_c, _ = scene.intersect(rays, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST | capi.PTB_FLAG_CERTIFIED_RELAXED)
-    assert (t >= 0).mean() > 0.05
-    assert np.array_equal(prim_c, prim) and np.array_equal(t_c[t >= 0], t[t >= 0])
+    which = rng.integers(0, n, 20000)
+    tri = prims["p"][which, :9].reshape(-1, 3, 3)
+    size = (np.float32(1.2) ** which.astype(np.float32))[:, None]
+    target = tri.mean(axis=1) + rng.normal(0, 0.05, (20000, 3)).astype(np.float32) * size
+    away = rng.normal(0, 1, (20000, 3)).astype(np.float32)
+    away /= np.linalg.norm(away, axis=1, keepdims=True)
+    origins = (target + away * size * rng.uniform(0.5, 30, (20000, 1)).astype(np.float32)).astype(np.float32)
+    rays = np.concatenate([origins, -away], axis=1).astype(np.float32)
     oracle = pto.OracleScene(prims, g["materials"], g["lights"])
     t_o, prim_o = oracle.intersect(rays)
-    assert np.array_equal(prim, prim_o) and np.array_equal(t[t_o >= 0], t_o[t_o >= 0])
-    scene.close()
+    assert (t_o >= 0).mean() > 0.3
+    limit = np.where(t_o >= 0, t_o * rng.choice([0.5, 2.0], size=len(t_o)).astype(np.float32), np.float32(1e9)).astype(np.float32)
+    shadow = np.concatenate([rays, limit[:, None]], axis=1)
+    want_occluded = ((t_o >= 0) & (t_o < limit)).astype(np.uint8)
+
+    for max_levels, kinds in ((None, (3,)), ("3", (0, 1))):
+        monkeypatch.setenv("PTB_QUERY_TREE", "sweep")
+        if max_levels is not None:
+            monkeypatch.setenv("PTB_QUERY_TREE_MAX_LEVELS", max_levels)
+        scene = capi.Scene(ctx, prims, g["materials"], g["lights"])
+        info = scene.info()
+        assert info.built_on_device == 1 and info.query_tree_kind in kinds, (max_levels, info.query_tree_kind)
+        if info.query_tree_kind != 0:
+            nodes = scene.read_nodes(query_tree=True)
+            boxes = _prim_boxes(prims[scene.read_slot_to_prim()])
+            assert _check_query_tree(nodes, boxes[:, :3], boxes[:, 3:]) <= 64
+        t, prim, _ = scene.intersect(rays)
+        assert np.array_equal(prim, prim_o) and np.array_equal(t[t_o >= 0], t_o[t_o >= 0])
+        t_c, prim_c, _ = scene.intersect(rays, flags=capi.PTB_FLAG_CERTIFIED_CLOSEST)
+        assert np.array_equal(prim_c, prim) and np.array_equal(t_c[t >= 0], t[t >= 0])
+        assert np.array_equal(scene.occluded(shadow)[0], want_occluded)
+        scene.close()
 
 
 def test_device_build_at_full_size(ctx, monkeypatch):
