@@ -485,12 +485,30 @@ def run_b200_arm(args):
 
     # ---- e2e through the reference-facing API with host buffers: processJob (one call -> the whole image in host memory).
     # On several GPUs rank 0 alone calls it, with ptb::RenderControl::devices = N: the library itself renders on all N GPUs
-    # of the node (ptb_render_multi: a host thread and a scene replica per GPU, NVLink gather of the tiles, one D2H) while
-    # the other ranks wait on the host.
+    # of the node (ptb_render_multi: a host thread and a scene replica per GPU, NVLink gather of the tiles, one D2H) after
+    # the other ranks have left.
     def host_barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier(group=control)
+
+    # On several GPUs the other ranks have done their part (every collective is behind us): they leave now, so that the
+    # one-call path below owns the GPUs the way a single-process caller of processJob does.  (Measured with the ranks
+    # merely idling on their GPUs instead: the replica sharing a GPU with another process's context ran 1.5-2x slower.)
+    if dist is not None:
+        dist.barrier(group=control)
+        dist.destroy_process_group()
+        dist = None
+        if rank != 0:
+            return
+        deadline = time.time() + 120.0
+        for k in range(1, world):
+            device = (local_rank + k) % torch.cuda.device_count()  # where Scene::deviceScenes puts replica k
+            while time.time() < deadline:
+                free_bytes, total_bytes = torch.cuda.mem_get_info(device)
+                if total_bytes - free_bytes < (3 << 30):  # the other rank's pool and buffers are gone
+                    break
+                time.sleep(0.25)
 
     e2e_ms = []
     e2e_devices = 1
@@ -513,11 +531,6 @@ def run_b200_arm(args):
     if rank == 0:
         b200.set_devices(1)
     e2e_value = (job_samples / args.steps) / (np.mean(e2e_ms) / 1e3) / 1e6 if rank == 0 else 0.0
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline and os.path.exists(pth.REF_FAST):
@@ -576,8 +589,6 @@ def run_b200_arm(args):
                         f"certified SAH walk; {totals['retraced']} of {totals['closest']} closest-hit rays had no certificate and were re-traced on the reference tree"),
     }
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 

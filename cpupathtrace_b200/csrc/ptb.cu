@@ -2735,14 +2735,20 @@ int ptb_render_multi(ptb_scene *const *replicas, int32_t n, const ptb_camera *ca
     std::vector<ReplicaProgress> sinks(static_cast<size_t>(n));
     std::vector<int> statuses(static_cast<size_t>(n), PTB_OK);
     std::vector<std::string> errors(static_cast<size_t>(n));
+    const bool log_multi = envLong("PTB_LOG_MULTI", 0) != 0;
+    const double t_begin = nowSeconds();
+    std::vector<ptb_render_stats> own_stats(static_cast<size_t>(n));
+    std::vector<double> wall(static_cast<size_t>(n), 0.0);
     auto render_share = [&](int i) {
         ptb_render_opts mine = *opts;
         mine.shard_index = i;
         mine.shard_count = n;
         mine.flags |= PTB_FLAG_DEVICE_IO;
         sinks[i] = ReplicaProgress{&all, i};
-        statuses[i] = ptb_render_with_progress(replicas[i], camera, &mine, x0, y0, w, h, replicas[i]->ctx->multi_image.as<float>(), stats != nullptr ? &stats[i] : nullptr,
+        const double t0 = nowSeconds();
+        statuses[i] = ptb_render_with_progress(replicas[i], camera, &mine, x0, y0, w, h, replicas[i]->ctx->multi_image.as<float>(), stats != nullptr ? &stats[i] : &own_stats[i],
                                                progress != nullptr ? replicaProgress : nullptr, &sinks[i]);
+        wall[i] = nowSeconds() - t0;
         if(statuses[i] != PTB_OK) {
             errors[i] = g_last_error; // thread-local: carried back to the caller's thread below
         }
@@ -2820,6 +2826,15 @@ int ptb_render_multi(ptb_scene *const *replicas, int32_t n, const ptb_camera *ca
     }
     PTB_CUDA(cudaStreamSynchronize(ctx->stream));
     PTB_CUDA(cudaGetLastError());
+    if(log_multi) {
+        for(int i = 0; i < n; i++) {
+            const ptb_render_stats &st = stats != nullptr ? stats[i] : own_stats[static_cast<size_t>(i)];
+            std::fprintf(stderr, "[ptb] render_multi: replica %d on device %d: %.1f ms wall, %.1f ms on the device, %llu samples, %llu bounce iterations\n", i,
+                         replicas[i]->ctx->device, wall[static_cast<size_t>(i)] * 1e3, st.device_ms_total, static_cast<unsigned long long>(st.samples),
+                         static_cast<unsigned long long>(st.bounce_iterations));
+        }
+        std::fprintf(stderr, "[ptb] render_multi: whole call %.1f ms\n", (nowSeconds() - t_begin) * 1e3);
+    }
     if(progress != nullptr) {
         uint64_t total = 0;
         for(int i = 0; i < n; i++) {
