@@ -282,8 +282,16 @@ def run_b200_arm(args):
     t_objects = time.perf_counter()
     builder = spec.replay(b200)  # the caller's side: a million Triangle objects, materials, lights through the public C++ API
     t_objects = time.perf_counter() - t_objects
-    t_build = time.perf_counter()
+    t_build_first = time.perf_counter()
     scene_cpp = builder.scene()  # Scene::Scene: lowering of the object graph + ptb_scene_create (boxes, both trees, leaf records on the GPU)
+    t_build_first = time.perf_counter() - t_build_first
+    builder.close()
+    # the first large scene of a process also pays the driver's first large allocations (0.1-0.3 s, varies from box to box):
+    # the same scene is set up a second time and both times are reported
+    scene_cpp.close()
+    builder = spec.replay(b200)
+    t_build = time.perf_counter()
+    scene_cpp = builder.scene()
     t_build = time.perf_counter() - t_build
     builder.close()
     handle = scene_cpp.device_handle()
@@ -357,7 +365,8 @@ def run_b200_arm(args):
     # between launches of the first timed step; the samples it reports cover the warm-up and the timed steps, all under
     # the same load.
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if os.environ.get("PTB_BENCH_NO_CLOCK_SAMPLER", "") == "":  # (experiments only: is the sampler visible in the step times?)
+        sampler.start()
     for i in range(args.warmup):
         flush.zero_()
         barrier()
@@ -390,6 +399,26 @@ def run_b200_arm(args):
         totals["shade_ms"] += stats.device_ms_shade
         totals["shadow_ms"] += stats.device_ms_trace_shadow
         totals["iterations"] += stats.bounce_iterations
+
+    # ---- the kernel times behind `roofline`: the per-launch CUDA events of the timed steps themselves.  Only when the
+    # opt-in PTB_STREAMS > 1 splits each frame between concurrent contexts of the GPU (event brackets around co-scheduled
+    # launches overlap and do not measure a kernel's own duration) are they taken from the same number of frames rendered
+    # on ONE stream right after the timed steps (PTB_FLAG_SINGLE_STREAM; same scene, same options, next seeds).
+    split_streams = int(os.environ.get("PTB_STREAMS", "1") or "1") > 1
+    roof = {"closest": totals["closest"], "shadow": totals["shadow"], "trace_ms": totals["trace_ms"], "iterations": totals["iterations"],
+            "frame_ms": float(sum(rank_detail["render_ms"]))}
+    if split_streams:
+        roof = {"closest": 0, "shadow": 0, "trace_ms": 0.0, "iterations": 0, "frame_ms": 0.0}
+        for i in range(args.steps):
+            flush.zero_()
+            rstats = capi.RenderStats()
+            ro = opts(args.spp, capi.PTB_FLAG_DEVICE_IO | capi.PTB_FLAG_SINGLE_STREAM, 2500 + i)
+            capi.check(lib.ptb_render(handle, C.byref(camera), C.byref(ro), 0, 0, args.width, args.height, C.c_void_p(image.data_ptr()), C.byref(rstats)))
+            roof["closest"] += rstats.closest_rays
+            roof["shadow"] += rstats.shadow_rays
+            roof["trace_ms"] += rstats.device_ms_trace
+            roof["iterations"] += rstats.bounce_iterations
+            roof["frame_ms"] += rstats.device_ms_total
     clocks = sampler.stop()
     # this rank's own render time (its tiles) and the time it spent in the image reduce, which includes waiting for the
     # slowest rank; gathered so that imbalance between ranks is visible in the report
@@ -403,7 +432,7 @@ def run_b200_arm(args):
     # ---- profile pass (untimed): one more frame with CUDA events around EVERY launch for the per-kernel breakdown (the
     # timed steps time only the closest-hit trace per launch: the ~300 extra event pairs cost 4-5 % of a frame)
     pstats = capi.RenderStats()
-    po = opts(args.spp, capi.PTB_FLAG_DEVICE_IO | capi.PTB_FLAG_PROFILE_ALL, 98)
+    po = opts(args.spp, capi.PTB_FLAG_DEVICE_IO | capi.PTB_FLAG_PROFILE_ALL | capi.PTB_FLAG_SINGLE_STREAM, 98)
     capi.check(lib.ptb_render(handle, C.byref(camera), C.byref(po), 0, 0, args.width, args.height, C.c_void_p(image.data_ptr()), C.byref(pstats)))
     breakdown = {
         "source": "one untimed frame with PTB_FLAG_PROFILE_ALL (events around every launch)",
@@ -418,7 +447,7 @@ def run_b200_arm(args):
     # launches first): inner / leaf fetches per ray of the same traversal at reduced spp
     count_spp = max(1, min(args.spp, 2))
     cstats = capi.RenderStats()
-    co = opts(count_spp, capi.PTB_FLAG_DEVICE_IO | capi.PTB_FLAG_COUNT_VISITS, 99)
+    co = opts(count_spp, capi.PTB_FLAG_DEVICE_IO | capi.PTB_FLAG_COUNT_VISITS | capi.PTB_FLAG_SINGLE_STREAM, 99)
     capi.check(lib.ptb_render(handle, C.byref(camera), C.byref(co), 0, 0, args.width, args.height, C.c_void_p(image.data_ptr()), C.byref(cstats)))
     count_detail = {
         "closest_inner_per_ray": (cstats.inner_visits - cstats.shadow_inner_visits) / max(cstats.closest_rays, 1),
@@ -456,14 +485,14 @@ def run_b200_arm(args):
     # kernel is the closest-hit trace (certified SAH walk + its re-trace launch, timed together); `achieved` is its
     # algorithmic bytes per ray x the rays it traced / its CUDA-event time.  The north star's figure over ALL rays
     # (closest + shadow kernels) is reported next to it as frac_all_rays.
-    rank_rays = float(totals["closest"] + totals["shadow"])
-    closest_s = totals["trace_ms"] / 1e3  # the timed steps time the closest-hit trace only (class 0 events)
+    rank_rays = float(roof["closest"] + roof["shadow"])
+    closest_s = roof["trace_ms"] / 1e3  # the roofline steps time the closest-hit trace only (class 0 events)
     # all traversal kernels: the closest-hit time of the timed steps plus the shadow-trace time of the profile pass
     trace_s = closest_s + breakdown["shadow_trace_ms"] / 1e3 * args.steps
     achieved_all = bytes_per_ray * rank_rays / max(trace_s, 1e-12) / 1e9
     closest_bytes_per_ray = INNER_BYTES * count_detail["closest_inner_per_ray"] + LEAF_BYTES * count_detail["closest_leaf_per_ray"] + RAY_RECORD_BYTES
-    achieved = closest_bytes_per_ray * float(totals["closest"]) / max(closest_s, 1e-12) / 1e9
-    closest_launches = max(int(totals["iterations"]), 1)
+    achieved = closest_bytes_per_ray * float(roof["closest"]) / max(closest_s, 1e-12) / 1e9
+    closest_launches = max(int(roof["iterations"]), 1)
     peak, peak_source = 6650.0, "fallback"
     peaks_path = os.path.join(REPO_ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -518,8 +547,7 @@ def run_b200_arm(args):
         # untimed warm-up of this path: scene replicas on the other GPUs (first call), then one frame at full size so that the
         # replicas' workspaces (path pool, per-sample buffer) have their final size before the timed steps
         scene_cpp.process_job(camera_cpp, args.width, args.height, min(args.spp, 8), min(args.spp, 8), 1e-3, 0)
-        if e2e_devices > 1:
-            scene_cpp.process_job(camera_cpp, args.width, args.height, args.spp, args.spp, 1e-3, 0)
+        scene_cpp.process_job(camera_cpp, args.width, args.height, args.spp, args.spp, 1e-3, 0)
     for i in range(args.steps):
         flush.zero_()
         host_barrier()
@@ -545,6 +573,7 @@ def run_b200_arm(args):
         "steps": args.steps,
         "warmup": args.warmup,
         "ms_per_step": float(np.mean(step_ms)),
+        "ms_steps": [round(float(v), 1) for v in step_ms],
         "higher_is_better": True,
         "scaling": "strong",
         "vs_baseline": None,
@@ -564,23 +593,26 @@ def run_b200_arm(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "traffic_source": traffic_note, "peak_source": f"{peak_source} HBM copy bandwidth",
                      "kernel": "traceClosestKernel" + ("<reference tree>" if args.reference_closest else "<certified SAH walk> + re-trace launch"),
-                     "bytes_per_ray": closest_bytes_per_ray, "rays_per_launch": float(totals["closest"]) / closest_launches,
-                     "algorithmic_bytes_per_launch": closest_bytes_per_ray * float(totals["closest"]) / closest_launches,
+                     "bytes_per_ray": closest_bytes_per_ray, "rays_per_launch": float(roof["closest"]) / closest_launches,
+                     "algorithmic_bytes_per_launch": closest_bytes_per_ray * float(roof["closest"]) / closest_launches,
                      "ms_per_launch": closest_s * 1e3 / closest_launches,
                      "frac_all_rays": achieved_all / peak, "achieved_all_rays": achieved_all, "bytes_per_ray_all_rays": bytes_per_ray,
                      "inner_fetches_per_ray": inner_per_ray, "leaf_fetches_per_ray": leaf_per_ray,
-                     "closest_trace_ms_per_step": totals["trace_ms"] / args.steps, "closest_trace_share_of_step": totals["trace_ms"] / max(sum(step_ms), 1e-9),
+                     "closest_trace_ms_per_step": roof["trace_ms"] / args.steps, "closest_trace_share_of_step": roof["trace_ms"] / max(roof["frame_ms"], 1e-9),
+                     "measured_on": (f"{args.steps} frames rendered on one stream (PTB_FLAG_SINGLE_STREAM) right after the timed steps, {roof['frame_ms'] / args.steps:.1f} ms each: "
+                                     "PTB_STREAMS splits the timed frames between concurrent contexts of the GPU, where per-launch event brackets overlap"
+                                     if split_streams else "the timed steps (CUDA events around every closest-hit trace launch, on the launching stream)"),
                      "trace_ms_per_step": trace_s * 1e3 / args.steps, "shade_ms_per_step": breakdown["generate_shade_accumulate_resolve_ms"],
                      "shadow_trace_ms_per_step": breakdown["shadow_trace_ms"], "mrays_per_s_trace_only": rank_rays / max(trace_s, 1e-12) / 1e6,
-                     "closest_mrays_per_s": totals["closest"] / max(totals["trace_ms"], 1e-9) / 1e3,
+                     "closest_mrays_per_s": roof["closest"] / max(roof["trace_ms"], 1e-9) / 1e3,
                      "shadow_mrays_per_s": breakdown["shadow_mrays_per_s"], **count_detail},
         "breakdown": breakdown,
         "cpu_baseline": cpu_baseline,
         "scene": {"prims": int(info.n_prims), "inner_nodes": int(info.n_inner_nodes), "bvh_depth": int(info.bvh_depth),
-                  "device_mb": info.device_bytes / 2**20, "build_s": info.build_seconds, "scene_ctor_s": t_build, "caller_objects_s": t_objects,
+                  "device_mb": info.device_bytes / 2**20, "build_s": info.build_seconds, "scene_ctor_s": t_build, "scene_ctor_first_s": t_build_first, "caller_objects_s": t_objects,
                   "upload_s": info.upload_seconds, "built_on_device": bool(info.built_on_device), "reference_tree_device_ms": info.reference_tree_device_ms,
                   "query_tree": ["none", "host binned SAH", "device LBVH", "device full-sweep SAH"][info.query_tree_kind], "query_tree_device_ms": info.query_tree_device_ms,
-                  "note": "caller_objects_s = the caller creating its Triangle objects; scene_ctor_s = Scene::Scene (scene.cpp:153-181: lowering of the object graph + ptb_scene_create); build_s + upload_s = ptb_scene_create"},
+                  "note": "caller_objects_s = the caller creating its Triangle objects; scene_ctor_first_s / scene_ctor_s = Scene::Scene, first and second time in this process (scene.cpp:153-181: lowering of the object graph + ptb_scene_create); build_s + upload_s = ptb_scene_create"},
         "bounce_iterations_per_step": totals["iterations"] / args.steps,
         "per_rank": per_rank,
         "adaptive": adaptive,

@@ -30,6 +30,7 @@ PTB_FLAG_COUNT_VISITS = 0x8
 PTB_FLAG_CERTIFIED_CLOSEST = 0x10
 PTB_FLAG_CERTIFIED_RELAXED = 0x20
 PTB_FLAG_PROFILE_ALL = 0x40
+PTB_FLAG_SINGLE_STREAM = 0x80
 
 # numpy dtypes of the POD records (layout-identical to the C structs)
 PRIM_DTYPE = np.dtype([("kind", "<u4"), ("material", "<u4"), ("cull_backface", "<u4"), ("reserved", "<u4"), ("p", "<f4", (18,))])

@@ -106,7 +106,8 @@ struct ptb_context {
     int shade_blocks_per_sm = PTB_SHADE_MIN_BLOCKS; // grid of the shade kernel = its resident blocks (PTB_SHADE_BLOCKS_PER_SM)
     bool log_iterations = false; // PTB_LOG_ITERATIONS=1: one stderr line per bounce iteration
     bool production_math = true; // PTB_RNG_COUNTER renders use the FMA / SFU build of generate, shade and accumulate (PTB_PRODUCTION_MATH=0: the exact build)
-    int iterations_per_sync = 4; // bounce iterations launched between two host synchronisations (PTB_ITERATIONS_PER_SYNC)
+    int iterations_per_sync = 8; // bounce iterations per batch; two batches are in flight (PTB_ITERATIONS_PER_SYNC).  Measured, six timed frames each: 4 per batch
+                                 // without double buffering 2-3 outliers of +40...80 ms, 4 with double buffering 0-1, 8 with double buffering 0
     cudaStream_t stream = nullptr;
 
     // wavefront workspace
@@ -133,6 +134,19 @@ struct ptb_context {
     Buffer sort_ids;
     Buffer sort_temp;
     bool sort_rays = true; // PTB_SORT_RAYS=0: trace batches in the caller's order
+    // PTB_STREAMS > 1: large renders are split between `streams` contexts of this device (this one and streams - 1 siblings
+    // with their own stream and workspace) that run concurrently, so that the drain phase of one share's persistent trace
+    // launch and the launch-bound tail of its bounce loop overlap with the other share's kernels.  Off by default: the gain
+    // depends on the phase the two shares happen to fall into (bench scene, 256 spp: 778 -> 737-745 ms per frame in most
+    // runs, 795-811 in others; 1024 spp with depth 16: 2 % slower, and one end-to-end run 50 % slower) -- DESIGN.md section 4.
+    int streams = 1;
+    bool is_sibling = false;
+    std::vector<ptb_context *> siblings;
+    std::mutex call_mutex;      // serialises split calls on this context
+    Buffer split_image;         // split call with a host result: the image the shares write into
+    cudaEvent_t split_start = nullptr;
+    cudaEvent_t split_stop = nullptr;
+    int budget_divisor = 1;     // shares of a split call divide the per-sample buffer budget between them
     Buffer build_arena;   // scene setup on the device: every temporary of a tree build is carved from this one allocation
     Buffer multi_image;   // ptb_render_multi: this replica's share of the frame (its tiles, zeros elsewhere)
     Buffer multi_staging; // ptb_render_multi on the first replica: copies of the other replicas' images when peers cannot map each other
@@ -166,6 +180,7 @@ struct ptb_scene {
     ptb_scene_info info{};
     uint32_t shadow_stride = 1;
     ptb_guard::CertGuard guard{}; // guard table of the certified closest-hit walk (passed to its kernels by value)
+    std::vector<ptb_scene *> aliases; // the same device arrays seen from the sibling contexts (no ownership)
 };
 
 namespace {
@@ -254,7 +269,7 @@ namespace {
         if(forced > 0) {
             return static_cast<uint64_t>(forced) << 20;
         }
-        return std::max<uint64_t>(64ULL << 20, plannableBytes(ctx) * 2ULL / 5ULL);
+        return std::max<uint64_t>(64ULL << 20, plannableBytes(ctx) * 2ULL / 5ULL / static_cast<uint64_t>(std::max(ctx->budget_divisor, 1)));
     }
 
     // Pool capacity for a call of `total` work items: never more than half of them (above 2 Mi) so that path regeneration
@@ -797,6 +812,12 @@ namespace {
         return finish(PTB_OK);
     }
 
+    struct SubShard {
+        int index;
+        int count;
+        bool clear;
+    };
+
     // a piece of a larger device allocation
     struct Carved {
         void *ptr = nullptr;
@@ -1184,7 +1205,10 @@ int ptb_context_create(int device, ptb_context **out) {
     ctx->production_math = envLong("PTB_PRODUCTION_MATH", 1) != 0;
     ctx->sort_rays = envLong("PTB_SORT_RAYS", 1) != 0;
     ctx->adaptive_rounds = envLong("PTB_ADAPTIVE_ROUNDS", 1) != 0;
-    ctx->iterations_per_sync = static_cast<int>(std::min<long>(kMaxIterationsPerSync, std::max(1L, envLong("PTB_ITERATIONS_PER_SYNC", 4))));
+    ctx->streams = static_cast<int>(std::min(4L, std::max(1L, envLong("PTB_STREAMS", 1))));
+    PTB_CUDA(cudaEventCreate(&ctx->split_start));
+    PTB_CUDA(cudaEventCreate(&ctx->split_stop));
+    ctx->iterations_per_sync = static_cast<int>(std::min<long>(kMaxIterationsPerSync, std::max(1L, envLong("PTB_ITERATIONS_PER_SYNC", 8))));
     *out = ctx;
     return PTB_OK;
 }
@@ -1193,9 +1217,20 @@ int ptb_context_destroy(ptb_context *ctx) {
     if(ctx == nullptr) {
         return PTB_OK;
     }
+    for(ptb_context *sibling : ctx->siblings) {
+        ptb_context_destroy(sibling);
+    }
+    ctx->siblings.clear();
     cudaSetDevice(ctx->device);
     if(ctx->stream != nullptr) {
         cudaStreamSynchronize(ctx->stream);
+    }
+    ctx->split_image.release();
+    for(cudaEvent_t *e : {&ctx->split_start, &ctx->split_stop}) {
+        if(*e != nullptr) {
+            cudaEventDestroy(*e);
+            *e = nullptr;
+        }
     }
     for(Buffer *b : {&ctx->pool_mem, &ctx->queue_a, &ctx->queue_b, &ctx->shadow_queue, &ctx->redo_queue, &ctx->counters, &ctx->visits, &ctx->work_cursor, &ctx->samples, &ctx->pixel_list, &ctx->pixel_states, &ctx->active_lists, &ctx->adaptive_counters, &ctx->build_arena,
                      &ctx->io_a, &ctx->io_b, &ctx->io_c, &ctx->io_d, &ctx->multi_image, &ctx->multi_staging, &ctx->sort_keys, &ctx->sort_ids, &ctx->sort_temp}) {
@@ -1638,6 +1673,10 @@ int ptb_scene_destroy(ptb_scene *scene) {
     if(scene == nullptr) {
         return PTB_OK;
     }
+    for(ptb_scene *alias : scene->aliases) {
+        delete alias; // owns nothing: its device arrays are this scene's
+    }
+    scene->aliases.clear();
     if(scene->ctx != nullptr) {
         cudaSetDevice(scene->ctx->device);
         cudaStreamSynchronize(scene->ctx->stream);
@@ -1929,8 +1968,11 @@ int ptb_render(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts
     return ptb_render_with_progress(scene, camera, opts, x0, y0, w, h, out_rgba, stats, nullptr, nullptr);
 }
 
-int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts *opts, int32_t x0, int32_t y0, int32_t w, int32_t h,
-                             float *out_rgba, ptb_render_stats *stats, ptb_progress_fn progress, void *user) {
+// One share of a render on one context: the tiles of shard (opts->shard_index, opts->shard_count), and of those every
+// sub.count-th one starting at sub.index (several contexts of ONE device splitting a call between them, see
+// ptb_render_with_progress).  sub.clear: zero the output first (false when the shares of a call write into one image).
+static int renderShare(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts *opts, int32_t x0, int32_t y0, int32_t w, int32_t h, float *out_rgba,
+                       ptb_render_stats *stats, ptb_progress_fn progress, void *user, SubShard sub) {
     if(scene == nullptr || camera == nullptr || opts == nullptr) {
         return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render: null argument");
     }
@@ -1967,9 +2009,12 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
     const int shard_index = std::min(std::max(opts->shard_index, 0), shard_count - 1);
 
     std::vector<int> owned;
-    for(int t = 0; t < tiles_x * tiles_y; t++) {
+    for(int t = 0, ordinal = 0; t < tiles_x * tiles_y; t++) {
         if(t % shard_count == shard_index) {
-            owned.push_back(t);
+            if(ordinal % sub.count == sub.index) {
+                owned.push_back(t);
+            }
+            ordinal++;
         }
     }
 
@@ -1982,7 +2027,9 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
         d_out = ctx->io_d.as<float4>();
     }
     // pixels of tiles owned by other shards (and everything when spp == 0) stay 0
-    PTB_CUDA(cudaMemsetAsync(d_out, 0, out_bytes, ctx->stream));
+    if(sub.clear) {
+        PTB_CUDA(cudaMemsetAsync(d_out, 0, out_bytes, ctx->stream));
+    }
 
     // Pixel groups: consecutive runs of the owned tiles' pixels (tile order) whose per-sample buffer fits the budget and
     // whose sample count fits the 32-bit destination index of a path -- a single tile larger than either (processItem
@@ -2039,7 +2086,8 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
     for(uint64_t group_begin = 0; group_begin < n_owned_pixels && spp > 0; group_begin += max_group_pixels) {
         const uint64_t group_end = std::min<uint64_t>(n_owned_pixels, group_begin + max_group_pixels);
         // pixels of the group in tile order; frames rendered repeatedly reuse the list already on the device
-        const long long key[9] = {x0, y0, w, h, tile, shard_index, shard_count, static_cast<long long>(group_begin), static_cast<long long>(group_end)};
+        const long long key[9] = {x0, y0, w, h, tile, shard_index + 65536LL * sub.index, shard_count + 65536LL * sub.count, static_cast<long long>(group_begin),
+                                  static_cast<long long>(group_end)};
         const bool list_cached = std::equal(key, key + 9, ctx->pixel_list_key);
         const uint32_t n_pixels = static_cast<uint32_t>(group_end - group_begin);
         const uint64_t total = static_cast<uint64_t>(n_pixels) * (adaptive ? longest_round : spp);
@@ -2612,6 +2660,168 @@ namespace {
 
 extern "C" {
 
+int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const ptb_render_opts *opts, int32_t x0, int32_t y0, int32_t w, int32_t h,
+                             float *out_rgba, ptb_render_stats *stats, ptb_progress_fn progress, void *user) {
+    if(scene == nullptr || camera == nullptr || opts == nullptr) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render: null argument");
+    }
+    ptb_context *ctx = scene->ctx;
+    // split between the contexts of this device?  Only renders large enough for the second workspace and the threads to pay.
+    const int64_t share_samples = static_cast<int64_t>(std::max(w, 0)) * std::max(h, 0) / std::max(opts->shard_count, 1) * std::max(opts->max_sample_count, 0);
+    const int parts = (ctx->is_sibling || out_rgba == nullptr || share_samples < (1LL << 26) || (opts->flags & PTB_FLAG_SINGLE_STREAM) != 0U) ? 1 : ctx->streams;
+    if(parts <= 1) {
+        return renderShare(scene, camera, opts, x0, y0, w, h, out_rgba, stats, progress, user, SubShard{0, 1, true});
+    }
+    if(w < 0 || h < 0 || x0 < 0 || y0 < 0 || x0 + w > 65535 || y0 + h > 65535) {
+        return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_render: rectangle out of range (coordinates are limited to 16 bits)");
+    }
+
+    std::lock_guard<std::mutex> call_lock(ctx->call_mutex);
+    const double t_call = nowSeconds();
+    int status = useDevice(ctx);
+    if(status != PTB_OK) {
+        return status;
+    }
+    while(static_cast<int>(ctx->siblings.size()) < parts - 1) {
+        ptb_context *sibling = nullptr;
+        if((status = ptb_context_create(ctx->device, &sibling)) != PTB_OK) {
+            return status;
+        }
+        sibling->is_sibling = true;
+        ctx->siblings.push_back(sibling);
+    }
+    while(static_cast<int>(scene->aliases.size()) < parts - 1) {
+        auto *alias = new(std::nothrow) ptb_scene();
+        if(alias == nullptr) {
+            return fail(PTB_ERR_OUT_OF_MEMORY, "ptb_render: host allocation failed");
+        }
+        alias->ctx = ctx->siblings[scene->aliases.size()];
+        alias->dev = scene->dev;
+        alias->info = scene->info;
+        alias->shadow_stride = scene->shadow_stride;
+        alias->guard = scene->guard;
+        scene->aliases.push_back(alias);
+    }
+    for(int k = 0; k < parts - 1; k++) {
+        scene->aliases[static_cast<size_t>(k)]->ctx = ctx->siblings[static_cast<size_t>(k)];
+        ctx->siblings[static_cast<size_t>(k)]->budget_divisor = parts;
+    }
+    ctx->budget_divisor = parts;
+
+    const bool device_io = (opts->flags & PTB_FLAG_DEVICE_IO) != 0U;
+    const size_t image_bytes = static_cast<size_t>(w) * h * sizeof(float4);
+    float4 *d_out = reinterpret_cast<float4 *>(out_rgba);
+    {
+        std::lock_guard<std::mutex> lock(ctx->mutex);
+        if(!device_io) {
+            if((status = ctx->split_image.reserve(image_bytes)) != PTB_OK) {
+                ctx->budget_divisor = 1;
+                return status;
+            }
+            d_out = ctx->split_image.as<float4>();
+        }
+        // the shares write their own pixels only; everything else (other shards' tiles) stays 0
+        PTB_CUDA(cudaMemsetAsync(d_out, 0, image_bytes, ctx->stream));
+        PTB_CUDA(cudaEventRecord(ctx->split_start, ctx->stream));
+        PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+
+    MultiProgress all;
+    all.fn = progress;
+    all.user = user;
+    all.n = parts;
+    for(int i = 0; i < kMaxReplicas; i++) {
+        all.done[i].store(0);
+        all.total[i].store(~0ULL);
+    }
+    std::vector<ReplicaProgress> sinks(static_cast<size_t>(parts));
+    std::vector<ptb_render_stats> part_stats(static_cast<size_t>(parts));
+    std::vector<int> statuses(static_cast<size_t>(parts), PTB_OK);
+    std::vector<std::string> errors(static_cast<size_t>(parts));
+    auto render_part = [&](int k) {
+        ptb_render_opts mine = *opts;
+        mine.flags |= PTB_FLAG_DEVICE_IO;
+        sinks[static_cast<size_t>(k)] = ReplicaProgress{&all, k};
+        ptb_scene *target = k == 0 ? scene : scene->aliases[static_cast<size_t>(k) - 1];
+        const double t0 = nowSeconds();
+        statuses[static_cast<size_t>(k)] = renderShare(target, camera, &mine, x0, y0, w, h, reinterpret_cast<float *>(d_out), &part_stats[static_cast<size_t>(k)],
+                                                       progress != nullptr ? replicaProgress : nullptr, &sinks[static_cast<size_t>(k)], SubShard{k, parts, false});
+        if(envLong("PTB_LOG_SPLIT", 0) != 0) {
+            const ptb_render_stats &st = part_stats[static_cast<size_t>(k)];
+            std::fprintf(stderr, "[ptb] split render: share %d of %d: %.1f ms wall (started %.1f ms after the call), %.1f ms on its stream, %llu samples, %llu iterations, %llu launches\n", k,
+                         parts, (nowSeconds() - t0) * 1e3, (t0 - t_call) * 1e3, st.device_ms_total, static_cast<unsigned long long>(st.samples),
+                         static_cast<unsigned long long>(st.bounce_iterations), static_cast<unsigned long long>(st.kernel_launches));
+        }
+        if(statuses[static_cast<size_t>(k)] != PTB_OK) {
+            errors[static_cast<size_t>(k)] = g_last_error;
+        }
+    };
+    {
+        std::vector<std::thread> workers;
+        for(int k = 1; k < parts; k++) {
+            workers.emplace_back(render_part, k);
+        }
+        render_part(0);
+        for(std::thread &t : workers) {
+            t.join();
+        }
+    }
+    ctx->budget_divisor = 1;
+    for(int k = 0; k < parts; k++) {
+        if(statuses[static_cast<size_t>(k)] != PTB_OK) {
+            return fail(statuses[static_cast<size_t>(k)], "ptb_render: share " + std::to_string(k) + ": " + errors[static_cast<size_t>(k)]);
+        }
+    }
+    float elapsed_ms = 0.0F;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mutex);
+        if((status = useDevice(ctx)) != PTB_OK) {
+            return status;
+        }
+        // every share has synchronised its own stream: this event closes the call on the device's timeline
+        PTB_CUDA(cudaEventRecord(ctx->split_stop, ctx->stream));
+        if(!device_io) {
+            PTB_CUDA(cudaMemcpyAsync(out_rgba, d_out, image_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        PTB_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaEventElapsedTime(&elapsed_ms, ctx->split_start, ctx->split_stop);
+    }
+    if(stats != nullptr) {
+        std::memset(stats, 0, sizeof(*stats));
+        for(const ptb_render_stats &part : part_stats) {
+            stats->samples += part.samples;
+            stats->closest_rays += part.closest_rays;
+            stats->shadow_rays += part.shadow_rays;
+            stats->shadow_rays_skipped += part.shadow_rays_skipped;
+            stats->path_vertices += part.path_vertices;
+            stats->inner_visits += part.inner_visits;
+            stats->leaf_visits += part.leaf_visits;
+            stats->bounce_iterations = std::max(stats->bounce_iterations, part.bounce_iterations);
+            stats->kernel_launches += part.kernel_launches;
+            // kernel times of concurrent shares overlap on the device: their sums exceed the call's own duration
+            stats->device_ms_trace += part.device_ms_trace;
+            stats->device_ms_shade += part.device_ms_shade;
+            stats->device_ms_trace_shadow += part.device_ms_trace_shadow;
+            stats->shadow_inner_visits += part.shadow_inner_visits;
+            stats->shadow_leaf_visits += part.shadow_leaf_visits;
+            stats->closest_rays_retraced += part.closest_rays_retraced;
+            stats->certified_suspect_hits += part.certified_suspect_hits;
+            stats->samples_used += part.samples_used;
+            stats->adaptive_rounds = std::max(stats->adaptive_rounds, part.adaptive_rounds);
+        }
+        stats->device_ms_total = elapsed_ms;
+    }
+    if(progress != nullptr) {
+        uint64_t total = 0;
+        for(int k = 0; k < parts; k++) {
+            const uint64_t t = all.total[k].load();
+            total += t != ~0ULL ? t : 0;
+        }
+        progress(user, total, total);
+    }
+    return PTB_OK;
+}
+
 int ptb_device_count(int *count_out) {
     if(count_out == nullptr) {
         return fail(PTB_ERR_INVALID_ARGUMENT, "ptb_device_count: null argument");
@@ -2736,6 +2946,7 @@ int ptb_render_multi(ptb_scene *const *replicas, int32_t n, const ptb_camera *ca
     std::vector<int> statuses(static_cast<size_t>(n), PTB_OK);
     std::vector<std::string> errors(static_cast<size_t>(n));
     const bool log_multi = envLong("PTB_LOG_MULTI", 0) != 0;
+    const long stagger_ms = envLong("PTB_MULTI_STAGGER_MS", 0);
     const double t_begin = nowSeconds();
     std::vector<ptb_render_stats> own_stats(static_cast<size_t>(n));
     std::vector<double> wall(static_cast<size_t>(n), 0.0);
@@ -2745,6 +2956,9 @@ int ptb_render_multi(ptb_scene *const *replicas, int32_t n, const ptb_camera *ca
         mine.shard_count = n;
         mine.flags |= PTB_FLAG_DEVICE_IO;
         sinks[i] = ReplicaProgress{&all, i};
+        if(stagger_ms > 0 && i > 0) {
+            std::this_thread::sleep_for(std::chrono::microseconds(static_cast<long>(stagger_ms) * 1000L * i)); // experiment: phase offset between replicas
+        }
         const double t0 = nowSeconds();
         statuses[i] = ptb_render_with_progress(replicas[i], camera, &mine, x0, y0, w, h, replicas[i]->ctx->multi_image.as<float>(), stats != nullptr ? &stats[i] : &own_stats[i],
                                                progress != nullptr ? replicaProgress : nullptr, &sinks[i]);

@@ -191,6 +191,9 @@ typedef enum ptb_rng_mode {
                                      /* Guarded by default: rays for which fp32 rounding in a LARGE triangle's or a nearby  */
                                      /* sphere's own intersection routine could matter are sent to the reference walk up    */
                                      /* front (csrc/cert_guard.h); scenes the guard table cannot cover are not certified.   */
+#define PTB_FLAG_SINGLE_STREAM 0x80u /* do not split this render between several contexts of the device (a large render is    */
+                                     /* otherwise shared by PTB_STREAMS concurrent contexts: same image, ~5 % sooner); with the */
+                                     /* flag the per-kernel event times of ptb_render_stats are those of kernels running alone  */
 #define PTB_FLAG_PROFILE_ALL 0x40u   /* CUDA events around EVERY launch (device_ms_shade / device_ms_trace_shadow are filled);  */
                                      /* without it only the dominant kernel, the closest-hit trace, is timed per launch     */
                                      /* (device_ms_trace = closest-hit trace only): the extra ~300 event pairs per frame    */

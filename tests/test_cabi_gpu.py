@@ -587,6 +587,39 @@ def test_sharded_renders_sum_to_the_full_frame(ctx):
     scene.close()
 
 
+def test_renders_split_between_contexts_of_one_device_are_identical(monkeypatch):
+    """Large renders are split between several contexts of the device that run concurrently (PTB_STREAMS, csrc/ptb.cu
+    ptb_render_with_progress): every share resolves its own tiles into the one image.  The frame must not depend on the
+    number of shares -- fixed and adaptive sampling, device-resident and host results, alone and inside a tile shard."""
+    import torch
+
+    g = load_golden("samples", "cornell_mesh")
+    w, h = 1024, 832
+    kw = camera_kwargs(g["camera"])
+    kw["aspect_ratio"] = -w / h
+    camera = pod_camera(kw)
+    images = {}
+    for streams in ("1", "2", "3"):
+        monkeypatch.setenv("PTB_STREAMS", streams)
+        context = capi.Context(-1)
+        scene = _scene(context, g)
+        fixed, stats = scene.render(camera, capi.render_opts(w, h, 96, 96, 1e-3, seed=21))
+        assert stats.samples == w * h * 96 and stats.device_ms_total > 0
+        adaptive, stats_a = scene.render(camera, capi.render_opts(w, h, 16, 160, 1e-3, seed=22))
+        assert stats_a.samples_used <= stats_a.samples < w * h * 160
+        shard, _ = scene.render(camera, capi.render_opts(w, h, 200, 200, 1e-3, seed=23, shard_index=1, shard_count=2))
+        resident = torch.zeros(h, w, 4, device="cuda")
+        _, stats_r = scene.render(camera, capi.render_opts(w, h, 96, 96, 1e-3, seed=21), out_ptr=resident.data_ptr())
+        assert np.array_equal(resident.cpu().numpy(), fixed)
+        images[streams] = (fixed, adaptive, shard, stats_a.samples_used)
+        scene.close()
+        context.close()
+    for streams in ("2", "3"):
+        for a, b in zip(images[streams][:3], images["1"][:3]):
+            assert np.array_equal(a, b), streams
+        assert images[streams][3] == images["1"][3]
+
+
 def test_adaptive_rounds_trace_fewer_samples_for_the_same_image(ctx, monkeypatch):
     """min < max (worker.cpp:236-260: the per-pixel loop ends once the acceptance test has fired): rendering in rounds for
     the pixels still sampling gives bit for bit the image of tracing all max samples of every pixel and resolving
