@@ -15,6 +15,58 @@
 
 namespace ptb {
 
+    // Path-pool, queue and per-sample traffic is streamed: every array is read or written once per kernel and is far larger
+    // than the 126 MB L2, while the scene's nodes and primitives (233 MiB on the bench scene) are re-read by every ray.
+    // PTB_STREAM_HINTS=1 marks the former evict-first (ld.global.cs / st.global.cs) so that it does not push the scene out
+    // of L2 between two traversal launches; PTB_STREAM_HINTS=2 does so in the traversal kernels only (sld_t / sst_t).
+#ifndef PTB_STREAM_HINTS
+#define PTB_STREAM_HINTS 2 // measured on the bench scene: 1 -> trace -2 % but shade + accumulate +13 % (what shade writes is re-read at once by the
+                           // shadow trace and accumulate); 2 -> closest trace 316.4 -> 309.6 ms, shadow 166.7 -> 164.4 ms per frame, the rest unchanged
+#endif
+    template<typename T>
+    __device__ __forceinline__ T sld_t(const T *p) {
+#if PTB_STREAM_HINTS
+        return __ldcs(p);
+#else
+        return *p;
+#endif
+    }
+    template<typename T>
+    __device__ __forceinline__ void sst_t(T *p, T v) {
+#if PTB_STREAM_HINTS
+        __stcs(p, v);
+#else
+        *p = v;
+#endif
+    }
+    template<typename T>
+    __device__ __forceinline__ T sld(const T *p) {
+#if PTB_STREAM_HINTS == 1
+        return __ldcs(p);
+#else
+        return *p;
+#endif
+    }
+    template<typename T>
+    __device__ __forceinline__ void sst(T *p, T v) {
+#if PTB_STREAM_HINTS == 1
+        __stcs(p, v);
+#else
+        *p = v;
+#endif
+    }
+#if PTB_STREAM_HINTS == 1
+    template<>
+    __device__ __forceinline__ unsigned long sld<unsigned long>(const unsigned long *p) {
+        return static_cast<unsigned long>(__ldcs(reinterpret_cast<const unsigned long long *>(p)));
+    }
+    template<>
+    __device__ __forceinline__ void sst<unsigned long>(unsigned long *p, unsigned long v) {
+        __stcs(reinterpret_cast<unsigned long long *>(p), static_cast<unsigned long long>(v));
+    }
+#endif
+
+
     constexpr float kFloatMax = 3.402823466e+38F;
     constexpr float kPi = 3.14159274101257324219F;    // static_cast<float>(M_PI)
     constexpr float kTwoPi = 6.28318548202514648438F; // 2.0F * kPi (exact doubling)
@@ -134,6 +186,8 @@ namespace ptb {
     // One 256-bit read-only load (LDG.E.256, sm_100+): 32 bytes, 32-byte aligned, two float4 lanes per request.
     // Node records are fetched with two of these instead of four 128-bit loads, which halves the L1 wavefronts per
     // node visit (profiles/r01_ncu_trace_vote.md: l1tex__data_pipe_lsu_wavefronts was the top limiter at 71 %).
+    // (eviction priorities on these loads -- ld.global.nc.L2::evict_last, with and without L1::evict_last -- were measured in
+    // round 2: no effect on the trace kernels, 309.6 ms of closest-hit trace per frame either way)
     PTB_DEV void ld256(const float4 *p, float4 &a, float4 &b) {
         asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)

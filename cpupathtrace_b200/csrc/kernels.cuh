@@ -128,35 +128,35 @@ namespace ptb {
     // It is therefore not carried through the pool (constant lanes let the compiler drop the alpha arithmetic).
     template<typename RNG>
     PTB_DEV void loadPath(const PathPool &pool, uint32_t i, PathRegs<RNG> &p, uint32_t &flags) {
-        const float4 o = pool.ray_o[i];
-        const float4 d = pool.ray_d[i];
+        const float4 o = sld(&pool.ray_o[i]);
+        const float4 d = sld(&pool.ray_d[i]);
         p.ray_o = mk3(o.x, o.y, o.z);
         p.ray_d = mk3(d.x, d.y, d.z);
-        const float4 thr = pool.throughput[i];
-        const float4 rad = pool.radiance[i];
+        const float4 thr = sld(&pool.throughput[i]);
+        const float4 rad = sld(&pool.radiance[i]);
         p.throughput = V4{thr.x, thr.y, thr.z, 1.0F};
         p.radiance = V4{rad.x, rad.y, rad.z, 0.0F};
-        p.divisor = pool.divisor[i];
-        p.bounce_pd = pool.bounce_pd[i];
-        p.contribution_unweighted = pool.contribution[i];
-        const uint32_t st = pool.state[i];
+        p.divisor = sld(&pool.divisor[i]);
+        p.bounce_pd = sld(&pool.bounce_pd[i]);
+        p.contribution_unweighted = sld(&pool.contribution[i]);
+        const uint32_t st = sld(&pool.state[i]);
         p.path_length = static_cast<int>(st >> 8);
         flags = st & 0xFFU;
-        p.rng.state = pool.rng[i];
+        p.rng.state = sld(&pool.rng[i]);
         p.rng.counter = 0U;
     }
 
     template<typename RNG>
     PTB_DEV void storePath(const PathPool &pool, uint32_t i, const PathRegs<RNG> &p, uint32_t flags, uint32_t radiance_word) {
-        pool.ray_o[i] = make_float4(p.ray_o.x, p.ray_o.y, p.ray_o.z, 0.0F);
-        pool.ray_d[i] = make_float4(p.ray_d.x, p.ray_d.y, p.ray_d.z, 0.0F);
-        pool.throughput[i] = make_float4(p.throughput.x, p.throughput.y, p.throughput.z, 1.0F);
-        pool.radiance[i] = make_float4(p.radiance.x, p.radiance.y, p.radiance.z, __uint_as_float(radiance_word));
-        pool.divisor[i] = p.divisor;
-        pool.bounce_pd[i] = p.bounce_pd;
-        pool.contribution[i] = p.contribution_unweighted;
-        pool.state[i] = (static_cast<uint32_t>(p.path_length) << 8) | (flags & 0xFFU);
-        pool.rng[i] = p.rng.state;
+        sst(&pool.ray_o[i], make_float4(p.ray_o.x, p.ray_o.y, p.ray_o.z, 0.0F));
+        sst(&pool.ray_d[i], make_float4(p.ray_d.x, p.ray_d.y, p.ray_d.z, 0.0F));
+        sst(&pool.throughput[i], make_float4(p.throughput.x, p.throughput.y, p.throughput.z, 1.0F));
+        sst(&pool.radiance[i], make_float4(p.radiance.x, p.radiance.y, p.radiance.z, __uint_as_float(radiance_word)));
+        sst(&pool.divisor[i], p.divisor);
+        sst(&pool.bounce_pd[i], p.bounce_pd);
+        sst(&pool.contribution[i], p.contribution_unweighted);
+        sst(&pool.state[i], (static_cast<uint32_t>(p.path_length) << 8) | (flags & 0xFFU));
+        sst(&pool.rng[i], p.rng.state);
     }
 
     // ------------------------------------------------------------------------------------------------ generate
@@ -252,9 +252,9 @@ namespace ptb {
         warpTrace<MODE, COUNT>(
           MODE == kTraceCertified ? occlusionView(scene) : scene, vote, &counters[cursor_slot], count,
           [&](uint32_t k, V3 &o, V3 &d, float &limit) {
-              const uint32_t i = queue[k];
-              const float4 ro = pool.ray_o[i];
-              const float4 rd = pool.ray_d[i];
+              const uint32_t i = sld_t(&queue[k]);
+              const float4 ro = sld_t(&pool.ray_o[i]);
+              const float4 rd = sld_t(&pool.ray_d[i]);
               o = mk3(ro.x, ro.y, ro.z);
               d = mk3(rd.x, rd.y, rd.z);
               limit = 0.0F;
@@ -265,7 +265,7 @@ namespace ptb {
                   redo_queue[atomicAdd(&counters[kCountRedo], 1U)] = i;
               }
               else {
-                  pool.hit[i] = make_float2(h.t, __int_as_float(h.slot));
+                  sst_t(&pool.hit[i], make_float2(h.t, __int_as_float(h.slot)));
               }
           },
           visits, (MODE == kTraceCertified && guarded != 0) ? &guard : nullptr);
@@ -276,9 +276,9 @@ namespace ptb {
                                                                 uint32_t *__restrict__ counters, uint32_t any_hit, VisitCounters *visits) {
         const uint32_t count = counters[kCountShadow];
         auto fetch = [&](uint32_t k, V3 &o, V3 &d, float &limit) {
-            const uint32_t slot = shadow_queue[k];
-            const float4 so = pool.shadow_o[slot];
-            const float4 sd = pool.shadow_d[slot];
+            const uint32_t slot = sld_t(&shadow_queue[k]);
+            const float4 so = sld_t(&pool.shadow_o[slot]);
+            const float4 sd = sld_t(&pool.shadow_d[slot]);
             o = mk3(so.x, so.y, so.z);
             d = mk3(sd.x, sd.y, sd.z);
             limit = so.w;
@@ -287,7 +287,7 @@ namespace ptb {
         if(any_hit != 0U) {
             warpTrace<kTraceAnyHit, COUNT>(
               occlusionView(scene), vote, &counters[kCountFetchShadow], count, fetch,
-              [&](uint32_t slot, const Hit &h, bool) { pool.shadow_c[slot].w = h.slot < 0 ? 1.0F : 0.0F; }, visits);
+              [&](uint32_t slot, const Hit &h, bool) { sst_t(&pool.shadow_c[slot].w, h.slot < 0 ? 1.0F : 0.0F); }, visits);
         }
         else {
             // the reference's full closest-hit query (worker.cpp:84-86): unoccluded iff t < 0 or t >= |to_light| - epsilon
@@ -330,9 +330,9 @@ namespace ptb {
             float t = -1.0F;
             uint32_t slot = 0U;
             if(active) {
-                i = queue[k];
+                i = sld(&queue[k]);
                 loadPath(pool, i, p, flags);
-                const float2 h = pool.hit[i];
+                const float2 h = sld(&pool.hit[i]);
                 t = h.x;
                 slot = static_cast<uint32_t>(__float_as_int(h.y));
                 hit_surface = !(t < 0.0F);
@@ -351,9 +351,9 @@ namespace ptb {
                     }
                     if(n_shadow < pool.shadow_stride) {
                         const uint32_t s = shadow_base + n_shadow;
-                        pool.shadow_o[s] = make_float4(c.o.x, c.o.y, c.o.z, c.limit);
-                        pool.shadow_d[s] = make_float4(c.d.x, c.d.y, c.d.z, 0.0F);
-                        pool.shadow_c[s] = make_float4(c.contribution.x, c.contribution.y, c.contribution.z, 0.0F);
+                        sst(&pool.shadow_o[s], make_float4(c.o.x, c.o.y, c.o.z, c.limit));
+                        sst(&pool.shadow_d[s], make_float4(c.d.x, c.d.y, c.d.z, 0.0F));
+                        sst(&pool.shadow_c[s], make_float4(c.contribution.x, c.contribution.y, c.contribution.z, 0.0F));
                         n_shadow++;
                     }
                 });
@@ -397,7 +397,7 @@ namespace ptb {
             __syncthreads();
             const uint32_t base = block_base[parity] + exclusive;
             for(uint32_t j = 0U; j < n_shadow; j++) {
-                shadow_queue[base + j] = shadow_base + j;
+                sst(&shadow_queue[base + j], shadow_base + j);
             }
         }
 
@@ -443,7 +443,7 @@ namespace ptb {
             uint32_t i = 0U;
             if(active) {
                 i = queue[k];
-                float4 radiance = pool.radiance[i];
+                float4 radiance = sld(&pool.radiance[i]);
                 const uint32_t word = __float_as_uint(radiance.w);
                 const uint32_t n_shadow = word & kRadianceShadowMask;
                 if(pool.shadow_stride == 2U) {
@@ -466,7 +466,7 @@ namespace ptb {
                 else {
                     const size_t base = static_cast<size_t>(i) * pool.shadow_stride;
                     for(uint32_t j = 0U; j < n_shadow; j++) {
-                        const float4 c = pool.shadow_c[base + j];
+                        const float4 c = sld(&pool.shadow_c[base + j]);
                         if(c.w != 0.0F) {
                             radiance.x = radiance.x + c.x;
                             radiance.y = radiance.y + c.y;
