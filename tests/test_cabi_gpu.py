@@ -59,7 +59,7 @@ def test_golden_samples(ctx, name):
 
 
 @pytest.mark.parametrize("name", GOLDEN_SCENES)
-@pytest.mark.parametrize("spp", [(16, 16), (5, 10), (1, 1), (3, 64)])
+@pytest.mark.parametrize("spp", [(16, 16), (5, 10), (1, 1), (3, 64), (8, 200), (40, 1000), (1, 2), (2, 3), (63, 65)])
 def test_render_equals_oracle_per_sample_plus_resolve(ctx, name, spp):
     """ptb_render with one reference engine per (pixel, sample) == oracle getSample per (pixel, sample) followed by the
     oracle's restatement of processItem's per-pixel statistics (fixed spp, adaptive acceptance, candidate merge)."""
