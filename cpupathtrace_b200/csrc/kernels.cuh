@@ -872,13 +872,13 @@ namespace ptb {
     // Batch closest-hit query.  `index` (may be null) selects the rays of a re-trace pass: work item k is ray index[k].
     // MODE = kTraceCertified appends the rays without a certificate to `redo` (length *redo_count) instead of
     // writing their result.
-    template<int MODE, bool COUNT>
+    template<int MODE, bool COUNT, int SMEM>
     __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) intersectKernel(DeviceScene scene, VoteParams vote, const float *__restrict__ rays, const uint32_t *__restrict__ index,
                                                               const uint32_t *__restrict__ index_count, uint32_t n, float *__restrict__ t_out, int32_t *__restrict__ prim_out,
                                                               uint32_t *__restrict__ cursor, uint32_t *__restrict__ redo, uint32_t *__restrict__ redo_count,
                                                               VisitCounters *visits, const __grid_constant__ ptb_guard::CertGuard guard, int guarded) {
         const uint32_t count = (index != nullptr && index_count != nullptr) ? *index_count : n; // (an index without a count: a permutation of all n rays)
-        warpTrace<MODE, COUNT>(
+        warpTrace<MODE, COUNT, SMEM>(
           MODE == kTraceCertified ? occlusionView(scene) : scene, vote, cursor, count,
           [&](uint32_t k, V3 &o, V3 &d, float &limit) {
               const uint32_t ray = index != nullptr ? index[k] : k;
@@ -900,10 +900,10 @@ namespace ptb {
           visits, (MODE == kTraceCertified && guarded != 0) ? &guard : nullptr);
     }
 
-    template<bool COUNT>
+    template<bool COUNT, int SMEM>
     __global__ void __launch_bounds__(kBlock, PTB_TRACE_MIN_BLOCKS) occludedKernel(DeviceScene scene, VoteParams vote, const float *__restrict__ rays, const uint32_t *__restrict__ index,
                                                              uint32_t n, uint8_t *__restrict__ out, uint32_t *__restrict__ cursor, VisitCounters *visits) {
-        warpTrace<kTraceAnyHit, COUNT>(
+        warpTrace<kTraceAnyHit, COUNT, SMEM>(
           occlusionView(scene), vote, cursor, n,
           [&](uint32_t k, V3 &o, V3 &d, float &limit) {
               const uint32_t ray = index != nullptr ? index[k] : k;

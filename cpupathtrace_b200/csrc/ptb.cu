@@ -1069,6 +1069,7 @@ namespace {
     }
 
     constexpr uint32_t kSortThreshold = 1U << 16; // smaller batches are traced in the caller's order
+    constexpr uint64_t kBigSceneBytes = 512ULL << 20; // batch queries on scenes beyond this keep the bottom of the traversal stack in shared memory
 
     // Fills ctx->sort_ids (second half) with the numbers of the chunk's n rays in sort-key order; returns the device pointer
     // through `order`.  stride_floats: 6 (closest-hit rays) or 7 (rays with a limit).
@@ -1786,32 +1787,34 @@ int ptb_intersect(ptb_scene *scene, const float *rays, uint64_t n_rays, float *t
             return status;
         }
         LaunchTimer timer(ctx, 0);
-        if(certified) {
+        // scenes far beyond the 126 MB L2 keep the bottom of the traversal stack in shared memory (traverse.cuh)
+        const bool big_scene = scene->info.device_bytes > kBigSceneBytes;
+        auto launch_intersect = [&](auto mode, const uint32_t *index, const uint32_t *index_count, uint32_t *cursor, uint32_t *redo_queue, uint32_t *redo_count) {
+            constexpr int kMode = decltype(mode)::value;
             if(count_visits) {
-                intersectKernel<kTraceCertified, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, order, nullptr, n, d_t + first, d_prim + first,
-                                                                                        counters + kCountFetchClosest, redo, counters + kCountRedo, visits, scene->guard, closest.guarded);
-                intersectKernel<kTraceClosest, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, redo, counters + kCountRedo, n, d_t + first, d_prim + first,
-                                                                                      counters + kCountFetchRedo, nullptr, nullptr, visits, scene->guard, closest.guarded);
+                intersectKernel<kMode, true, 0><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, index, index_count, n, d_t + first, d_prim + first, cursor, redo_queue,
+                                                                                  redo_count, visits, scene->guard, closest.guarded);
+            }
+            else if(big_scene) {
+                intersectKernel<kMode, false, kQuerySmemClosest><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, index, index_count, n, d_t + first, d_prim + first,
+                                                                                                   cursor, redo_queue, redo_count, visits, scene->guard, closest.guarded);
             }
             else {
-                intersectKernel<kTraceCertified, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, order, nullptr, n, d_t + first, d_prim + first,
-                                                                                         counters + kCountFetchClosest, redo, counters + kCountRedo, visits, scene->guard, closest.guarded);
-                intersectKernel<kTraceClosest, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, redo, counters + kCountRedo, n, d_t + first, d_prim + first,
-                                                                                       counters + kCountFetchRedo, nullptr, nullptr, visits, scene->guard, closest.guarded);
+                intersectKernel<kMode, false, 0><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, index, index_count, n, d_t + first, d_prim + first, cursor, redo_queue,
+                                                                                   redo_count, visits, scene->guard, closest.guarded);
             }
+        };
+        if(certified) {
+            launch_intersect(std::integral_constant<int, kTraceCertified>{}, order, nullptr, counters + kCountFetchClosest, redo, counters + kCountRedo);
+            launch_intersect(std::integral_constant<int, kTraceClosest>{}, redo, counters + kCountRedo, counters + kCountFetchRedo, nullptr, nullptr);
             if(stats != nullptr) {
                 PTB_CUDA(cudaMemcpyAsync(ctx->host_counters, counters, kCounterSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
                 PTB_CUDA(cudaStreamSynchronize(ctx->stream));
                 retraced += ctx->host_counters[kCountRedo];
             }
         }
-        else if(count_visits) {
-            intersectKernel<kTraceClosest, true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, order, nullptr, n, d_t + first, d_prim + first,
-                                                                                  counters + kCountFetchClosest, nullptr, nullptr, visits, scene->guard, closest.guarded);
-        }
         else {
-            intersectKernel<kTraceClosest, false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote, chunk_rays, order, nullptr, n, d_t + first, d_prim + first,
-                                                                                   counters + kCountFetchClosest, nullptr, nullptr, visits, scene->guard, closest.guarded);
+            launch_intersect(std::integral_constant<int, kTraceClosest>{}, order, nullptr, counters + kCountFetchClosest, nullptr, nullptr);
         }
     }
     PTB_CUDA(cudaGetLastError());
@@ -1874,12 +1877,16 @@ int ptb_occluded(ptb_scene *scene, const float *rays, uint64_t n_rays, uint8_t *
         }
         LaunchTimer timer(ctx, 0); // the only kernel of this entry: always timed
         if(count_visits) {
-            occludedKernel<true><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, d_rays + 7 * first, order, n, d_out + first, ctx->counters.as<uint32_t>(),
-                                                                    ctx->visits.as<VisitCounters>() + 1);
+            occludedKernel<true, 0><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, d_rays + 7 * first, order, n, d_out + first, ctx->counters.as<uint32_t>(),
+                                                                       ctx->visits.as<VisitCounters>() + 1);
+        }
+        else if(scene->info.device_bytes > kBigSceneBytes) {
+            occludedKernel<false, kQuerySmemAnyHit><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, d_rays + 7 * first, order, n, d_out + first,
+                                                                                      ctx->counters.as<uint32_t>(), ctx->visits.as<VisitCounters>() + 1);
         }
         else {
-            occludedKernel<false><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, d_rays + 7 * first, order, n, d_out + first, ctx->counters.as<uint32_t>(),
-                                                                     ctx->visits.as<VisitCounters>() + 1);
+            occludedKernel<false, 0><<<grid, kBlock, 0, ctx->stream>>>(scene->dev, ctx->vote_shadow, d_rays + 7 * first, order, n, d_out + first, ctx->counters.as<uint32_t>(),
+                                                                        ctx->visits.as<VisitCounters>() + 1);
         }
     }
     PTB_CUDA(cudaGetLastError());

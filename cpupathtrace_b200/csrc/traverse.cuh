@@ -23,15 +23,21 @@ namespace ptb {
 
     constexpr int kStackCapacity = 64; // deferred far siblings only; the host asserts bvh depth <= capacity
 
-    // Optionally the bottom kSmemStackLevels entries of every thread's stack live in shared memory, [level][thread] so
-    // that the 32 lanes of a warp never collide on a bank whatever their individual depths are; deeper entries spill to
-    // local memory.  Round 1's ncu capture had the all-local stack at 1.48 G L1 sectors per 134 M-ray launch -- as many
-    // as all global loads together -- which suggested this; measured, it does not pay (the sectors are L1 hits that the
-    // issue-bound kernel hides, the extra predicated instructions and the smaller L1 are not), so the default is 0.
+    // Optionally the bottom SMEM levels of every thread's stack live in shared memory, [level][thread] so that the 32
+    // lanes of a warp never collide on a bank whatever their individual depths are; deeper entries spill to local
+    // memory.  It is a template parameter of warpTrace because it pays in one regime and not in the other (round 2):
+    //   * wavefront kernels on the bench scene (233 MiB scene served by L2 / L1, kernel bound by instruction issue):
+    //     0 levels 7.77, 8 levels 7.52, 12 levels 7.49 Grays/s closest -- the local stack's sectors are L1 hits that the
+    //     kernel hides, the extra predicated instructions and the smaller L1 are not: PTB_SMEM_STACK = 0;
+    //   * batch queries on the 4 / 16 Mi-triangle soups (2-4 GB scene, kernel bound by memory latency, L1 hit rate 12 %, the
+    //     local stack's 2.3 G sectors per launch go to L2): closest hits with 8 levels 562 -> 611 and 288 -> 306 Mrays/s
+    //     (16 levels: half the speed), any-hit with 16 levels 566 -> 591 Mrays/s: kQuerySmemClosest / kQuerySmemAnyHit.
 #ifndef PTB_SMEM_STACK
-#define PTB_SMEM_STACK 0 // measured in round 2 (bench scene, 128 spp): 0 -> 7.77, 8 -> 7.52, 12 -> 7.49 Grays/s closest: the local stack stays
+#define PTB_SMEM_STACK 0
 #endif
     constexpr int kSmemStackLevels = PTB_SMEM_STACK;
+    constexpr int kQuerySmemClosest = 8;
+    constexpr int kQuerySmemAnyHit = 16;
     constexpr int kTraceBlock = 128; // threads per CTA of every kernel that calls warpTrace (== kBlock in kernels.cuh)
 
     struct RayInv {
@@ -265,18 +271,20 @@ namespace ptb {
     // sub-warp of its own.  `exhausted` is re-agreed at every refill vote (groups can merge again), and a full-mask
     // __syncwarp() at the top of the outer loop invites split groups to merge where the compiler keeps it.
     // one allocation per kernel, however many warpTrace instantiations the kernel contains
+    template<int SMEM>
     PTB_DEV uint2 *sharedStackBase() {
-#if PTB_SMEM_STACK > 0
-        __shared__ uint2 shared_stack[kSmemStackLevels * kTraceBlock];
-        return shared_stack;
-#else
-        return nullptr;
-#endif
+        if constexpr(SMEM > 0) {
+            __shared__ uint2 shared_stack[SMEM * kTraceBlock];
+            return shared_stack;
+        }
+        else {
+            return nullptr;
+        }
     }
 
     // `guard` (certified mode only, may be null = relaxed): rays it flags are committed as uncertain without a walk, and a
     // certified hit closer than guard->tau_safe loses its certificate.
-    template<int MODE, bool COUNT, typename Fetch, typename Commit>
+    template<int MODE, bool COUNT, int SMEM = kSmemStackLevels, typename Fetch, typename Commit>
     PTB_DEV void warpTrace(const DeviceScene &s, VoteParams vote, uint32_t *cursor, uint32_t count, Fetch fetch, Commit commit, VisitCounters *counters,
                            const ptb_guard::CertGuard *guard = nullptr) {
         constexpr bool ANY_HIT = MODE == kTraceAnyHit;
@@ -304,21 +312,21 @@ namespace ptb {
         int32_t node = 0;
         int sp = 0;
         // (node ref, entry distance bits) of deferred far children
-        uint2 local_stack[kStackCapacity - kSmemStackLevels];
-        uint2 *const my_shared_stack = sharedStackBase() + threadIdx.x;
+        uint2 local_stack[kStackCapacity - SMEM];
+        uint2 *const my_shared_stack = sharedStackBase<SMEM>() + threadIdx.x;
         auto stackStore = [&](int at, uint2 e) {
-            if(at < kSmemStackLevels) {
+            if(at < SMEM) {
                 my_shared_stack[at * kTraceBlock] = e;
             }
             else {
-                local_stack[at - kSmemStackLevels] = e;
+                local_stack[at - SMEM] = e;
             }
         };
         auto stackLoad = [&](int at) -> uint2 {
-            if(at < kSmemStackLevels) {
+            if(at < SMEM) {
                 return my_shared_stack[at * kTraceBlock];
             }
-            return local_stack[at - kSmemStackLevels];
+            return local_stack[at - SMEM];
         };
         bool exhausted = count == 0U;
         unsigned long long n_inner = 0;

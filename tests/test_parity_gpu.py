@@ -234,7 +234,7 @@ def test_progress_callbacks_fire_while_the_frame_renders(b200):
 
     spec = scenes.cornell_demo(("obj", scenes.standin_obj(120, 80)))
     scene = spec.build(b200)
-    w, h, spp = 640, 360, 64
+    w, h, spp = 640, 360, 256  # with the 2 Mi-path pool below: ~150 bounce iterations = ~19 batches of 8
     camera = scenes.demo_camera(b200, w, h)
     scene.process_job(camera, w, h, spp, spp, 1e-3)  # warm-up at the same size: the workspace (pool, per-sample buffer) is allocated here, not in the timed call
     for budget_mb in ("0", "64"):  # one pixel group / several pixel groups
