@@ -851,21 +851,32 @@ namespace ptb {
         return v;
     }
 
-    __global__ void rayKeyKernel(DeviceScene scene, const float *__restrict__ rays, uint32_t stride_floats, uint32_t n, uint32_t *__restrict__ keys, uint32_t *__restrict__ ids) {
+    // dir_bits = b: the top 3 b bits of the key are the direction quantised to b bits per axis (b = 1: the octant), the
+    // remaining 30 - 3 b bits the Morton code of the origin at 10 - b bits per axis.  Measured on the soups (round 2,
+    // incoherent rays, 16 Mi / 4 Mi triangles): b = 1 307 / 612 Mrays/s, 2 -> 224 / 517, 3 -> 218 / 469, 4 -> 207 / 450: where
+    // a ray starts matters more than where exactly it heads; the octant stays.
+    __global__ void rayKeyKernel(DeviceScene scene, const float *__restrict__ rays, uint32_t stride_floats, uint32_t n, uint32_t dir_bits, uint32_t *__restrict__ keys,
+                                 uint32_t *__restrict__ ids) {
         const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
         if(k >= n) {
             return;
         }
         const float *p = rays + static_cast<size_t>(stride_floats) * k;
+        const uint32_t cell_bits = 10U - dir_bits;
         uint32_t cell[3];
+        uint32_t heading[3];
         for(int c = 0; c < 3; c++) {
             const float extent = scene.root_hi[c] - scene.root_lo[c];
             float u = extent > 0.0F ? (p[c] - scene.root_lo[c]) / extent : 0.0F;
             u = fminf(fmaxf(u, 0.0F), 0.99999F);
-            cell[c] = static_cast<uint32_t>(u * 512.0F);
+            cell[c] = static_cast<uint32_t>(u * static_cast<float>(1U << cell_bits));
+            // negative directions first within every bit, like the octant of dir_bits = 1
+            const float v = fminf(fmaxf(0.5F - 0.5F * p[3 + c], 0.0F), 0.99999F);
+            heading[c] = static_cast<uint32_t>(v * static_cast<float>(1U << dir_bits));
         }
-        const uint32_t octant = (p[3] < 0.0F ? 1U : 0U) | (p[4] < 0.0F ? 2U : 0U) | (p[5] < 0.0F ? 4U : 0U);
-        keys[k] = (octant << 27) | (spread3(cell[0]) << 2) | (spread3(cell[1]) << 1) | spread3(cell[2]);
+        const uint32_t origin = (spread3(cell[0]) << 2) | (spread3(cell[1]) << 1) | spread3(cell[2]);
+        const uint32_t direction = (spread3(heading[0]) << 2) | (spread3(heading[1]) << 1) | spread3(heading[2]);
+        keys[k] = (direction << (3U * cell_bits)) | origin;
         ids[k] = k;
     }
 

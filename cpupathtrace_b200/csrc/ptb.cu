@@ -134,6 +134,7 @@ struct ptb_context {
     Buffer sort_ids;
     Buffer sort_temp;
     bool sort_rays = true; // PTB_SORT_RAYS=0: trace batches in the caller's order
+    int sort_dir_bits = 1; // bits per axis of the ray direction in the sort key (PTB_SORT_DIR_BITS; 1 = the octant)
     // PTB_STREAMS > 1: large renders are split between `streams` contexts of this device (this one and streams - 1 siblings
     // with their own stream and workspace) that run concurrently, so that the drain phase of one share's persistent trace
     // launch and the launch-bound tail of its bounce loop overlap with the other share's kernels.  Off by default: the gain
@@ -1089,7 +1090,7 @@ namespace {
         }
         uint32_t *keys = ctx->sort_keys.as<uint32_t>();
         uint32_t *ids = ctx->sort_ids.as<uint32_t>();
-        rayKeyKernel<<<(n + 255U) / 256U, 256, 0, ctx->stream>>>(scene->dev, d_rays, stride_floats, n, keys, ids);
+        rayKeyKernel<<<(n + 255U) / 256U, 256, 0, ctx->stream>>>(scene->dev, d_rays, stride_floats, n, static_cast<uint32_t>(ctx->sort_dir_bits), keys, ids);
         PTB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->sort_temp.ptr, temp_bytes, keys, keys + n, ids, ids + n, static_cast<int>(n), 0, 30, ctx->stream));
         *order = ids + n;
         return PTB_OK;
@@ -1205,6 +1206,7 @@ int ptb_context_create(int device, ptb_context **out) {
     ctx->log_iterations = envLong("PTB_LOG_ITERATIONS", 0) != 0;
     ctx->production_math = envLong("PTB_PRODUCTION_MATH", 1) != 0;
     ctx->sort_rays = envLong("PTB_SORT_RAYS", 1) != 0;
+    ctx->sort_dir_bits = static_cast<int>(std::min(4L, std::max(1L, envLong("PTB_SORT_DIR_BITS", 1))));
     ctx->adaptive_rounds = envLong("PTB_ADAPTIVE_ROUNDS", 1) != 0;
     ctx->streams = static_cast<int>(std::min(4L, std::max(1L, envLong("PTB_STREAMS", 1))));
     PTB_CUDA(cudaEventCreate(&ctx->split_start));
