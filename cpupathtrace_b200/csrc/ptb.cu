@@ -153,6 +153,7 @@ struct ptb_context {
     Buffer multi_staging; // ptb_render_multi on the first replica: copies of the other replicas' images when peers cannot map each other
     uint32_t *host_counters = nullptr; // pinned: two batches of bounce iterations (double-buffered)
     cudaEvent_t batch_done[2] = {nullptr, nullptr};
+    bool log_batches = false;      // PTB_LOG_BATCHES=1: one stderr line per batch of bounce iterations (device time since the previous batch ended)
     bool pipelined_batches = true; // PTB_PIPELINED_BATCHES=0: the host waits for every batch before enqueuing the next
     unsigned long long *host_cursor = nullptr; // pinned: the work cursor as of the last batch of bounce iterations
 
@@ -545,6 +546,11 @@ namespace {
                 ahead = true;
             }
             PTB_CUDA(cudaEventSynchronize(ctx->batch_done[oldest]));
+            if(ctx->log_batches) {
+                float since_start = 0.0F;
+                cudaEventElapsedTime(&since_start, ctx->call_start, ctx->batch_done[oldest]);
+                std::fprintf(stderr, "[ptb] batch of %d iterations done %.1f ms after the call started (%u paths entered it)\n", inflight[oldest].launched, since_start, n_cur);
+            }
 
             // walk the oldest batch in launch order
             const Inflight &done = inflight[oldest];
@@ -1181,8 +1187,9 @@ int ptb_context_create(int device, ptb_context **out) {
     }
     PTB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     PTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->host_counters), 2 * kMaxIterationsPerSync * kCounterSlots * sizeof(uint32_t)));
-    PTB_CUDA(cudaEventCreateWithFlags(&ctx->batch_done[0], cudaEventDisableTiming));
-    PTB_CUDA(cudaEventCreateWithFlags(&ctx->batch_done[1], cudaEventDisableTiming));
+    PTB_CUDA(cudaEventCreate(&ctx->batch_done[0]));
+    PTB_CUDA(cudaEventCreate(&ctx->batch_done[1]));
+    ctx->log_batches = envLong("PTB_LOG_BATCHES", 0) != 0;
     ctx->pipelined_batches = envLong("PTB_PIPELINED_BATCHES", 1) != 0;
     PTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->host_cursor), sizeof(unsigned long long)));
     for(auto &pair : ctx->events) {

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 cp cpupathtrace_b200/lib/libptb.so /tmp/libptb_base.so
-for v in base smem8 smem16; do
+for v in "$@"; do
   if [ $v == base ]; then cp /tmp/libptb_base.so cpupathtrace_b200/lib/libptb.so; else cp variants/libptb_$v.so cpupathtrace_b200/lib/libptb.so; fi
   for cfg in "16 incoherent" "4 incoherent" "4 shadow"; do
     set -- $cfg
