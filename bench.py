@@ -14,8 +14,9 @@ One step = one full render of the frame (every pixel, every sample, resolve incl
   value   device-resident: ptb_render writes the image into HBM; tiles are interleaved over the ranks and, for N > 1,
           one image-sized NCCL reduce to rank 0 follows (scene + BVH replicated per GPU).  Timed with CUDA events on
           the launching streams (ptb_render_stats.device_ms_total + torch events around the reduce), max over ranks.
-  e2e     the same render through the reference-facing API with HOST buffers: processJob (N = 1) resp. the C-ABI with
-          a host result (N > 1); the device->host copy of the image is inside the timed region.
+  e2e     the same render through the reference-facing API with HOST buffers: one processJob call per step (the duration
+          of the call itself, device->host copy of the image included).  For N > 1 rank 0 makes that ONE call render on
+          all N GPUs in-library (ptb::RenderControl::devices -> ptb_render_multi) after the other ranks have left.
   roofline  traversal kernels only: algorithmic bytes per ray (64 B per inner record fetched + 48 B per primitive
           fetched + 48 B ray/hit record, fetch counts measured by a counting pass of the same traversal) x rays traced
           / summed CUDA-event time of the trace kernels, against the measured HBM copy bandwidth.
