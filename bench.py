@@ -114,7 +114,7 @@ def config_dict(args, label, n_gpus):
         "max_depth": args.max_depth,
         "scene": label,
         "parallelism": f"interleaved 32x32 tiles over {n_gpus} GPU(s), scene+BVH replicated, one NCCL image reduce" if n_gpus > 1 else "1 GPU",
-        "l2": "working set (path pool of up to 128 Mi paths ~30 GB + per-sample buffer, BVH ~230 MB) exceeds the 126 MB L2; a 512 MB buffer is also written between steps",
+        "l2": "working set (path pool of up to 256 Mi paths ~63 GB + per-sample buffer, BVH ~230 MB) exceeds the 126 MB L2; a 512 MB buffer is also written between steps",
     }
 
 

@@ -253,16 +253,17 @@ namespace {
 
     // Paths kept in flight.  The trace kernels are persistent and end every launch with a drain phase in which each warp
     // finishes its last rays at low lane occupancy; its length does not depend on the queue length, so the pool is made
-    // as large as memory comfortably allows (measured on the bench scene at 256 spp: 4 Mi paths 321, 32 Mi 438,
-    // 128 Mi 469 Msamples/s).  Default: 128 Mi paths (~30 GB with two shadow slots), at most a fifth of the HBM at hand.
+    // as large as memory comfortably allows (measured on the bench scene at 256 spp, round 1: 4 Mi paths 321, 32 Mi 438,
+    // 128 Mi 469 Msamples/s; round 2: 128 Mi 769, 160 Mi 756, 192 Mi 751, 256 Mi 745 ms per frame).  Default: 256 Mi paths
+    // (~63 GB with two shadow slots), at most three eighths of the HBM at hand.
     uint64_t poolLimit(const ptb_context *ctx, uint32_t shadow_stride) {
         const long forced = envLong("PTB_POOL_PATHS", 0);
         if(forced > 0) {
             return static_cast<uint64_t>(forced);
         }
         const uint64_t bytes_per_path = 112ULL + 48ULL * shadow_stride + 4ULL * (3ULL + shadow_stride);
-        const uint64_t by_memory = plannableBytes(ctx) / 5ULL / bytes_per_path;
-        return std::max<uint64_t>(1ULL << 16, std::min<uint64_t>(1ULL << 27, by_memory));
+        const uint64_t by_memory = plannableBytes(ctx) * 3ULL / 8ULL / static_cast<uint64_t>(std::max(ctx->budget_divisor, 1)) / bytes_per_path;
+        return std::max<uint64_t>(1ULL << 16, std::min<uint64_t>(1ULL << 28, by_memory));
     }
 
     // Per-sample buffer budget of ptb_render (16 B per pixel-sample): PTB_SAMPLE_BUFFER_MB, else 40 % of the HBM at hand.

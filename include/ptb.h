@@ -22,7 +22,7 @@
  *
  * Environment (read when a context is created / a scene is built / a frame is rendered; none changes a result)
  *   PTB_DEVICE, LOCAL_RANK        device of ptb_context_create(-1)
- *   PTB_POOL_PATHS                paths in flight (default: 128 Mi, at most a fifth of the free HBM, at most half of a call's samples)
+ *   PTB_POOL_PATHS                paths in flight (default: 256 Mi, at most 3/8 of the free HBM, at most half of a call's samples)
  *   PTB_SAMPLE_BUFFER_MB          per-sample buffer budget of ptb_render (default: 40 % of the free HBM)
  *   PTB_GPU_BVH=1                 build the query hierarchy on the GPU (PTB_BVH_REFERENCE_GPU_QUERY_TREE); PTB_OCCLUSION_BVH=0: none
  *   PTB_BUILD_THREADS             host threads of the BVH builders
