@@ -2724,6 +2724,10 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
         ctx->siblings[static_cast<size_t>(k)]->budget_divisor = parts;
     }
     ctx->budget_divisor = parts;
+    struct RestoreBudget { // every way out of this call gives the context its whole budget back
+        ptb_context *context;
+        ~RestoreBudget() { context->budget_divisor = 1; }
+    } restore_budget{ctx};
 
     const bool device_io = (opts->flags & PTB_FLAG_DEVICE_IO) != 0U;
     const size_t image_bytes = static_cast<size_t>(w) * h * sizeof(float4);
@@ -2732,7 +2736,6 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
         std::lock_guard<std::mutex> lock(ctx->mutex);
         if(!device_io) {
             if((status = ctx->split_image.reserve(image_bytes)) != PTB_OK) {
-                ctx->budget_divisor = 1;
                 return status;
             }
             d_out = ctx->split_image.as<float4>();
@@ -2783,7 +2786,6 @@ int ptb_render_with_progress(ptb_scene *scene, const ptb_camera *camera, const p
             t.join();
         }
     }
-    ctx->budget_divisor = 1;
     for(int k = 0; k < parts; k++) {
         if(statuses[static_cast<size_t>(k)] != PTB_OK) {
             return fail(statuses[static_cast<size_t>(k)], "ptb_render: share " + std::to_string(k) + ": " + errors[static_cast<size_t>(k)]);
