@@ -9,6 +9,7 @@ import numpy as np
 
 from . import lib_path
 
+PTB_ABI_VERSION = 2  # include/ptb.h: the struct layouts mirrored below belong to this version
 PTB_OK = 0
 PTB_ERR_INVALID_ARGUMENT = 1
 PTB_ERR_NO_DEVICE = 2

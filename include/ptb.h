@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 1
+#define PTB_ABI_VERSION 2 /* 2: ptb_scene_info and ptb_render_stats grew at the end (round 2); compare with ptb_abi_version() */
 
 typedef enum ptb_status {
     PTB_OK = 0,

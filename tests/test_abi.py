@@ -55,7 +55,7 @@ def test_host_libraries_load_and_identify():
 
     b200 = pth.load_b200()
     assert b200.name == "b200"
-    assert capi.load().ptb_abi_version() == 1
+    assert capi.load().ptb_abi_version() == capi.PTB_ABI_VERSION == 2
 
 
 def test_camera_init_is_host_side_and_matches_reference(ref):
